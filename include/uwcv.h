@@ -1,0 +1,132 @@
+/*
+ * uwcv.h -- C ABI of libuwcv.so, the B200 (sm_100a) implementation of the
+ * post-inference hot path of Deam0on/uw-com-vision.
+ *
+ * The reference has no plugin / FFI API of its own (it is four Python scripts); the
+ * boundary this library replaces is the Detectron2 data contract its scripts consume
+ * (SURVEY.md section 8(b)).  Each entry point names the reference interface it stands
+ * in for; INTEGRATION.md shows the ctypes binding a maintainer adds on the reference
+ * side.
+ *
+ * Conventions
+ *   - every function returns 0 on success or a negative uwcv error code
+ *     (uwcv_strerror); no exception crosses the ABI;
+ *   - all array arguments are DEVICE pointers on the current CUDA device, 16-byte
+ *     aligned, owned by the caller (workspace included); unless stated otherwise the
+ *     library never allocates, frees or synchronises: it only enqueues work on
+ *     `stream` (a cudaStream_t passed as void*);
+ *   - re-entrant, no global state: safe from several host threads on different
+ *     streams / devices.
+ */
+#ifndef UWCV_H_
+#define UWCV_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define UWCV_MASK_SIDE 28   /* mask head output side (Detectron2 ROI_MASK_HEAD.POOLER_RESOLUTION*2) */
+#define UWCV_NUM_INT   20   /* int64 columns of a measurement row   */
+#define UWCV_NUM_FLOAT 30   /* float64 columns of a measurement row */
+
+#define UWCV_OK            0
+#define UWCV_E_NULL       -1  /* required pointer is NULL                         */
+#define UWCV_E_SHAPE      -2  /* negative / zero / inconsistent sizes             */
+#define UWCV_E_ALIGN      -3  /* pointer not 16-byte aligned                      */
+#define UWCV_E_THRESH     -4  /* mask threshold must be > 0       */
+#define UWCV_E_WORKSPACE  -5  /* workspace smaller than uwcv_workspace_bytes(N,0) */
+#define UWCV_E_LAUNCH     -6  /* CUDA reported a launch error                     */
+#define UWCV_E_CAPACITY   -7  /* (device status) tile words exceed the workspace  */
+#define UWCV_E_TOO_LARGE  -8  /* image side > 32768 or candidate count too large  */
+
+/* Library version, major * 10000 + minor * 100 + patch. */
+int uwcv_version(void);
+
+/* Static string for an error code. */
+const char* uwcv_strerror(int code);
+
+/* Words (uint32) per row of a full-frame bit-plane for image width W:
+ * ceil(W / 32) rounded up to a multiple of 4 (16-byte rows). */
+int uwcv_plane_row_words(int W);
+
+/* Bytes of workspace uwcv_paste_measure needs for N instances whose tiles hold
+ * `tile_words` 32-pixel words in total (20 bytes per word + descriptors).  The exact
+ * word count of a call is reported back in status[1]; a caller that does not know it
+ * passes a generous value and checks status[0]. */
+size_t uwcv_workspace_bytes(int64_t N, int64_t tile_words);
+
+/*
+ * uwcv_paste_measure -- fused paste + threshold + bit-pack + per-instance measurement.
+ *
+ * Stands in for (reference file:line):
+ *   detectron2 ROIMasks.to_bitmasks / layers.mask_ops.paste_masks_in_image reached from
+ *     predictor(im) at nn_inference.py:372 (via detector_postprocess),
+ *   pred_masks.to("cpu").numpy() at nn_inference.py:376,
+ *   and the measurement block nn_inference.py:405-459 applied per instance.
+ *
+ *   masks      [N, 28, 28] float32 mask probabilities (after sigmoid, predicted class)
+ *   boxes      [N, 4] float32 XYXY in OUTPUT-image pixels, already scaled / clipped /
+ *              non-empty-filtered exactly as detector_postprocess does (keep those
+ *              three torch ops on the caller side so the floats are bit-identical)
+ *   image_idx  [N] int32 or NULL (0)      -> row column image_idx
+ *   inst_idx   [N] int32 or NULL (0..N-1) -> row column inst_idx
+ *   classes    [N] int64 or NULL (0)      -> row column class_id
+ *   scores     [N] float32 or NULL (0)    -> row column score
+ *   H, W       output image size (all instances of a call share it); <= 32768
+ *   thr        mask threshold, > 0 (Detectron2 default 0.5; compared as out >= thr)
+ *   pixels_per_metric   nn_inference.py:409 (0.85)
+ *   bitplanes  NULL, or [N, H, uwcv_plane_row_words(W)] uint32: Detectron2-literal
+ *              full-frame masks, 1 bit per pixel (bit b of word w = pixel x = 32 w + b)
+ *   rows_i     [N, UWCV_NUM_INT] int64 out     (column order: SURVEY.md 8(b))
+ *   rows_f     [N, UWCV_NUM_FLOAT] float64 out
+ *   workspace / ws_bytes   >= uwcv_workspace_bytes(N, tile_words)
+ *   status     [4] int64 out (device): [0] 0 or UWCV_E_CAPACITY, [1] tile words needed,
+ *              [2] tile rows needed, [3] reserved.  On E_CAPACITY no row is written.
+ */
+int uwcv_paste_measure(const float* masks, const float* boxes, const int32_t* image_idx,
+                       const int32_t* inst_idx, const int64_t* classes, const float* scores,
+                       int64_t N, int H, int W, float thr, double pixels_per_metric,
+                       uint32_t* bitplanes, int64_t* rows_i, double* rows_f,
+                       void* workspace, size_t ws_bytes, int64_t* status, void* stream);
+
+/*
+ * uwcv_unpack_planes -- expand bit-planes into the Detectron2-literal N x H x W bool
+ * tensor (one byte per pixel), for callers that read pred_masks as such
+ * (nn_inference.py:326, :376).
+ */
+int uwcv_unpack_planes(const uint32_t* bitplanes, int64_t N, int H, int W, uint8_t* out,
+                       void* stream);
+
+/* Bytes of workspace for uwcv_nms_filter; image_off is a HOST array [B + 1]. */
+size_t uwcv_nms_workspace_bytes(const int64_t* image_off, int B);
+
+/*
+ * uwcv_nms_filter -- batched score filter + per-class NMS + top-k.
+ *
+ * Stands in for detectron2 fast_rcnn_inference_single_image (score > thresh,
+ * batched_nms, keep[:topk]) whose thresholds the reference sets at
+ * nn_inference.py:226, with torchvision _batched_nms_vanilla semantics.
+ *
+ *   boxes      [R, 4] float32 XYXY (already clipped), candidates of image b are rows
+ *              image_off[b] .. image_off[b+1]-1
+ *   scores     [R] float32,  classes [R] int64
+ *   image_off  HOST pointer, [B + 1] int64, image_off[0] = 0, non-decreasing
+ *   score_thr  keep candidates with score > score_thr (float32 compare)
+ *   iou_thr    suppress when (double)iou > iou_thr
+ *   topk       per image, < 0 = unlimited
+ *   keep       [R] int64 out: for image b, keep[image_off[b] + r] for r < keep_count[b]
+ *              are candidate row indices in score-descending order
+ *   keep_count [B] int32 out
+ */
+int uwcv_nms_filter(const float* boxes, const float* scores, const int64_t* classes,
+                    const int64_t* image_off, int B, float score_thr, double iou_thr, int topk,
+                    int64_t* keep, int32_t* keep_count, void* workspace, size_t ws_bytes,
+                    void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif  /* UWCV_H_ */

@@ -1,0 +1,484 @@
+// Kernel 3: external-border trace, contour descriptors, min-area rectangle / Feret,
+// and the floating-point columns of the measurement row.  One thread per instance.
+//
+// Replaces nn_inference.py:405-459 (cvtColor + cv2.findContours(RETR_EXTERNAL,
+// CHAIN_APPROX_SIMPLE) + contourArea / arcLength / minAreaRect / boxPoints + the
+// descriptor block) applied to each instance mask, and cv2.moments' central moments.
+//
+// The arithmetic mirrors the library code the reference runs (pinned bit-for-bit
+// against OpenCV 4.13 by the oracle tests):
+//   * border following: Suzuki-Abe as in OpenCV's contour scanner -- raster scan, an
+//     unvisited foreground pixel with background on its left starts an outer border
+//     unless the last marked pixel to its left on the row carries a positive mark;
+//     first move counter-clockwise on screen; a pixel gets the negative mark when its
+//     right neighbour was examined and found empty.
+//   * contourArea: shoelace over the steps (exact integers).
+//   * arcLength: float32 sqrt per CHAIN_APPROX_SIMPLE segment, summed in double.
+//   * minAreaRect: strict convex hull (clockwise on screen, the component's raster-first
+//     pixel last) -> float32 rotating calipers (exact cross-product side selection,
+//     "area <= minarea" keeps the last minimum) -> centre / sides / angle in [-90, 0).
+//   * boxPoints -> int truncation -> imutils order_points -> midpoints -> dA, dB -> the
+//     nine descriptors of nn_inference.py:434-449.
+// Compiled with -fmad=false: no contraction anywhere in this file.
+#include "uwcv_common.cuh"
+
+namespace uwcv {
+
+struct TileView {
+  const uint32_t* M;
+  uint32_t* V;
+  uint32_t* G;
+  int tw, th;
+};
+
+__device__ __forceinline__ bool fg(const TileView& t, int x, int y) {
+  if ((unsigned)y >= (unsigned)t.th || (unsigned)x >= (unsigned)(t.tw * 32)) return false;
+  return (__ldg(t.M + y * t.tw + (x >> 5)) >> (x & 31)) & 1u;
+}
+// direction s: 0 = east, then counter-clockwise on a y-up plane (1 = x+1, y-1 on screen)
+__device__ __forceinline__ int dir_dx(int s) { return (int)((0x901Au >> (2 * s)) & 3u) - 1; }
+__device__ __forceinline__ int dir_dy(int s) { return (int)((0xA901u >> (2 * s)) & 3u) - 1; }
+
+struct ContourStat {
+  long long area2;    // signed twice-area (shoelace)
+  double perim;
+  int npts;
+  int ymax;           // last tile row touched
+};
+
+// Follow the outer border that starts at the raster-first pixel (x0, y0) of a component.
+// kMark: pass 1 (write V / G marks).  !kMark: pass 2 (record per-row extremes).
+template <bool kMark>
+__device__ void follow_border(const TileView& t, int x0, int y0, ContourStat& st,
+                              uint32_t* ext_l, uint32_t* ext_r) {
+  st.area2 = 0; st.perim = 0.0; st.npts = 0; st.ymax = y0;
+  int s = 4;
+  const int s_stop = 4;
+  do {
+    s = (s - 1) & 7;
+  } while (!fg(t, x0 + dir_dx(s), y0 + dir_dy(s)) && s != s_stop);
+  if (s == s_stop) {                          // isolated pixel
+    if (kMark) {
+      const int o = y0 * t.tw + (x0 >> 5);
+      const uint32_t b = 1u << (x0 & 31);
+      t.V[o] |= b; t.G[o] |= b;
+    } else {
+      ext_l[y0] = min(ext_l[y0], (uint32_t)x0);
+      ext_r[y0] = max(ext_r[y0], (uint32_t)x0);
+    }
+    st.npts = 1;
+    return;
+  }
+  const int x1 = x0 + dir_dx(s), y1 = y0 + dir_dy(s);
+  int x3 = x0, y3 = y0;
+  int prev_s = s ^ 4;
+  int fvx = 0, fvy = 0, lvx = 0, lvy = 0;     // first / last emitted vertex
+  for (;;) {
+    const int s_end = s;
+    int x4, y4;
+    do {
+      ++s;
+      x4 = x3 + dir_dx(s & 7);
+      y4 = y3 + dir_dy(s & 7);
+    } while (!fg(t, x4, y4));
+    s &= 7;
+    if (kMark) {
+      const int o = y3 * t.tw + (x3 >> 5);
+      const uint32_t b = 1u << (x3 & 31);
+      if ((unsigned)(s - 1) < (unsigned)s_end) { t.V[o] |= b; t.G[o] |= b; }
+      else t.V[o] |= b;
+    } else {
+      ext_l[y3] = min(ext_l[y3], (uint32_t)x3);
+      ext_r[y3] = max(ext_r[y3], (uint32_t)x3);
+    }
+    if (s != prev_s) {                        // CHAIN_APPROX_SIMPLE vertex
+      if (st.npts == 0) { fvx = x3; fvy = y3; }
+      else {
+        const float dx = (float)(x3 - lvx), dy = (float)(y3 - lvy);
+        st.perim += (double)sqrtf(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)));
+      }
+      lvx = x3; lvy = y3;
+      ++st.npts;
+      prev_s = s;
+    }
+    st.area2 += (long long)x3 * y4 - (long long)y3 * x4;
+    st.ymax = max(st.ymax, y3);
+    if (x4 == x0 && y4 == y0 && x3 == x1 && y3 == y1) break;
+    x3 = x4; y3 = y4;
+    s = (s + 4) & 7;
+  }
+  if (st.npts >= 2) {
+    const float dx = (float)(fvx - lvx), dy = (float)(fvy - lvy);
+    st.perim += (double)sqrtf(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)));
+  }
+}
+
+// sign of the last marked pixel left of (x, y): 0 none, +1 positive mark, -1 negative mark
+__device__ int last_mark_left(const TileView& t, int x, int y) {
+  int wi = x >> 5;
+  uint32_t keep = (x & 31) ? ((1u << (x & 31)) - 1u) : 0u;
+  const int row = y * t.tw;
+  for (; wi >= 0; --wi) {
+    const uint32_t v = t.V[row + wi] & keep;
+    if (v) {
+      const int b = 31 - __clz(v);
+      return ((t.G[row + wi] >> b) & 1u) ? -1 : +1;
+    }
+    keep = 0xffffffffu;
+  }
+  return 0;
+}
+
+__device__ __forceinline__ uint32_t pk(int x, int y) { return (uint32_t)x | ((uint32_t)y << 16); }
+__device__ __forceinline__ int pkx(uint32_t p) { return (int)(p & 0xffffu); }
+__device__ __forceinline__ int pky(uint32_t p) { return (int)(p >> 16); }
+__device__ __forceinline__ long long cross3(uint32_t a, uint32_t b, uint32_t c) {
+  return (long long)(pkx(b) - pkx(a)) * (pky(c) - pky(b)) -
+         (long long)(pky(b) - pky(a)) * (pkx(c) - pkx(b));
+}
+
+struct Hull {
+  const uint32_t* R; int nr; int skip_r0;   // right chain, top -> bottom
+  const uint32_t* L; int nl; int skip_lb;   // left chain,  top -> bottom (walked backwards)
+  int n;
+  int ox, oy;                               // tile origin in frame pixels
+  bool swap2;                               // n == 2: (x, y)-larger point first
+  __device__ __forceinline__ uint32_t raw(int i) const {
+    if (n == 2 && swap2) i ^= 1;
+    const int nrr = nr - skip_r0;
+    if (i < nrr) return R[i + skip_r0];
+    return L[nl - 1 - skip_lb - (i - nrr)];
+  }
+  __device__ __forceinline__ float x(int i) const { return (float)(pkx(raw(i)) + ox); }
+  __device__ __forceinline__ float y(int i) const { return (float)(pky(raw(i)) + oy); }
+};
+
+struct Rect { float cx, cy, w, h, angle; };
+
+// OpenCV rotcalipers.cpp::rotatingCalipers(CALIPERS_MINAREARECT) + minAreaRect epilogue
+__device__ Rect min_area_rect(const Hull& hl) {
+  const double kPi = 3.1415926535897932384626433832795;
+  Rect r;
+  const int n = hl.n;
+  float o0x = 0, o0y = 0, o1x = 0, o1y = 0, o2x = 0, o2y = 0;
+  float w = 0.f, h = 0.f;
+  double ang = 0.0;
+  if (n > 2) {
+    int left = 0, bottom = 0, right = 0, top = 0;
+    float left_x, right_x, top_y, bottom_y;
+    left_x = right_x = hl.x(0);
+    top_y = bottom_y = hl.y(0);
+    for (int i = 0; i < n; ++i) {
+      const float px = hl.x(i), py = hl.y(i);
+      if (px < left_x) { left_x = px; left = i; }
+      if (px > right_x) { right_x = px; right = i; }
+      if (py > top_y) { top_y = py; top = i; }
+      if (py < bottom_y) { bottom_y = py; bottom = i; }
+    }
+    auto vx = [&](int i) { const int j = (i + 1 == n) ? 0 : i + 1; return hl.x(j) - hl.x(i); };
+    auto vy = [&](int i) { const int j = (i + 1 == n) ? 0 : i + 1; return hl.y(j) - hl.y(i); };
+    float orientation = 0.f;
+    {
+      double ax = vx(n - 1), ay = vy(n - 1);
+      for (int i = 0; i < n; ++i) {
+        const double bx = vx(i), by = vy(i);
+        const double convexity = ax * by - ay * bx;
+        if (convexity != 0) { orientation = convexity > 0 ? 1.f : -1.f; break; }
+        ax = bx; ay = by;
+      }
+    }
+    float base_a = orientation, base_b = 0.f;
+    int seq[4] = {bottom, right, top, left};
+    float minarea = 3.402823466e+38f;
+    int b_left = 0, b_bottom = 0;
+    float b_a = 0, b_b = 0, b_w = 0, b_h = 0;
+    for (int k = 0; k < n; ++k) {
+      // edge of each caliper side rotated into side 0's frame
+      float rvx[4], rvy[4];
+      rvx[0] = vx(seq[0]);  rvy[0] = vy(seq[0]);
+      rvx[1] = vy(seq[1]);  rvy[1] = -vx(seq[1]);
+      rvx[2] = -vx(seq[2]); rvy[2] = -vy(seq[2]);
+      rvx[3] = -vy(seq[3]); rvy[3] = vx(seq[3]);
+      int main_el = 0;
+#pragma unroll
+      for (int i = 1; i < 4; ++i) {
+        // firstVecIsRight(rv[i], rv[main]): rotate90CW(rv[i]) . rv[main] < 0
+        const float t0 = rvy[i], t1 = -rvx[i];
+        if (__fadd_rn(__fmul_rn(t0, rvx[main_el]), __fmul_rn(t1, rvy[main_el])) < 0.f) main_el = i;
+      }
+      {
+        const int pindex = seq[main_el];
+        const double dx = vx(pindex), dy = vy(pindex);
+        const float inv_len = (float)(1.0 / sqrt(dx * dx + dy * dy));
+        const float lead_x = __fmul_rn(vx(pindex), inv_len);
+        const float lead_y = __fmul_rn(vy(pindex), inv_len);
+        switch (main_el) {
+          case 0: base_a = lead_x;  base_b = lead_y;  break;
+          case 1: base_a = lead_y;  base_b = -lead_x; break;
+          case 2: base_a = -lead_x; base_b = -lead_y; break;
+          default: base_a = -lead_y; base_b = lead_x; break;
+        }
+      }
+      seq[main_el] += 1;
+      if (seq[main_el] == n) seq[main_el] = 0;
+      float dx = hl.x(seq[1]) - hl.x(seq[3]);
+      float dy = hl.y(seq[1]) - hl.y(seq[3]);
+      const float width = __fadd_rn(__fmul_rn(dx, base_a), __fmul_rn(dy, base_b));
+      dx = hl.x(seq[2]) - hl.x(seq[0]);
+      dy = hl.y(seq[2]) - hl.y(seq[0]);
+      const float height = __fadd_rn(__fmul_rn(-dx, base_b), __fmul_rn(dy, base_a));
+      const float area = __fmul_rn(width, height);
+      if (area <= minarea) {
+        minarea = area;
+        b_left = seq[3]; b_a = base_a; b_w = width; b_b = base_b; b_h = height; b_bottom = seq[0];
+      }
+    }
+    const float A1 = b_a, B1 = b_b, A2 = -b_b, B2 = b_a;
+    const float C1 = __fadd_rn(__fmul_rn(A1, hl.x(b_left)), __fmul_rn(hl.y(b_left), B1));
+    const float C2 = __fadd_rn(__fmul_rn(A2, hl.x(b_bottom)), __fmul_rn(hl.y(b_bottom), B2));
+    const float idet = __fdiv_rn(1.f, __fsub_rn(__fmul_rn(A1, B2), __fmul_rn(A2, B1)));
+    o0x = __fmul_rn(__fsub_rn(__fmul_rn(C1, B2), __fmul_rn(C2, B1)), idet);
+    o0y = __fmul_rn(__fsub_rn(__fmul_rn(A1, C2), __fmul_rn(A2, C1)), idet);
+    o1x = __fmul_rn(A1, b_w); o1y = __fmul_rn(B1, b_w);
+    o2x = __fmul_rn(A2, b_h); o2y = __fmul_rn(B2, b_h);
+    r.cx = __fadd_rn(o0x, __fmul_rn(__fadd_rn(o1x, o2x), 0.5f));
+    r.cy = __fadd_rn(o0y, __fmul_rn(__fadd_rn(o1y, o2y), 0.5f));
+    w = (float)sqrt((double)o1x * o1x + (double)o1y * o1y);
+    h = (float)sqrt((double)o2x * o2x + (double)o2y * o2y);
+    if (o1y == 0.f) ang = o1x >= 0.f ? 0.0 : kPi;
+    else if (o1x == 0.f) ang = o1y > 0.f ? kPi * 0.5 : -kPi * 0.5;
+    else ang = atan2((double)o1y, (double)o1x);
+  } else if (n == 2) {
+    r.cx = __fmul_rn(__fadd_rn(hl.x(0), hl.x(1)), 0.5f);
+    r.cy = __fmul_rn(__fadd_rn(hl.y(0), hl.y(1)), 0.5f);
+    const double dx = hl.x(1) - hl.x(0), dy = hl.y(1) - hl.y(0);
+    w = (float)sqrt(dx * dx + dy * dy);
+    h = 0.f;
+    if (dy == 0.0) ang = dx >= 0.0 ? 0.0 : kPi;
+    else if (dx == 0.0) ang = dy > 0.0 ? kPi * 0.5 : -kPi * 0.5;
+    else ang = atan2(dy, dx);
+  } else {
+    r.cx = n == 1 ? hl.x(0) : 0.f;
+    r.cy = n == 1 ? hl.y(0) : 0.f;
+  }
+  ang = ang * 180 / kPi;
+  while (ang >= 0.0) { ang -= 90.0; const float t = w; w = h; h = t; }
+  while (ang < -90.0) { ang += 90.0; const float t = w; w = h; h = t; }
+  r.w = w; r.h = h; r.angle = (float)ang;
+  return r;
+}
+
+// cv2.boxPoints -> np.array(dtype="int") -> imutils order_points -> midpoints -> (dA, dB)
+__device__ void feret_extents(const Rect& r, float& dA, float& dB) {
+  const double kPi = 3.1415926535897932384626433832795;
+  const double ang = (double)r.angle * kPi / 180.;
+  const float b = __fmul_rn((float)cos(ang), 0.5f);
+  const float a = __fmul_rn((float)sin(ang), 0.5f);
+  float px[4], py[4];
+  px[0] = __fsub_rn(__fsub_rn(r.cx, __fmul_rn(a, r.h)), __fmul_rn(b, r.w));
+  py[0] = __fsub_rn(__fadd_rn(r.cy, __fmul_rn(b, r.h)), __fmul_rn(a, r.w));
+  px[1] = __fsub_rn(__fadd_rn(r.cx, __fmul_rn(a, r.h)), __fmul_rn(b, r.w));
+  py[1] = __fsub_rn(__fsub_rn(r.cy, __fmul_rn(b, r.h)), __fmul_rn(a, r.w));
+  px[2] = __fsub_rn(__fmul_rn(2.f, r.cx), px[0]);
+  py[2] = __fsub_rn(__fmul_rn(2.f, r.cy), py[0]);
+  px[3] = __fsub_rn(__fmul_rn(2.f, r.cx), px[1]);
+  py[3] = __fsub_rn(__fmul_rn(2.f, r.cy), py[1]);
+  int X[4], Y[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { X[i] = (int)px[i]; Y[i] = (int)py[i]; }   // truncation toward zero
+  // order_points: stable sort by x (NumPy argsort of 4 elements is an insertion sort)
+  int idx[4] = {0, 1, 2, 3};
+#pragma unroll
+  for (int i = 1; i < 4; ++i) {
+#pragma unroll
+    for (int j = i; j > 0; --j) {
+      if (X[idx[j]] < X[idx[j - 1]]) { const int t = idx[j]; idx[j] = idx[j - 1]; idx[j - 1] = t; }
+    }
+  }
+  int l0 = idx[0], l1 = idx[1], r0 = idx[2], r1 = idx[3];
+  if (Y[l1] < Y[l0]) { const int t = l0; l0 = l1; l1 = t; }      // (tl, bl) by y, stable
+  const int tl = l0, bl = l1;
+  const long long d0 = (long long)(X[r0] - X[tl]) * (X[r0] - X[tl]) +
+                       (long long)(Y[r0] - Y[tl]) * (Y[r0] - Y[tl]);
+  const long long d1 = (long long)(X[r1] - X[tl]) * (X[r1] - X[tl]) +
+                       (long long)(Y[r1] - Y[tl]) * (Y[r1] - Y[tl]);
+  // argsort(D)[::-1]: ascending stable then reversed -> (br, tr)
+  int br, tr;
+  if (d1 < d0) { br = r0; tr = r1; } else { br = r1; tr = r0; }
+  // midpoints are float32 half-integers (order_points returns float32, exact); scipy's
+  // dist.euclidean keeps float32 and reduces with snrm2 = sqrtf(fl(dx*dx) + fl(dy*dy))
+  // (pinned by probe against scipy 1.18 / OpenBLAS in this image).
+  const float ax = 0.5f * (float)((X[tl] + X[tr]) - (X[bl] + X[br]));
+  const float ay = 0.5f * (float)((Y[tl] + Y[tr]) - (Y[bl] + Y[br]));
+  const float bx = 0.5f * (float)((X[tl] + X[bl]) - (X[tr] + X[br]));
+  const float by = 0.5f * (float)((Y[tl] + Y[bl]) - (Y[tr] + Y[br]));
+  dA = sqrtf(__fadd_rn(__fmul_rn(ax, ax), __fmul_rn(ay, ay)));
+  dB = sqrtf(__fadd_rn(__fmul_rn(bx, bx), __fmul_rn(by, by)));
+}
+
+constexpr int kContourThreads = 64;
+
+__global__ void __launch_bounds__(kContourThreads)
+contour_measure_kernel(int64_t n, const float* __restrict__ scores, double pixels_per_metric,
+                       int64_t* __restrict__ rows_i, double* __restrict__ rows_f, Workspace ws,
+                       const int64_t* __restrict__ status) {
+  if (status[0] != 0) return;
+  const int64_t inst = (int64_t)blockIdx.x * kContourThreads + threadIdx.x;
+  if (inst >= n) return;
+  const double kPi = 3.141592653589793;
+  const TileDesc d = ws.desc[inst];
+  int64_t* ri = rows_i + inst * kNumInt;
+  double* rf = rows_f + inst * kNumFloat;
+  for (int k = 0; k < kNumFloat; ++k) rf[k] = 0.0;
+  rf[F_SCORE] = scores ? (double)scores[inst] : 0.0;
+  const long long m00i = ri[I_AREA];
+  if (m00i <= 0 || d.th == 0) return;
+
+  // ---- central moments (OpenCV completeMomentState) ---------------------------------
+  {
+    const double m00 = (double)m00i, m10 = (double)ri[I_M10], m01 = (double)ri[I_M01];
+    const double m20 = (double)ri[I_M20], m11 = (double)ri[I_M11], m02 = (double)ri[I_M02];
+    const double m30 = (double)ri[I_M30], m21 = (double)ri[I_M21], m12 = (double)ri[I_M12];
+    const double m03 = (double)ri[I_M03];
+    const double inv_m00 = 1.0 / m00;
+    const double cx = m10 * inv_m00, cy = m01 * inv_m00;
+    const double mu20 = m20 - m10 * cx;
+    double mu11 = m11 - m10 * cy;
+    const double mu02 = m02 - m01 * cy;
+    rf[F_CX] = cx; rf[F_CY] = cy;
+    rf[F_MU20] = mu20; rf[F_MU11] = mu11; rf[F_MU02] = mu02;
+    rf[F_MU30] = m30 - cx * (3 * mu20 + cx * m10);
+    const double a = mu20 / m00, b = mu11 / m00, c = mu02 / m00;
+    mu11 += mu11;
+    rf[F_MU21] = m21 - cx * (mu11 + cx * m01) - cy * mu20;
+    rf[F_MU12] = m12 - cy * (mu11 + cy * m10) - cx * mu02;
+    rf[F_MU03] = m03 - cy * (3 * mu02 + cy * m01);
+    rf[F_EQD] = sqrt(4.0 * m00 / kPi);
+    // moment ellipse (the build's definition)
+    const double common = sqrt(((a - c) * 0.5) * ((a - c) * 0.5) + b * b);
+    const double lp = (a + c) * 0.5 + common, lm = (a + c) * 0.5 - common;
+    rf[F_ELL_MAJOR] = 4.0 * sqrt(lp > 0.0 ? lp : 0.0);
+    rf[F_ELL_MINOR] = 4.0 * sqrt(lm > 0.0 ? lm : 0.0);
+    rf[F_ELL_THETA] = 0.5 * atan2(2.0 * b, a - c);
+  }
+
+  // ---- pass 1: raster scan + border following, keep the largest contour -------------
+  TileView t;
+  t.M = ws.M + d.word_off; t.V = ws.V + d.word_off; t.G = ws.G + d.word_off;
+  t.tw = d.tw; t.th = d.th;
+  int ncont = 0;
+  long long best_a2 = -1;
+  int best_x = 0, best_y = 0, best_npts = 0, best_ymax = 0;
+  double best_perim = 0.0;
+  // rows outside the pixel bbox cannot hold a start pixel
+  const int ylo = (int)ri[I_BY0] - d.y0, yhi = (int)ri[I_BY1] - d.y0;
+  for (int y = ylo; y <= yhi; ++y) {
+    const int row = y * t.tw;
+    uint32_t carry = 0;
+    for (int wi = 0; wi < t.tw; ++wi) {
+      const uint32_t m = __ldg(t.M + row + wi);
+      const uint32_t start_mask = m & ~((m << 1) | carry);   // foreground with background on the left
+      carry = m >> 31;
+      if (!start_mask) continue;
+      uint32_t cand = start_mask & ~t.V[row + wi];
+      while (cand) {
+        const int b = __ffs(cand) - 1;
+        const int x = wi * 32 + b;
+        if (last_mark_left(t, x, y) <= 0) {
+          ContourStat st;
+          follow_border<true>(t, x, y, st, nullptr, nullptr);
+          ++ncont;
+          const long long a2 = st.area2 < 0 ? -st.area2 : st.area2;
+          if (a2 > best_a2) {
+            best_a2 = a2; best_x = x; best_y = y; best_npts = st.npts; best_perim = st.perim;
+            best_ymax = st.ymax;
+          }
+        }
+        const uint32_t above = (b == 31) ? 0u : (0xffffffffu << (b + 1));
+        cand = start_mask & ~t.V[row + wi] & above;
+      }
+    }
+  }
+  ri[I_NCONT] = ncont;
+  ri[I_NPTS] = best_npts;
+  if (ncont == 0) return;     // cannot happen for a non-empty mask
+
+  // ---- pass 2: per-row extremes of the best contour -> convex hull --------------------
+  uint32_t* ext_r = ws.scratch + 2 * d.row_off;
+  uint32_t* ext_l = ext_r + d.th;
+  for (int y = best_y; y <= best_ymax; ++y) { ext_l[y] = 0xffffu; ext_r[y] = 0u; }
+  {
+    ContourStat st;
+    follow_border<false>(t, best_x, best_y, st, ext_l, ext_r);
+  }
+  // right chain (top -> bottom, clockwise on screen): pop while the turn is not strictly convex
+  int nr = 0, nl = 0;
+  for (int y = best_y; y <= best_ymax; ++y) {
+    const uint32_t p = pk((int)ext_r[y], y);
+    while (nr >= 2 && cross3(ext_r[best_y + nr - 2], ext_r[best_y + nr - 1], p) <= 0) --nr;
+    ext_r[best_y + nr] = p; ++nr;
+  }
+  // left chain, also top -> bottom (counter-clockwise on screen): mirrored turn test
+  for (int y = best_y; y <= best_ymax; ++y) {
+    const uint32_t p = pk((int)ext_l[y], y);
+    while (nl >= 2 && cross3(ext_l[best_y + nl - 2], ext_l[best_y + nl - 1], p) >= 0) --nl;
+    ext_l[best_y + nl] = p; ++nl;
+  }
+  Hull hl;
+  hl.R = ext_r + best_y; hl.nr = nr;
+  hl.L = ext_l + best_y; hl.nl = nl;
+  hl.skip_r0 = (hl.R[0] == hl.L[0]) ? 1 : 0;                      // single-pixel top row
+  hl.skip_lb = (hl.R[nr - 1] == hl.L[nl - 1]) ? 1 : 0;            // single-pixel bottom row
+  hl.n = (nr - hl.skip_r0) + (nl - hl.skip_lb);
+  hl.ox = d.wx0 * 32; hl.oy = d.y0;
+  hl.swap2 = false;
+  if (hl.n <= 0) {            // a single pixel: both chains hold the same point
+    hl.skip_r0 = 0; hl.skip_lb = 1; hl.n = 1;
+  }
+  if (hl.n == 2) {
+    const uint32_t p0 = hl.raw(0), p1 = hl.raw(1);
+    const bool p0_larger = pkx(p0) > pkx(p1) || (pkx(p0) == pkx(p1) && pky(p0) > pky(p1));
+    hl.swap2 = !p0_larger;
+  }
+  const Rect rect = min_area_rect(hl);
+  float dA, dB;
+  feret_extents(rect, dA, dB);
+
+  // ---- descriptor block (nn_inference.py:434-449) -------------------------------------
+  const double ppm = pixels_per_metric;
+  const double area = (double)best_a2 * 0.5;
+  const double perimeter = best_perim;
+  // dA, dB are numpy float32 scalars in the reference; float32 / Python float stays
+  // float32 (NumPy >= 2 promotion), so Feret / Aspect_Ratio / Roundness / Length / Width
+  // are float32 arithmetic, while area and perimeter (Python floats) stay float64.
+  const float ppm32 = (float)ppm;
+  const float dimA = __fdiv_rn(dA, ppm32), dimB = __fdiv_rn(dB, ppm32);
+  const double dimArea = area / ppm, dimPerimeter = perimeter / ppm;
+  const float mx = dimA > dimB ? dimA : dimB, mn = dimA < dimB ? dimA : dimB;
+  const float aspect = (dimA != 0.f && dimB != 0.f) ? __fdiv_rn(mx, mn) : 0.f;
+  rf[F_CAREA] = area;
+  rf[F_PERIM] = perimeter;
+  rf[F_RCX] = rect.cx; rf[F_RCY] = rect.cy; rf[F_RW] = rect.w; rf[F_RH] = rect.h;
+  rf[F_RANGLE] = rect.angle;
+  rf[F_FERET] = mx;
+  rf[F_ASPECT] = aspect;
+  rf[F_ROUND] = aspect != 0.f ? __fdiv_rn(1.f, aspect) : 0.f;
+  rf[F_CIRC] = 4 * kPi * (dimArea / (dimPerimeter * dimPerimeter));
+  rf[F_SPHER] = (2 * sqrt(kPi * dimArea)) / dimPerimeter;
+  rf[F_LENGTH] = mn;
+  rf[F_WIDTH] = mx;
+  rf[F_CED] = sqrt(4 * area / kPi);
+  rf[F_CHORDS] = perimeter;
+}
+
+cudaError_t launch_contour_measure(int64_t n, const float* scores, double ppm, int64_t* rows_i,
+                                   double* rows_f, const Workspace& ws, const int64_t* status,
+                                   cudaStream_t stream) {
+  if (n == 0) return cudaSuccess;
+  const unsigned grid = (unsigned)((n + kContourThreads - 1) / kContourThreads);
+  contour_measure_kernel<<<grid, kContourThreads, 0, stream>>>(n, scores, ppm, rows_i, rows_f, ws,
+                                                               status);
+  return cudaPeekAtLastError();
+}
+
+}  // namespace uwcv

@@ -1,0 +1,355 @@
+// Kernel 0 (tile layout) and kernel 1+2 (fused paste / threshold / bit-pack / moments).
+//
+// Replaces, for the whole batch at once:
+//   * detectron2/layers/mask_ops.py::paste_masks_in_image + _do_paste_mask
+//     (F.grid_sample bilinear, zeros padding, align_corners=False, ">= threshold"),
+//     reached from nn_inference.py:372 via detector_postprocess;
+//   * the pixel-set reductions the reference gets from NumPy/OpenCV afterwards
+//     (nn_inference.py:394-401 union paint; cv2.moments / bbox of each instance).
+//
+// Arithmetic contract (bit-exact vs torch 2.11 CPU grid_sample):
+//   g  = ((p + 0.5f) - x0) / (x1 - x0) * 2 - 1          every op rounded separately
+//   ix = fmaf(g + 1, 14, -0.5);  fx = floor(ix);  w = ix - fx;  e = 1 - w   (same for y: n, s)
+//   out = fmaf(v_se, n*w, fmaf(v_sw, n*e, fmaf(v_ne, s*w, v_nw * (s*e))));  bit = out >= thr
+// The file is compiled with -fmad=false; every FMA below is explicit.
+//
+// Data movement: the full-frame bit-plane of an instance is H rows of `wpr` 32-bit
+// words.  Rows above / below the instance's tile are zero and are written with TMA
+// bulk stores (cp.async.bulk shared->global) from a zeroed shared-memory buffer;
+// the rows of the tile band are written with ordinary stores.  Algorithmic bytes per
+// instance: 3136 (probabilities) + 16 (box) read, H*W/8 + rows written.
+#include "uwcv_common.cuh"
+
+namespace uwcv {
+
+// ---------------------------------------------------------------------------------
+// kernel 0: tile geometry + exclusive prefix sums (single CTA)
+// ---------------------------------------------------------------------------------
+__device__ __forceinline__ void tile_geometry(const float* __restrict__ box, int H, int W,
+                                              int& wx0, int& y0, int& tw, int& th) {
+  float x0 = box[0], yy0 = box[1], x1 = box[2], y1 = box[3];
+  float bw = x1 - x0, bh = y1 - yy0;
+  wx0 = y0 = tw = th = 0;
+  if (!(bw > 0.f) || !(bh > 0.f)) return;                    // also rejects NaN
+  if (!isfinite(x0) || !isfinite(x1) || !isfinite(yy0) || !isfinite(y1)) return;
+  // support of the zero-padded bilinear kernel: p + 0.5 in (x0 - bw/56, x1 + bw/56);
+  // one mask cell + one pixel of slack covers it for any positive threshold.
+  double mx = (double)bw / kMaskSide + 1.0, my = (double)bh / kMaskSide + 1.0;
+  double fa = floor((double)x0 - mx), fb = ceil((double)x1 + mx);
+  double ga = floor((double)yy0 - my), gb = ceil((double)y1 + my);
+  if (fb < 0 || ga > H - 1 || fa > W - 1 || gb < 0) return;
+  int pxa = fa < 0 ? 0 : (int)fa;
+  int pxb = fb > W - 1 ? W - 1 : (int)fb;
+  int pya = ga < 0 ? 0 : (int)ga;
+  int pyb = gb > H - 1 ? H - 1 : (int)gb;
+  if (pxa > pxb || pya > pyb) return;
+  wx0 = pxa >> 5;
+  tw = (pxb >> 5) - wx0 + 1;
+  y0 = pya;
+  th = pyb - pya + 1;
+}
+
+constexpr int kLayoutThreads = 1024;
+
+__global__ void __launch_bounds__(kLayoutThreads)
+layout_kernel(const float* __restrict__ boxes, int64_t n, int H, int W,
+              TileDesc* __restrict__ desc, int64_t cap_words, int64_t* __restrict__ status) {
+  __shared__ int64_t s_words[kLayoutThreads];
+  __shared__ int64_t s_rows[kLayoutThreads];
+  const int t = threadIdx.x;
+  const int64_t per = (n + kLayoutThreads - 1) / kLayoutThreads;
+  const int64_t lo = (int64_t)t * per;
+  const int64_t hi = lo + per < n ? lo + per : n;
+  int64_t words = 0, rows = 0;
+  for (int64_t i = lo; i < hi; ++i) {
+    int wx0, y0, tw, th;
+    tile_geometry(boxes + 4 * i, H, W, wx0, y0, tw, th);
+    words += (int64_t)tw * th;
+    rows += th;
+  }
+  s_words[t] = words;
+  s_rows[t] = rows;
+  __syncthreads();
+  // Hillis-Steele inclusive scan over the 1024 partials
+  for (int off = 1; off < kLayoutThreads; off <<= 1) {
+    int64_t a = 0, b = 0;
+    if (t >= off) { a = s_words[t - off]; b = s_rows[t - off]; }
+    __syncthreads();
+    s_words[t] += a;
+    s_rows[t] += b;
+    __syncthreads();
+  }
+  int64_t woff = s_words[t] - words, roff = s_rows[t] - rows;
+  const int64_t total_words = s_words[kLayoutThreads - 1];
+  const int64_t total_rows = s_rows[kLayoutThreads - 1];
+  for (int64_t i = lo; i < hi; ++i) {
+    int wx0, y0, tw, th;
+    tile_geometry(boxes + 4 * i, H, W, wx0, y0, tw, th);
+    TileDesc d;
+    d.wx0 = wx0; d.y0 = y0; d.tw = tw; d.th = th;
+    d.word_off = woff; d.row_off = roff;
+    desc[i] = d;
+    woff += (int64_t)tw * th;
+    roff += th;
+  }
+  if (t == 0) {
+    status[1] = total_words;
+    status[2] = total_rows;
+    status[0] = (total_words > cap_words) ? (int64_t)E_CAPACITY : 0;
+  }
+}
+
+// ---------------------------------------------------------------------------------
+// kernel 1+2: paste + threshold + bit-pack + raw moments / bbox
+// ---------------------------------------------------------------------------------
+constexpr int kPasteThreads = 256;
+constexpr int kPasteWarps = kPasteThreads / 32;
+constexpr int kZeroBytes = 16384;            // shared zero source for the bulk stores
+
+__device__ __forceinline__ void bulk_store_zero(void* gdst, uint32_t smem_src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+               :: "l"(gdst), "r"(smem_src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() {
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_wait_read_all() {
+  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_smem() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+// coordinate of pixel index p along one axis -> (padded tap base, weight hi, weight lo)
+// base indexes the zero-framed 32-wide mask copy: taps are base and base + 1.
+__device__ __forceinline__ void axis_coord(int p, float lo, float hi, int& base, float& w_hi,
+                                           float& w_lo) {
+  float g = __fsub_rn(__fmul_rn(__fdiv_rn(__fsub_rn(__fadd_rn((float)p, 0.5f), lo),
+                                          __fsub_rn(hi, lo)), 2.0f), 1.0f);
+  float i = __fmaf_rn(__fadd_rn(g, 1.0f), (float)kMaskSide * 0.5f, -0.5f);
+  float f = floorf(i);
+  w_hi = __fsub_rn(i, f);          // weight of the tap at f + 1  ("w" / "n")
+  w_lo = __fsub_rn(1.0f, w_hi);    // weight of the tap at f      ("e" / "s")
+  // taps outside [0, 27] read zeros from the frame; clamp in the float domain so that
+  // huge / non-finite coordinates never reach a float->int conversion out of range.
+  float fc = fminf(fmaxf(f, -(float)kPad), (float)kMaskSide);
+  base = (int)fc + kPad;           // in [0, kMaskSide + kPad] = [0, 30]; taps base, base+1 <= 31
+}
+
+template <bool kPlanes>
+__global__ void __launch_bounds__(kPasteThreads)
+paste_measure_kernel(const float* __restrict__ masks, const float* __restrict__ boxes,
+                     const int32_t* __restrict__ image_idx, const int32_t* __restrict__ inst_idx,
+                     const int64_t* __restrict__ classes, int64_t n, int H, int W, float thr,
+                     uint32_t* __restrict__ planes, int64_t* __restrict__ rows_i,
+                     Workspace ws, const int64_t* __restrict__ status) {
+  __shared__ __align__(128) unsigned char s_zero[kPlanes ? kZeroBytes : 16];
+  __shared__ __align__(16) float s_mask[kMaskPitch * kMaskPitch];
+  __shared__ unsigned long long s_acc[10];
+  __shared__ int s_bbox[4];
+
+  if (status[0] != 0) return;                       // layout overflowed the workspace
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int wpr = plane_row_words(W);
+  const int64_t plane_words = (int64_t)H * wpr;
+
+  if (kPlanes) {
+    for (int k = tid; k < kZeroBytes / 16; k += kPasteThreads)
+      reinterpret_cast<uint4*>(s_zero)[k] = make_uint4(0, 0, 0, 0);
+    fence_proxy_async_smem();                       // generic-proxy zeros -> visible to TMA
+  }
+  // the frame of the padded mask stays zero for the whole kernel
+  for (int k = tid; k < kMaskPitch * kMaskPitch; k += kPasteThreads) s_mask[k] = 0.f;
+  __syncthreads();
+  const uint32_t zero_smem = (uint32_t)__cvta_generic_to_shared(s_zero);
+
+  for (int64_t inst = blockIdx.x; inst < n; inst += gridDim.x) {
+    const TileDesc d = ws.desc[inst];
+    const float bx0 = boxes[4 * inst + 0], by0 = boxes[4 * inst + 1];
+    const float bx1 = boxes[4 * inst + 2], by1 = boxes[4 * inst + 3];
+    uint32_t* plane = kPlanes ? planes + inst * plane_words : nullptr;
+
+    // ---- zero rows above and below the band: TMA bulk stores by one thread --------
+    if (kPlanes && tid == 0) {
+      const int band_lo = d.th > 0 ? d.y0 : H;              // empty tile: whole plane is zero
+      const int band_hi = d.th > 0 ? d.y0 + d.th : H;
+      char* base = reinterpret_cast<char*>(plane);
+      int64_t seg_lo[2] = {0, (int64_t)band_hi * wpr * 4};
+      int64_t seg_hi[2] = {(int64_t)band_lo * wpr * 4, plane_words * 4};
+      for (int sgi = 0; sgi < 2; ++sgi)
+        for (int64_t o = seg_lo[sgi]; o < seg_hi[sgi]; o += kZeroBytes) {
+          int64_t rem = seg_hi[sgi] - o;
+          bulk_store_zero(base + o, zero_smem, (uint32_t)(rem < kZeroBytes ? rem : kZeroBytes));
+        }
+      bulk_commit();
+    }
+
+    // ---- stage the 28x28 probabilities into the zero-framed copy --------------------
+    const float* msrc = masks + inst * (kMaskSide * kMaskSide);
+    for (int k = tid; k < kMaskSide * kMaskSide; k += kPasteThreads) {
+      int r = k / kMaskSide, c = k - r * kMaskSide;
+      s_mask[(r + kPad) * kMaskPitch + c + kPad] = __ldg(msrc + k);
+    }
+    if (tid < 10) s_acc[tid] = 0ull;
+    if (tid == 0) { s_bbox[0] = INT_MAX; s_bbox[1] = INT_MAX; s_bbox[2] = -1; s_bbox[3] = -1; }
+    __syncthreads();
+
+    // ---- zero the non-tile words of the band rows (ordinary stores) ----------------
+    if (kPlanes && d.th > 0) {
+      const int outside = wpr - d.tw;
+      const int total = outside * d.th;
+      for (int k = tid; k < total; k += kPasteThreads) {
+        int r = k / outside, c = k - r * outside;
+        if (c >= d.wx0) c += d.tw;
+        plane[(int64_t)(d.y0 + r) * wpr + c] = 0u;
+      }
+    }
+
+    // ---- the tile: each warp takes groups of 32 rows --------------------------------
+    long long m00 = 0, m10 = 0, m01 = 0, m20 = 0, m11 = 0, m02 = 0, m30 = 0, m21 = 0, m12 = 0,
+              m03 = 0;
+    int xmin = INT_MAX, xmax = -1, ymin = INT_MAX, ymax = -1;
+    uint32_t* tM = ws.M + d.word_off;
+    uint32_t* tV = ws.V + d.word_off;
+    uint32_t* tG = ws.G + d.word_off;
+
+    for (int g = warp; g * 32 < d.th; g += kPasteWarps) {
+      const int rbase = g * 32;
+      int rowb; float rn, rs;
+      axis_coord(d.y0 + rbase + lane, by0, by1, rowb, rn, rs);
+      rowb *= kMaskPitch;
+      const int nrows = min(32, d.th - rbase);
+      for (int strip = 0; strip < d.tw; ++strip) {
+        const int px = (d.wx0 + strip) * 32 + lane;
+        int colb; float cw, ce;
+        axis_coord(px, bx0, bx1, colb, cw, ce);
+        const bool col_ok = px < W;
+        int S0 = 0, S1 = 0, S2 = 0, S3 = 0;
+        uint32_t myword = 0;
+#pragma unroll 4
+        for (int j = 0; j < 32; ++j) {
+          const int rb = __shfl_sync(0xffffffffu, rowb, j);
+          const float n_ = __shfl_sync(0xffffffffu, rn, j);
+          const float s_ = __shfl_sync(0xffffffffu, rs, j);
+          const float* mp = s_mask + rb + colb;
+          const float v_nw = mp[0], v_ne = mp[1], v_sw = mp[kMaskPitch], v_se = mp[kMaskPitch + 1];
+          const float nw = __fmul_rn(s_, ce), ne = __fmul_rn(s_, cw);
+          const float sw = __fmul_rn(n_, ce), se = __fmul_rn(n_, cw);
+          float out = __fmul_rn(v_nw, nw);
+          out = __fmaf_rn(v_ne, ne, out);
+          out = __fmaf_rn(v_sw, sw, out);
+          out = __fmaf_rn(v_se, se, out);
+          const bool bit = (out >= thr) && col_ok && (j < nrows);
+          const uint32_t word = __ballot_sync(0xffffffffu, bit);
+          if (lane == j) myword = word;
+          const int b = bit ? 1 : 0;
+          S0 += b; S1 += b * j; S2 += b * j * j; S3 += b * j * j * j;
+        }
+        // lane r holds the word of row rbase + r
+        if (lane < nrows) {
+          const int64_t o = (int64_t)(rbase + lane) * d.tw + strip;
+          tM[o] = myword; tV[o] = 0u; tG[o] = 0u;
+          if (kPlanes) plane[(int64_t)(d.y0 + rbase + lane) * wpr + d.wx0 + strip] = myword;
+          if (myword) { ymin = min(ymin, d.y0 + rbase + lane); ymax = max(ymax, d.y0 + rbase + lane); }
+        }
+        if (S0) {
+          // column sums over the 32 rows, shifted to frame coordinates (exact integers)
+          const long long yb = d.y0 + rbase, x = px;
+          const long long T0 = S0;
+          const long long T1 = S1 + yb * S0;
+          const long long T2 = S2 + 2 * yb * S1 + yb * yb * S0;
+          const long long T3 = S3 + 3 * yb * S2 + 3 * yb * yb * S1 + yb * yb * yb * S0;
+          const long long x2 = x * x, x3 = x2 * x;
+          m00 += T0; m10 += x * T0; m20 += x2 * T0; m30 += x3 * T0;
+          m01 += T1; m11 += x * T1; m21 += x2 * T1;
+          m02 += T2; m12 += x * T2;
+          m03 += T3;
+          xmin = min(xmin, px); xmax = max(xmax, px);
+        }
+      }
+    }
+    // ---- warp-shuffle reduction, one shared-memory atomic per warp and moment -------
+    long long acc[10] = {m00, m10, m01, m20, m11, m02, m30, m21, m12, m03};
+#pragma unroll
+    for (int k = 0; k < 10; ++k) {
+      long long v = acc[k];
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+      if (lane == 0 && v != 0) atomicAdd(&s_acc[k], (unsigned long long)v);
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      xmin = min(xmin, __shfl_xor_sync(0xffffffffu, xmin, off));
+      ymin = min(ymin, __shfl_xor_sync(0xffffffffu, ymin, off));
+      xmax = max(xmax, __shfl_xor_sync(0xffffffffu, xmax, off));
+      ymax = max(ymax, __shfl_xor_sync(0xffffffffu, ymax, off));
+    }
+    if (lane == 0 && xmax >= 0) {
+      atomicMin(&s_bbox[0], xmin); atomicMin(&s_bbox[1], ymin);
+      atomicMax(&s_bbox[2], xmax); atomicMax(&s_bbox[3], ymax);
+    }
+    __syncthreads();
+    // ---- integer part of the row --------------------------------------------------------
+    if (tid < kNumInt) {
+      long long v = 0;
+      const long long area = (long long)s_acc[0];
+      switch (tid) {
+        case I_IMAGE: v = image_idx ? image_idx[inst] : 0; break;
+        case I_INST:  v = inst_idx ? inst_idx[inst] : inst; break;
+        case I_CLASS: v = classes ? classes[inst] : 0; break;
+        case I_VALID: v = area > 0; break;
+        case I_NCONT: v = 0; break;
+        case I_AREA:  v = area; break;
+        case I_BX0: v = area > 0 ? s_bbox[0] : -1; break;
+        case I_BY0: v = area > 0 ? s_bbox[1] : -1; break;
+        case I_BX1: v = area > 0 ? s_bbox[2] : -1; break;
+        case I_BY1: v = area > 0 ? s_bbox[3] : -1; break;
+        case I_NPTS: v = 0; break;
+        default: v = (long long)s_acc[tid - I_M10 + 1]; break;     // m10 .. m03
+      }
+      rows_i[inst * kNumInt + tid] = v;
+    }
+    __syncthreads();                                 // s_mask / s_acc are rewritten next round
+  }
+  if (kPlanes && tid == 0) bulk_wait_read_all();     // shared zero source must outlive the copies
+}
+
+// ---------------------------------------------------------------------------------
+// host-side launchers (called from the C ABI)
+// ---------------------------------------------------------------------------------
+cudaError_t launch_layout(const float* boxes, int64_t n, int H, int W, const Workspace& ws,
+                          int64_t* status, cudaStream_t stream) {
+  layout_kernel<<<1, kLayoutThreads, 0, stream>>>(boxes, n, H, W, ws.desc, ws.cap_words, status);
+  return cudaPeekAtLastError();
+}
+
+cudaError_t launch_paste_measure(const float* masks, const float* boxes, const int32_t* image_idx,
+                                 const int32_t* inst_idx, const int64_t* classes, int64_t n, int H,
+                                 int W, float thr, uint32_t* planes, int64_t* rows_i,
+                                 const Workspace& ws, const int64_t* status, int num_sms,
+                                 cudaStream_t stream) {
+  if (n == 0) return cudaSuccess;
+  int per_sm = 0;
+  cudaError_t e;
+  if (planes) {
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, paste_measure_kernel<true>,
+                                                      kPasteThreads, 0);
+  } else {
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, paste_measure_kernel<false>,
+                                                      kPasteThreads, 0);
+  }
+  if (e != cudaSuccess) return e;
+  if (per_sm < 1) per_sm = 1;
+  int64_t grid = (int64_t)num_sms * per_sm;           // persistent: a whole number of waves
+  if (grid > n) grid = n;
+  if (planes)
+    paste_measure_kernel<true><<<(unsigned)grid, kPasteThreads, 0, stream>>>(
+        masks, boxes, image_idx, inst_idx, classes, n, H, W, thr, planes, rows_i, ws, status);
+  else
+    paste_measure_kernel<false><<<(unsigned)grid, kPasteThreads, 0, stream>>>(
+        masks, boxes, image_idx, inst_idx, classes, n, H, W, thr, planes, rows_i, ws, status);
+  return cudaPeekAtLastError();
+}
+
+}  // namespace uwcv

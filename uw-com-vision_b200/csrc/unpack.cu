@@ -1,0 +1,51 @@
+// Bit-plane -> Detectron2-literal N x H x W bool (uint8 0/1), on demand.
+//
+// detectron2's paste_masks_in_image returns a bool tensor (one byte per pixel); the
+// product keeps 1 bit per pixel and expands only when a caller asks for the literal
+// layout (nn_inference.py:376 reads pred_masks as such).  One thread expands one
+// 32-pixel word into two 16-byte stores; rows are W bytes, words past W are skipped.
+#include "uwcv_common.cuh"
+
+namespace uwcv {
+
+__global__ void __launch_bounds__(256)
+unpack_planes_kernel(const uint32_t* __restrict__ planes, int64_t n, int H, int W, int wpr,
+                     uint8_t* __restrict__ out) {
+  const int wreal = (W + 31) >> 5;
+  const int64_t total = n * H * wreal;
+  for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < total;
+       k += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t row = k / wreal;
+    const int wi = (int)(k - row * wreal);
+    const uint32_t bits = __ldg(planes + row * wpr + wi);
+    uint8_t* dst = out + row * W + (int64_t)wi * 32;
+    const int npx = min(32, W - wi * 32);
+    if (npx == 32 && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+      uint32_t v[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const uint32_t nib = (bits >> (4 * q)) & 0xFu;
+        // spread 4 bits into 4 bytes: bit i -> byte i
+        v[q] = ((nib & 1u)) | ((nib & 2u) << 7) | ((nib & 4u) << 14) | ((nib & 8u) << 21);
+      }
+      reinterpret_cast<uint4*>(dst)[0] = make_uint4(v[0], v[1], v[2], v[3]);
+      reinterpret_cast<uint4*>(dst)[1] = make_uint4(v[4], v[5], v[6], v[7]);
+    } else {
+      for (int i = 0; i < npx; ++i) dst[i] = (bits >> i) & 1u;
+    }
+  }
+}
+
+cudaError_t launch_unpack(const uint32_t* planes, int64_t n, int H, int W, uint8_t* out,
+                          int num_sms, cudaStream_t stream) {
+  if (n == 0) return cudaSuccess;
+  const int wpr = plane_row_words(W);
+  const int64_t total = n * H * ((W + 31) >> 5);
+  int64_t grid = (total + 255) / 256;
+  const int64_t cap = (int64_t)num_sms * 32;
+  if (grid > cap) grid = cap;
+  unpack_planes_kernel<<<(unsigned)grid, 256, 0, stream>>>(planes, n, H, W, wpr, out);
+  return cudaPeekAtLastError();
+}
+
+}  // namespace uwcv

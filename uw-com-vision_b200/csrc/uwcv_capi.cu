@@ -1,0 +1,128 @@
+// extern "C" entry points of libuwcv.so (declared in include/uwcv.h).
+#include "../../include/uwcv.h"
+#include "uwcv_common.cuh"
+
+namespace uwcv {
+cudaError_t launch_layout(const float*, int64_t, int, int, const Workspace&, int64_t*, cudaStream_t);
+cudaError_t launch_paste_measure(const float*, const float*, const int32_t*, const int32_t*,
+                                 const int64_t*, int64_t, int, int, float, uint32_t*, int64_t*,
+                                 const Workspace&, const int64_t*, int, cudaStream_t);
+cudaError_t launch_contour_measure(int64_t, const float*, double, int64_t*, double*,
+                                   const Workspace&, const int64_t*, cudaStream_t);
+cudaError_t launch_unpack(const uint32_t*, int64_t, int, int, uint8_t*, int, cudaStream_t);
+size_t nms_workspace_bytes_host(const int64_t*, int);
+cudaError_t launch_nms(const float*, const float*, const int64_t*, const int64_t*, int, float,
+                       double, int, int64_t*, int32_t*, void*, cudaStream_t);
+}  // namespace uwcv
+
+namespace {
+inline bool misaligned(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) != 0; }
+int num_sms() {
+  int dev = 0, sms = 148;
+  if (cudaGetDevice(&dev) == cudaSuccess)
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  return sms > 0 ? sms : 148;
+}
+}  // namespace
+
+extern "C" {
+
+int uwcv_version(void) { return 100; }
+
+const char* uwcv_strerror(int code) {
+  switch (code) {
+    case UWCV_OK: return "ok";
+    case UWCV_E_NULL: return "required pointer is NULL";
+    case UWCV_E_SHAPE: return "invalid shape or size argument";
+    case UWCV_E_ALIGN: return "pointer is not 16-byte aligned";
+    case UWCV_E_THRESH: return "mask threshold must be > 0";
+    case UWCV_E_WORKSPACE: return "workspace too small";
+    case UWCV_E_LAUNCH: return "CUDA launch error";
+    case UWCV_E_CAPACITY: return "tile words exceed workspace capacity (see status[1])";
+    case UWCV_E_TOO_LARGE: return "image side or candidate count too large";
+    default: return "unknown uwcv error";
+  }
+}
+
+int uwcv_plane_row_words(int W) { return uwcv::plane_row_words(W); }
+
+size_t uwcv_workspace_bytes(int64_t N, int64_t tile_words) {
+  if (N < 0) N = 0;
+  if (tile_words < 0) tile_words = 0;
+  return uwcv::workspace_bytes(N, tile_words + 4);
+}
+
+int uwcv_paste_measure(const float* masks, const float* boxes, const int32_t* image_idx,
+                       const int32_t* inst_idx, const int64_t* classes, const float* scores,
+                       int64_t N, int H, int W, float thr, double pixels_per_metric,
+                       uint32_t* bitplanes, int64_t* rows_i, double* rows_f, void* workspace,
+                       size_t ws_bytes, int64_t* status, void* stream) {
+  if (N < 0 || H <= 0 || W <= 0) return UWCV_E_SHAPE;
+  if (H > 32768 || W > 32768) return UWCV_E_TOO_LARGE;
+  if (!(thr > 0.f)) return UWCV_E_THRESH;
+  if (!(pixels_per_metric > 0.0)) return UWCV_E_SHAPE;
+  if (!status) return UWCV_E_NULL;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (N == 0) {
+    return cudaMemsetAsync(status, 0, 4 * sizeof(int64_t), st) == cudaSuccess ? UWCV_OK
+                                                                              : UWCV_E_LAUNCH;
+  }
+  if (!masks || !boxes || !rows_i || !rows_f || !workspace) return UWCV_E_NULL;
+  if (misaligned(masks) || misaligned(boxes) || misaligned(rows_i) || misaligned(rows_f) ||
+      misaligned(workspace) || misaligned(status) || (bitplanes && misaligned(bitplanes)))
+    return UWCV_E_ALIGN;
+  if (ws_bytes < uwcv::workspace_bytes(N, 4)) return UWCV_E_WORKSPACE;
+  const uwcv::Workspace ws = uwcv::carve(workspace, ws_bytes, N);
+  if (uwcv::launch_layout(boxes, N, H, W, ws, status, st) != cudaSuccess) return UWCV_E_LAUNCH;
+  if (uwcv::launch_paste_measure(masks, boxes, image_idx, inst_idx, classes, N, H, W, thr,
+                                 bitplanes, rows_i, ws, status, num_sms(), st) != cudaSuccess)
+    return UWCV_E_LAUNCH;
+  if (uwcv::launch_contour_measure(N, scores, pixels_per_metric, rows_i, rows_f, ws, status, st) !=
+      cudaSuccess)
+    return UWCV_E_LAUNCH;
+  return UWCV_OK;
+}
+
+int uwcv_unpack_planes(const uint32_t* bitplanes, int64_t N, int H, int W, uint8_t* out,
+                       void* stream) {
+  if (N < 0 || H <= 0 || W <= 0) return UWCV_E_SHAPE;
+  if (N == 0) return UWCV_OK;
+  if (!bitplanes || !out) return UWCV_E_NULL;
+  if (misaligned(bitplanes)) return UWCV_E_ALIGN;
+  return uwcv::launch_unpack(bitplanes, N, H, W, out, num_sms(),
+                             reinterpret_cast<cudaStream_t>(stream)) == cudaSuccess
+             ? UWCV_OK : UWCV_E_LAUNCH;
+}
+
+size_t uwcv_nms_workspace_bytes(const int64_t* image_off, int B) {
+  if (!image_off || B <= 0) return 256;
+  return uwcv::nms_workspace_bytes_host(image_off, B);
+}
+
+int uwcv_nms_filter(const float* boxes, const float* scores, const int64_t* classes,
+                    const int64_t* image_off, int B, float score_thr, double iou_thr, int topk,
+                    int64_t* keep, int32_t* keep_count, void* workspace, size_t ws_bytes,
+                    void* stream) {
+  if (B < 0) return UWCV_E_SHAPE;
+  if (B == 0) return UWCV_OK;
+  if (!image_off || !keep_count) return UWCV_E_NULL;
+  if (image_off[0] != 0) return UWCV_E_SHAPE;
+  for (int b = 0; b < B; ++b) {
+    const int64_t n = image_off[b + 1] - image_off[b];
+    if (n < 0) return UWCV_E_SHAPE;
+    if (n > 262144) return UWCV_E_TOO_LARGE;
+  }
+  if (B > 65535) return UWCV_E_TOO_LARGE;
+  const int64_t R = image_off[B];
+  if (R > 0 && (!boxes || !scores || !classes || !keep)) return UWCV_E_NULL;
+  if (!workspace) return UWCV_E_NULL;
+  if (misaligned(boxes) || misaligned(workspace)) return UWCV_E_ALIGN;
+  if (ws_bytes < uwcv::nms_workspace_bytes_host(image_off, B)) return UWCV_E_WORKSPACE;
+  if (topk < 0) topk = 0x7fffffff;
+  return uwcv::launch_nms(boxes, scores, classes, image_off, B, score_thr, iou_thr, topk, keep,
+                          keep_count, workspace, reinterpret_cast<cudaStream_t>(stream)) ==
+                 cudaSuccess
+             ? UWCV_OK : UWCV_E_LAUNCH;
+}
+
+}  // extern "C"

@@ -1,0 +1,82 @@
+// Shared definitions for the uwcv sm_100a kernels.
+//
+// Hot path: the post-inference stage of uw-com-vision's Mask R-CNN pipeline
+// (/root/reference/nn_inference.py:371-459 and the Detectron2 post-process it
+// reaches through predictor(im), :372).  See DESIGN.md for the data layout.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace uwcv {
+
+constexpr int kMaskSide = 28;              // Detectron2 / torchvision mask head output side
+constexpr int kPad = 2;                    // zero frame so that taps at -2..29 need no branch
+constexpr int kMaskPitch = kMaskSide + 2 * kPad;   // 32
+constexpr int kNumInt = 20;                // int64 columns per row  
+constexpr int kNumFloat = 30;              // float64 columns per row
+
+// int64 column indices
+enum IntCol {
+  I_IMAGE = 0, I_INST, I_CLASS, I_VALID, I_NCONT, I_AREA, I_BX0, I_BY0, I_BX1, I_BY1,
+  I_M10, I_M01, I_M20, I_M11, I_M02, I_M30, I_M21, I_M12, I_M03, I_NPTS
+};
+// float64 column indices
+enum FloatCol {
+  F_SCORE = 0, F_CX, F_CY, F_MU20, F_MU11, F_MU02, F_MU30, F_MU21, F_MU12, F_MU03,
+  F_EQD, F_ELL_MAJOR, F_ELL_MINOR, F_ELL_THETA, F_CAREA, F_PERIM,
+  F_RCX, F_RCY, F_RW, F_RH, F_RANGLE,
+  F_FERET, F_ASPECT, F_ROUND, F_CIRC, F_SPHER, F_LENGTH, F_WIDTH, F_CED, F_CHORDS
+};
+
+// error codes (C ABI returns these; 0 = ok)
+enum Err {
+  OK = 0, E_NULL = -1, E_SHAPE = -2, E_ALIGN = -3, E_THRESH = -4, E_WORKSPACE = -5,
+  E_LAUNCH = -6, E_CAPACITY = -7, E_TOO_LARGE = -8
+};
+
+// Per-instance tile: the word-aligned window of the frame that can hold set pixels.
+struct __align__(16) TileDesc {
+  int32_t wx0;        // first 32-pixel word column of the tile (pixel x origin = wx0 * 32)
+  int32_t y0;         // first pixel row
+  int32_t tw;         // width in words
+  int32_t th;         // height in rows  (0 => empty tile)
+  int64_t word_off;   // offset of the tile's first word in the M / V / G planes
+  int64_t row_off;    // offset of the tile's first row in the per-row trace scratch
+};
+
+// Workspace carve-up, computed identically on host and device.
+struct Workspace {
+  TileDesc* desc;      // [N]
+  uint32_t* M;         // [cap_words]  mask bits
+  uint32_t* V;         // [cap_words]  border-visited marks
+  uint32_t* G;         // [cap_words]  "right neighbour was background" marks (negative marks)
+  uint32_t* scratch;   // [2 * cap_words]  packed (x | y << 16) row extremes / hull chains
+  int64_t cap_words;
+};
+
+__host__ __device__ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+__host__ __device__ inline size_t workspace_bytes(int64_t n, int64_t tile_words) {
+  return align_up((size_t)n * sizeof(TileDesc), 256) + (size_t)tile_words * 20 + 256;
+}
+
+__host__ __device__ inline Workspace carve(void* ws, size_t ws_bytes, int64_t n) {
+  Workspace w;
+  char* p = (char*)ws;
+  w.desc = (TileDesc*)p;
+  size_t d = align_up((size_t)n * sizeof(TileDesc), 256);
+  int64_t cap = ws_bytes > d + 256 ? (int64_t)((ws_bytes - d - 256) / 20) : 0;
+  cap &= ~(int64_t)3;                         // keep every plane 16-byte aligned
+  w.cap_words = cap;
+  w.M = (uint32_t*)(p + d);
+  w.V = w.M + cap;
+  w.G = w.V + cap;
+  w.scratch = w.G + cap;
+  return w;
+}
+
+// plane row stride in 32-bit words: ceil(W / 32) rounded up to a multiple of 4 so that
+// every row (and every plane) starts on a 16-byte boundary for the bulk stores.
+__host__ __device__ inline int plane_row_words(int W) { return ((W + 31) / 32 + 3) & ~3; }
+
+}  // namespace uwcv

@@ -1,0 +1,63 @@
+"""ctypes binding of libuwcv.so (include/uwcv.h).  There is no fallback: if the
+shared object is missing the import of any product entry point raises."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+from .build import LIB_PATH
+
+_lib = None
+
+E_CAPACITY = -7
+
+
+class UwcvError(RuntimeError):
+    def __init__(self, code: int, where: str):
+        self.code = code
+        super().__init__(f"{where}: uwcv error {code}: {strerror(code)}")
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(the uwcv hot path has no CPU or PyTorch fallback)")
+    L = C.CDLL(LIB_PATH)
+    vp, i64, i32, f32, f64, sz = C.c_void_p, C.c_int64, C.c_int, C.c_float, C.c_double, C.c_size_t
+    L.uwcv_version.restype = C.c_int
+    L.uwcv_strerror.restype = C.c_char_p
+    L.uwcv_strerror.argtypes = [C.c_int]
+    L.uwcv_plane_row_words.restype = C.c_int
+    L.uwcv_plane_row_words.argtypes = [C.c_int]
+    L.uwcv_workspace_bytes.restype = sz
+    L.uwcv_workspace_bytes.argtypes = [i64, i64]
+    L.uwcv_paste_measure.restype = C.c_int
+    L.uwcv_paste_measure.argtypes = [vp, vp, vp, vp, vp, vp, i64, i32, i32, f32, f64,
+                                     vp, vp, vp, vp, sz, vp, vp]
+    L.uwcv_unpack_planes.restype = C.c_int
+    L.uwcv_unpack_planes.argtypes = [vp, i64, i32, i32, vp, vp]
+    L.uwcv_nms_workspace_bytes.restype = sz
+    L.uwcv_nms_workspace_bytes.argtypes = [C.POINTER(C.c_int64), i32]
+    L.uwcv_nms_filter.restype = C.c_int
+    L.uwcv_nms_filter.argtypes = [vp, vp, vp, C.POINTER(C.c_int64), i32, f32, f64, i32,
+                                  vp, vp, vp, sz, vp]
+    _lib = L
+    return L
+
+
+EXPORTS = ("uwcv_version", "uwcv_strerror", "uwcv_plane_row_words", "uwcv_workspace_bytes",
+           "uwcv_paste_measure", "uwcv_unpack_planes", "uwcv_nms_workspace_bytes",
+           "uwcv_nms_filter")
+
+
+def strerror(code: int) -> str:
+    return lib().uwcv_strerror(int(code)).decode()
+
+
+def check(code: int, where: str) -> None:
+    if code != 0:
+        raise UwcvError(code, where)

@@ -1,0 +1,464 @@
+"""Host-side mirror of the reference's call surface for the hot path.
+
+Same names, argument meaning and error behaviour as the Detectron2 functions the
+reference reaches through ``predictor(im)`` (nn_inference.py:372) and as its own
+measurement entry ``GetMask_Contours`` (nn_inference.py:371-459):
+
+* ``paste_masks_in_image(masks, boxes, image_shape, threshold)``  -> N x H x W bool
+* ``detector_postprocess(results, output_height, output_width, mask_threshold)``
+* ``fast_rcnn_inference_single_image(boxes, scores, image_shape, score_thresh,
+  nms_thresh, topk_per_image)``
+* ``measure_instances(instances, output_size, classes_of_interest, ...)`` -> table
+
+PyTorch is used for device memory, streams and the three N x 4 box ops that must stay
+bit-identical to Detectron2's (scale, clip, non-empty); every pixel- or box-pair-level
+computation runs in libuwcv.so.  There is no CPU path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import List, Optional, Sequence, Tuple, Union
+
+import numpy as np
+import torch
+
+from . import _lib
+from .schema import (CSV_SOURCE, FCOL, FLOAT_COLUMNS, ICOL, INT_COLUMNS, NUM_FLOAT, NUM_INT)
+from .structures import Boxes, Instances
+
+MASK_SIDE = 28
+
+
+def _require_cuda(device=None) -> torch.device:
+    if not torch.cuda.is_available():
+        raise RuntimeError("uwcv needs a CUDA device (sm_100a); there is no CPU fallback")
+    if device is None:
+        return torch.device("cuda", torch.cuda.current_device())
+    device = torch.device(device)
+    if device.type != "cuda":
+        raise RuntimeError(f"uwcv runs on CUDA devices only, got {device}")
+    if device.index is None:
+        device = torch.device("cuda", torch.cuda.current_device())
+    return device
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _stream_ptr(device: torch.device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+# ----------------------------------------------------------------------------------
+# box glue: the three Detectron2 ops that must be bit-identical
+# ----------------------------------------------------------------------------------
+
+def scale_clip_boxes(boxes: torch.Tensor, in_size: Tuple[int, int], out_size: Tuple[int, int]
+                     ) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Boxes.scale + Boxes.clip + Boxes.nonempty of detector_postprocess.
+    Returns (output-space boxes, keep mask); works on whatever device ``boxes`` is on."""
+    out_h, out_w = int(out_size[0]), int(out_size[1])
+    scale_x, scale_y = out_w / in_size[1], out_h / in_size[0]
+    b = boxes.to(torch.float32).clone()
+    b[:, 0::2] *= scale_x
+    b[:, 1::2] *= scale_y
+    if not torch.isfinite(b).all():
+        raise AssertionError("Box tensor contains infinite or NaN!")   # Boxes.clip asserts
+    x1 = b[:, 0].clamp(min=0, max=out_w)
+    y1 = b[:, 1].clamp(min=0, max=out_h)
+    x2 = b[:, 2].clamp(min=0, max=out_w)
+    y2 = b[:, 3].clamp(min=0, max=out_h)
+    b = torch.stack((x1, y1, x2, y2), dim=-1)
+    keep = ((b[:, 2] - b[:, 0]) > 0) & ((b[:, 3] - b[:, 1]) > 0)
+    return b, keep
+
+
+def tile_words(boxes: torch.Tensor, H: int, W: int) -> int:
+    """Exact number of 32-pixel tile words the layout kernel will allocate for these
+    output-space boxes (host mirror of csrc/paste_measure.cu::tile_geometry)."""
+    if boxes.numel() == 0:
+        return 0
+    b = boxes.detach().to(torch.float32)
+    x0, y0, x1, y1 = b[:, 0], b[:, 1], b[:, 2], b[:, 3]
+    bw, bh = x1 - x0, y1 - y0
+    ok = (bw > 0) & (bh > 0) & torch.isfinite(b).all(dim=1)
+    mx = bw.double() / MASK_SIDE + 1.0
+    my = bh.double() / MASK_SIDE + 1.0
+    fa, fb = torch.floor(x0.double() - mx), torch.ceil(x1.double() + mx)
+    ga, gb = torch.floor(y0.double() - my), torch.ceil(y1.double() + my)
+    ok &= ~((fb < 0) | (ga > H - 1) | (fa > W - 1) | (gb < 0))
+    pxa = fa.clamp(min=0, max=W - 1).nan_to_num(0).long()
+    pxb = fb.clamp(min=0, max=W - 1).nan_to_num(0).long()
+    pya = ga.clamp(min=0, max=H - 1).nan_to_num(0).long()
+    pyb = gb.clamp(min=0, max=H - 1).nan_to_num(0).long()
+    tw = (pxb >> 5) - (pxa >> 5) + 1
+    th = pyb - pya + 1
+    words = torch.where(ok, tw * th, torch.zeros_like(tw))
+    return int(words.sum().item())
+
+
+# ----------------------------------------------------------------------------------
+# result table
+# ----------------------------------------------------------------------------------
+
+@dataclass
+class MeasurementTable:
+    """int64 [R, 20] + float64 [R, 30] measurement rows (schema.py)."""
+    ints: np.ndarray
+    floats: np.ndarray
+
+    INT_COLUMNS = INT_COLUMNS
+    FLOAT_COLUMNS = FLOAT_COLUMNS
+
+    def __len__(self) -> int:
+        return self.ints.shape[0]
+
+    def __getitem__(self, name: str) -> np.ndarray:
+        if name in ICOL:
+            return self.ints[:, ICOL[name]]
+        if name in FCOL:
+            return self.floats[:, FCOL[name]]
+        raise KeyError(name)
+
+    def select(self, mask) -> "MeasurementTable":
+        return MeasurementTable(self.ints[mask], self.floats[mask])
+
+    def for_class(self, class_id: int) -> "MeasurementTable":
+        return self.select(self["class_id"] == class_id)
+
+    def reference_rows(self, min_contour_area: float = 100.0) -> np.ndarray:
+        """K x 9 rows in the reference's CSV column order (nn_inference.py:561, :569) for the
+        instances that pass its ``contourArea < 100 -> skip`` cut (nn_inference.py:412)."""
+        ok = (self["valid"] == 1) & (self["contour_area"] >= min_contour_area)
+        cols = [FCOL[c] for c in CSV_SOURCE]
+        return self.floats[ok][:, cols]
+
+    @staticmethod
+    def empty() -> "MeasurementTable":
+        return MeasurementTable(np.zeros((0, NUM_INT), np.int64), np.zeros((0, NUM_FLOAT), np.float64))
+
+    @staticmethod
+    def concat(tables: Sequence["MeasurementTable"]) -> "MeasurementTable":
+        if not tables:
+            return MeasurementTable.empty()
+        return MeasurementTable(np.concatenate([t.ints for t in tables], axis=0),
+                                np.concatenate([t.floats for t in tables], axis=0))
+
+    def to_dataframe(self):
+        import pandas as pd
+        df = pd.DataFrame(self.ints, columns=list(INT_COLUMNS))
+        for j, c in enumerate(FLOAT_COLUMNS):
+            df[c] = self.floats[:, j]
+        return df
+
+
+# ----------------------------------------------------------------------------------
+# the engine: buffers + the C-ABI calls
+# ----------------------------------------------------------------------------------
+
+class Engine:
+    """Per-device cache of workspace / output buffers around the C ABI.
+
+    ``run`` enqueues layout + paste/measure + contour kernels on the current stream and
+    returns device tensors; nothing synchronises until the caller reads them."""
+
+    _engines = {}
+
+    @classmethod
+    def get(cls, device=None) -> "Engine":
+        device = _require_cuda(device)
+        e = cls._engines.get(device)
+        if e is None:
+            e = cls._engines[device] = Engine(device)
+        return e
+
+    def __init__(self, device: torch.device):
+        self.device = device
+        self.L = _lib.lib()
+        self._ws: Optional[torch.Tensor] = None
+        self._cap_words = 0
+        self._cap_n = 0
+        self.status = torch.zeros(4, dtype=torch.int64, device=device)
+        self.launches = 0            # kernels enqueued by this engine (for bench accounting)
+
+    def _workspace(self, n: int, words: int) -> torch.Tensor:
+        if self._ws is None or n > self._cap_n or words > self._cap_words:
+            cap_n = max(n, self._cap_n)
+            cap_w = max(int(words * 1.25) + 1024, self._cap_words)
+            nbytes = self.L.uwcv_workspace_bytes(cap_n, cap_w)
+            self._ws = None
+            self._ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+            self._cap_n, self._cap_words = cap_n, cap_w
+        return self._ws
+
+    def run(self, masks: torch.Tensor, boxes: torch.Tensor, H: int, W: int, *,
+            image_idx: Optional[torch.Tensor] = None, inst_idx: Optional[torch.Tensor] = None,
+            classes: Optional[torch.Tensor] = None, scores: Optional[torch.Tensor] = None,
+            threshold: float = 0.5, pixels_per_metric: float = 0.85,
+            planes: Optional[torch.Tensor] = None, n_tile_words: Optional[int] = None,
+            rows_i: Optional[torch.Tensor] = None, rows_f: Optional[torch.Tensor] = None):
+        """All tensors on ``self.device``, contiguous: masks [N,28,28] f32, boxes [N,4] f32
+        (output space), image_idx/inst_idx int32, classes int64, scores f32,
+        planes None or uint32/int32 [N, H, plane_row_words(W)].
+        Returns (rows_i [N,20] int64, rows_f [N,30] float64, status [4] int64)."""
+        n = int(boxes.shape[0])
+        dev = self.device
+        if rows_i is None:
+            rows_i = torch.empty((n, NUM_INT), dtype=torch.int64, device=dev)
+        if rows_f is None:
+            rows_f = torch.empty((n, NUM_FLOAT), dtype=torch.float64, device=dev)
+        if n_tile_words is None:
+            n_tile_words = tile_words(boxes, H, W)
+        ws = self._workspace(n, n_tile_words)
+        with torch.cuda.device(dev):
+            rc = self.L.uwcv_paste_measure(
+                _ptr(masks), _ptr(boxes), _ptr(image_idx), _ptr(inst_idx), _ptr(classes),
+                _ptr(scores), n, int(H), int(W), float(threshold), float(pixels_per_metric),
+                _ptr(planes), _ptr(rows_i), _ptr(rows_f), _ptr(ws), ws.numel(),
+                _ptr(self.status), _stream_ptr(dev))
+        _lib.check(rc, "uwcv_paste_measure")
+        self.launches += 3 if n > 0 else 0
+        return rows_i, rows_f, self.status
+
+    def check_status(self) -> None:
+        """Synchronising read of the device status word; raises on workspace overflow."""
+        st = self.status.cpu()
+        if int(st[0]) != 0:
+            raise _lib.UwcvError(int(st[0]), f"uwcv_paste_measure (needs {int(st[1])} tile words)")
+
+    def alloc_planes(self, n: int, H: int, W: int) -> torch.Tensor:
+        wpr = self.L.uwcv_plane_row_words(int(W))
+        return torch.empty((n, H, wpr), dtype=torch.int32, device=self.device)
+
+    def unpack(self, planes: torch.Tensor, H: int, W: int) -> torch.Tensor:
+        n = int(planes.shape[0])
+        out = torch.empty((n, H, W), dtype=torch.bool, device=self.device)
+        with torch.cuda.device(self.device):
+            rc = self.L.uwcv_unpack_planes(_ptr(planes), n, int(H), int(W), _ptr(out),
+                                           _stream_ptr(self.device))
+        _lib.check(rc, "uwcv_unpack_planes")
+        self.launches += 1 if n > 0 else 0
+        return out
+
+    def nms(self, boxes: torch.Tensor, scores: torch.Tensor, classes: torch.Tensor,
+            image_off: Sequence[int], score_thresh: float, nms_thresh: float, topk: int):
+        """boxes [R,4] f32, scores [R] f32, classes [R] i64 on device; image_off host ints [B+1].
+        Returns (keep [R] int64, keep_count [B] int32) device tensors."""
+        B = len(image_off) - 1
+        off = (C.c_int64 * (B + 1))(*[int(v) for v in image_off])
+        R = int(image_off[-1])
+        dev = self.device
+        keep = torch.empty(max(R, 1), dtype=torch.int64, device=dev)
+        cnt = torch.zeros(max(B, 1), dtype=torch.int32, device=dev)
+        nbytes = self.L.uwcv_nms_workspace_bytes(off, B)
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        with torch.cuda.device(dev):
+            rc = self.L.uwcv_nms_filter(_ptr(boxes), _ptr(scores), _ptr(classes), off, B,
+                                        float(score_thresh), float(nms_thresh), int(topk),
+                                        _ptr(keep), _ptr(cnt), _ptr(ws), ws.numel(),
+                                        _stream_ptr(dev))
+        _lib.check(rc, "uwcv_nms_filter")
+        self.launches += 4 if R > 0 else 3
+        self._nms_ws = ws           # keep alive until the stream has consumed it
+        return keep, cnt
+
+
+# ----------------------------------------------------------------------------------
+# Detectron2-shaped entry points
+# ----------------------------------------------------------------------------------
+
+def _as_box_tensor(boxes) -> torch.Tensor:
+    return boxes.tensor if hasattr(boxes, "tensor") else boxes
+
+
+def paste_masks_in_image(masks: torch.Tensor, boxes, image_shape: Tuple[int, int],
+                         threshold: float = 0.5, *, packed: bool = False,
+                         device=None) -> torch.Tensor:
+    """detectron2.layers.mask_ops.paste_masks_in_image: N x Hm x Wm probabilities + N x 4
+    boxes (already in image coordinates) -> N x H x W bool on the CUDA device.
+    ``packed=True`` returns the bit-planes [N, H, plane_row_words(W)] int32 instead."""
+    if masks.shape[-1] != masks.shape[-2]:
+        raise AssertionError("Only square mask predictions are supported")
+    if masks.shape[-1] != MASK_SIDE and len(masks) > 0:
+        raise ValueError(f"uwcv is built for {MASK_SIDE}x{MASK_SIDE} mask heads, got {tuple(masks.shape)}")
+    if not threshold > 0:
+        raise ValueError("uwcv requires a positive mask threshold (Detectron2's soft-mask "
+                         "mode threshold < 0 is not part of the reference path)")
+    boxes = _as_box_tensor(boxes)
+    if len(boxes) != len(masks):
+        raise AssertionError(boxes.shape)
+    H, W = int(image_shape[0]), int(image_shape[1])
+    dev = _require_cuda(device if device is not None else
+                        (boxes.device if boxes.is_cuda else None))
+    eng = Engine.get(dev)
+    n = len(masks)
+    if n == 0:
+        if packed:
+            return eng.alloc_planes(0, H, W)
+        return torch.zeros((0, H, W), dtype=torch.bool, device=dev)
+    m = masks.reshape(n, MASK_SIDE, MASK_SIDE).to(dev, torch.float32).contiguous()
+    b = boxes.to(dev, torch.float32).contiguous()
+    planes = eng.alloc_planes(n, H, W)
+    eng.run(m, b, H, W, threshold=threshold, planes=planes)
+    eng.check_status()
+    return planes if packed else eng.unpack(planes, H, W)
+
+
+def detector_postprocess(results, output_height: int, output_width: int,
+                         mask_threshold: float = 0.5) -> Instances:
+    """detectron2.modeling.postprocessing.detector_postprocess: rescale boxes to the output
+    size, clip, drop empty ones, paste ``pred_masks`` (N x 1 x 28 x 28) to N x H x W bool."""
+    fields = dict(results.get_fields()) if hasattr(results, "get_fields") else dict(results._fields)
+    box_key = "pred_boxes" if "pred_boxes" in fields else "proposal_boxes"
+    if box_key not in fields:
+        raise AssertionError("Predictions must contain boxes!")
+    b, keep = scale_clip_boxes(_as_box_tensor(fields[box_key]), results.image_size,
+                               (output_height, output_width))
+    out = Instances((output_height, output_width))
+    for k, v in fields.items():
+        if k == box_key:
+            out.set(k, Boxes(b[keep]))
+        else:
+            out.set(k, v[keep])
+    if out.has("pred_masks"):
+        pm = out.pred_masks
+        out.remove("pred_masks")
+        out.set("pred_masks", paste_masks_in_image(pm[:, 0, :, :], out.get(box_key).tensor,
+                                                   (output_height, output_width),
+                                                   threshold=mask_threshold))
+    return out
+
+
+def fast_rcnn_inference_single_image(boxes: torch.Tensor, scores: torch.Tensor,
+                                     image_shape: Tuple[int, int], score_thresh: float,
+                                     nms_thresh: float, topk_per_image: int, device=None):
+    """detectron2 fast_rcnn_inference_single_image: boxes R x (K*4) (or R x 4), scores
+    R x (K+1) with the background column last.  Returns (Instances, kept proposal rows)."""
+    dev = _require_cuda(device if device is not None else (boxes.device if boxes.is_cuda else None))
+    boxes = boxes.to(dev, torch.float32)
+    scores = scores.to(dev, torch.float32)
+    valid = torch.isfinite(boxes).all(dim=1) & torch.isfinite(scores).all(dim=1)
+    rows = torch.arange(boxes.shape[0], device=dev)
+    if not bool(valid.all()):
+        boxes, scores, rows = boxes[valid], scores[valid], rows[valid]
+    scores = scores[:, :-1]
+    R, K = scores.shape
+    nreg = boxes.shape[1] // 4
+    h, w = image_shape
+    bx = boxes.reshape(-1, 4)
+    bx = torch.stack((bx[:, 0].clamp(min=0, max=w), bx[:, 1].clamp(min=0, max=h),
+                      bx[:, 2].clamp(min=0, max=w), bx[:, 3].clamp(min=0, max=h)), dim=-1)
+    bx = bx.view(R, nreg, 4)
+    if nreg == 1:
+        bx = bx.expand(R, K, 4)
+    cand_boxes = bx.reshape(R * K, 4).contiguous()           # candidate (r, k) at row r*K + k
+    cand_scores = scores.reshape(R * K).contiguous()
+    cand_cls = torch.arange(K, device=dev, dtype=torch.int64).repeat(R)
+    eng = Engine.get(dev)
+    keep, cnt = eng.nms(cand_boxes, cand_scores, cand_cls, [0, R * K], score_thresh, nms_thresh,
+                        topk_per_image)
+    k = int(cnt[0].item())
+    keep = keep[:k]
+    res = Instances(tuple(image_shape))
+    res.pred_boxes = Boxes(cand_boxes[keep])
+    res.scores = cand_scores[keep]
+    res.pred_classes = cand_cls[keep]
+    return res, rows[keep // K]
+
+
+# ----------------------------------------------------------------------------------
+# measurement entry (GetMask_Contours / GetCounts replacement)
+# ----------------------------------------------------------------------------------
+
+def _gather_fields(inst, classes_of_interest):
+    boxes = _as_box_tensor(inst.pred_boxes)
+    scores = inst.scores
+    classes = inst.pred_classes
+    masks = inst.pred_masks
+    if masks.dim() == 4:
+        masks = masks[:, 0]
+    if classes_of_interest is not None:
+        sel = torch.zeros(len(classes), dtype=torch.bool, device=classes.device)
+        for c in classes_of_interest:
+            sel |= classes == int(c)
+        boxes, scores, classes, masks = boxes[sel], scores[sel], classes[sel], masks[sel]
+    return boxes, scores, classes, masks
+
+
+def measure_instances(instances: Union[object, Sequence[object]],
+                      output_size: Optional[Tuple[int, int]] = None,
+                      classes_of_interest: Optional[Sequence[int]] = None, *,
+                      mask_threshold: float = 0.5, pixels_per_metric: float = 0.85,
+                      image_idx_offset: int = 0, return_planes: bool = False,
+                      write_planes: bool = False, device=None):
+    """Per-instance measurement rows for one image or a batch of images.
+
+    ``instances``: a Detectron2-style ``Instances`` (or a list of them, one per image)
+    holding the RAW predictor output -- ``pred_boxes`` in network-input coordinates
+    (``image_size``), ``scores``, ``pred_classes`` and ``pred_masks`` as N x 1 x 28 x 28
+    probabilities -- on the CPU (pinned memory is used as is) or on the CUDA device.
+    ``output_size`` (H, W) is the original image size the boxes are rescaled to
+    (``detector_postprocess``); default: each ``image_size``.  All images of one call must
+    share the output size.  ``classes_of_interest`` keeps only those classes
+    (nn_inference.py:379).  Returns a ``MeasurementTable`` (and the device bit-planes when
+    ``return_planes``); an empty selection returns an empty table (the reference prints
+    and returns, nn_inference.py:383-385).
+    """
+    single = not isinstance(instances, (list, tuple))
+    batch: List[object] = [instances] if single else list(instances)
+    dev = _require_cuda(device)
+    eng = Engine.get(dev)
+    if not batch:
+        return MeasurementTable.empty()
+    H, W = (int(output_size[0]), int(output_size[1])) if output_size is not None else \
+        tuple(int(v) for v in batch[0].image_size)
+
+    bl, sl, cl, ml, il, jl = [], [], [], [], [], []
+    for k, inst in enumerate(batch):
+        boxes, scores, classes, masks = _gather_fields(inst, classes_of_interest)
+        out_sz = (H, W)
+        if output_size is None and tuple(int(v) for v in inst.image_size) != out_sz:
+            raise ValueError("all images of one call must share the output size")
+        b, keep = scale_clip_boxes(boxes, inst.image_size, out_sz)
+        nk = int(keep.sum().item()) if keep.numel() else 0
+        if nk != keep.numel():
+            b, scores, classes, masks = b[keep], scores[keep], classes[keep], masks[keep]
+        bl.append(b)
+        sl.append(scores.to(torch.float32))
+        cl.append(classes.to(torch.int64))
+        ml.append(masks.to(torch.float32).reshape(-1, MASK_SIDE, MASK_SIDE))
+        il.append(torch.full((nk,), image_idx_offset + k, dtype=torch.int32))
+        jl.append(torch.arange(nk, dtype=torch.int32))
+    boxes = torch.cat(bl)
+    n = int(boxes.shape[0])
+    if n == 0:
+        return (MeasurementTable.empty(), None) if return_planes else MeasurementTable.empty()
+    words = tile_words(boxes, H, W)
+    nb = dict(non_blocking=True)
+    d_boxes = boxes.contiguous().to(dev, **nb)
+    d_scores = torch.cat(sl).contiguous().to(dev, **nb)
+    d_classes = torch.cat(cl).contiguous().to(dev, **nb)
+    d_masks = (ml[0] if len(ml) == 1 else torch.cat(ml)).contiguous().to(dev, **nb)
+    d_img = torch.cat(il).to(dev, **nb)
+    d_inst = torch.cat(jl).to(dev, **nb)
+    planes = eng.alloc_planes(n, H, W) if (return_planes or write_planes) else None
+    rows_i, rows_f, status = eng.run(d_masks, d_boxes, H, W, image_idx=d_img, inst_idx=d_inst,
+                                     classes=d_classes, scores=d_scores,
+                                     threshold=mask_threshold,
+                                     pixels_per_metric=pixels_per_metric, planes=planes,
+                                     n_tile_words=words)
+    hi, hf = rows_i.cpu(), rows_f.cpu()          # device -> host read of the result
+    eng.check_status()
+    table = MeasurementTable(hi.numpy(), hf.numpy())
+    return (table, planes) if return_planes else table
+
+
+def get_counts(instances) -> List[int]:
+    """What GetCounts (nn_inference.py:355-366) is meant to produce: instances per class id
+    0..3 (the reference compares against ids 1..4 and duplicates ``classes == 3``)."""
+    from .schema import CLASS_NAMES
+    c = instances.pred_classes
+    c = c.cpu().numpy() if hasattr(c, "cpu") else np.asarray(c)
+    return [int((c == k).sum()) for k in range(len(CLASS_NAMES))]
