@@ -1,0 +1,369 @@
+#!/usr/bin/env python
+"""Benchmark of the uw-com-vision post-inference hot path on B200.
+
+    python bench.py --gpus N --steps K --warmup W            our arm (CUDA, C ABI)
+    python bench.py --impl reference --gpus N --steps K ...  the reference's CPU path
+
+Workload (BASELINE.json configs[1]): per GPU a batch of 64 synthetic 2048 x 2048 images
+with 1000 Mask R-CNN-shaped instances each (28 x 28 mask probabilities, boxes, scores,
+classes; uwcv/synth.py).  One step = one pass of the hot path over that batch:
+tile layout -> fused paste / threshold / bit-pack (Detectron2-literal full-frame
+planes, 1 bit / pixel) / moments -> border trace + descriptors; at N > 1 ranks an
+all-gather of the measurement table follows (image-sharded, weak scaling).
+
+Printed JSON keys (driver contract): metric/value/unit (instances measured per second,
+whole job), ms_per_step, mp_per_sec, e2e (same metric through uwcv.measure_instances
+with pinned HOST inputs: H2D of the step's inputs and D2H of the rows inside the timed
+region), roofline (paste kernel, algorithmic bytes / live CUDA-event time vs measured
+HBM peak), cpu_baseline (the reference's CPU path on a bounded sample, N = 1 only),
+gpu_launches, clocks.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "uw-com-vision_b200")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+H = W = 2048
+IMAGES_PER_GPU = 64
+INSTANCES_PER_IMAGE = 1000
+METRIC = "instances_measured_per_sec"
+UNIT = "instances/s"
+WORKLOAD = "configs[1]: 64 synthetic 2048x2048 images x 1000 instances per GPU, full-frame bit-planes"
+
+
+def algorithmic_bytes_per_instance(h: int, w: int) -> int:
+    """SURVEY.md 8(d), full-frame contract: read 3136 (probs) + 16 (box) + 4 (score) +
+    8 (class) + 4 (image idx); write H*W/8 (bit-plane) + 400 (row)."""
+    return 3168 + h * w // 8 + 400
+
+
+def measured_peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured"
+        except Exception:
+            pass
+    return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-lms", "100", "-i", str(self.index)],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
+                                "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None,
+                "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------
+# reference arm: the reference's own CPU implementation of the path
+# ---------------------------------------------------------------------------------------
+
+def reference_step(inst, out_size, literal_paint=True):
+    """What the reference script does per image after the forward pass: Detectron2
+    post-process (paste all N masks to N x H x W bool, nn_inference.py:372) once, then
+    GetMask_Contours for each of the four class keywords (nn_inference.py:487-496) with the
+    literal union-paint loop (:399-401).  (The script repeats the post-process 12 times per
+    image; one is charged here.)  Returns the number of instances processed."""
+    from oracle import d2, measure as M, pipeline as P
+    o = P.to_oracle_instances(inst)
+    res = d2.detector_postprocess(o, out_size[0], out_size[1], 0.5)
+    classes = res.pred_classes.numpy()
+    masks = res.pred_masks.numpy()
+    rows = 0
+    for k in range(len(M.KEYWORDS)):
+        try:
+            r = M.get_mask_contours((out_size[0], out_size[1], 3), classes, masks, [k],
+                                    literal_paint=literal_paint)
+        except ValueError:
+            r = None
+        rows += 0 if r is None else len(r)
+    return len(res), rows
+
+
+def cpu_sample_size(steps: int, warmup: int) -> int:
+    return int(min(INSTANCES_PER_IMAGE, max(25, INSTANCES_PER_IMAGE * 3 // max(steps + warmup, 1))))
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from uwcv import synth
+    n = cpu_sample_size(args.steps, args.warmup)
+    inst = synth.blob_instances(0, n, H, W, seed=1234)
+    for _ in range(args.warmup):
+        reference_step(inst, (H, W))
+    t0 = time.perf_counter()
+    done = 0
+    for _ in range(args.steps):
+        k, _rows = reference_step(inst, (H, W))
+        done += k
+    dt = time.perf_counter() - t0
+    val = done / dt
+    sample = f"1 image 2048x2048 x {n} instances per step (detector_postprocess + 4 x GetMask_Contours)"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / max(args.steps, 1) * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": {"workload": WORKLOAD, "sample": sample},
+        "mp_per_sec": args.steps * H * W / 1e6 / dt,
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": torch.get_num_threads(),
+                         "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------
+
+def run_ours(args):
+    import torch.distributed as dist
+    import uwcv
+    from uwcv import api, dist as udist, synth
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py (our arm) needs a CUDA device"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    n_img, n_inst = args.images, args.instances
+    # weak scaling: rank r owns images r, r + world, ... of a (n_img * world)-image set
+    batch = synth.blob_batch(n_img, n_inst, H, W, seed=1234, first_image=rank, stride=world)
+    for inst in batch:                                  # pinned host copies for the e2e leg
+        for k, v in list(inst.get_fields().items()):
+            if isinstance(v, torch.Tensor):
+                inst.set(k, v.pin_memory())
+            else:
+                inst.set(k, uwcv.Boxes(v.tensor.pin_memory()))
+    eng = api.Engine.get(dev)
+
+    # ---- device-resident inputs for `value` ------------------------------------------
+    boxes = torch.cat([api.scale_clip_boxes(b.pred_boxes.tensor, (H, W), (H, W))[0] for b in batch])
+    n = int(boxes.shape[0])
+    words = api.tile_words(boxes, H, W)
+    d_boxes = boxes.to(dev)
+    d_masks = torch.cat([b.pred_masks[:, 0] for b in batch]).contiguous().to(dev)
+    d_scores = torch.cat([b.scores for b in batch]).to(dev)
+    d_classes = torch.cat([b.pred_classes for b in batch]).to(dev)
+    d_img = torch.cat([torch.full((len(b),), rank + i * world, dtype=torch.int32)
+                       for i, b in enumerate(batch)]).to(dev)
+    d_inst = torch.cat([torch.arange(len(b), dtype=torch.int32) for b in batch]).to(dev)
+    planes = eng.alloc_planes(n, H, W)
+    rows_i = torch.empty((n, 20), dtype=torch.int64, device=dev)
+    rows_f = torch.empty((n, 30), dtype=torch.float64, device=dev)
+    counts = None
+    if world > 1:
+        c = torch.tensor([n], dtype=torch.int64, device=dev)
+        cs = torch.empty(world, dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(cs, c)
+        counts = cs.cpu().tolist()
+    total_instances = sum(counts) if counts else n
+
+    def step(stages=7):
+        eng.run(d_masks, d_boxes, H, W, image_idx=d_img, inst_idx=d_inst, classes=d_classes,
+                scores=d_scores, planes=planes, n_tile_words=words, rows_i=rows_i, rows_f=rows_f,
+                stages=stages)
+        if world > 1 and stages == 7:
+            return udist.all_gather_table(rows_i, rows_f, counts=counts)
+        return rows_i, rows_f
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    eng.check_status()
+
+    # ---- timed region: exactly K steps, CUDA events, max over ranks -------------------
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = eng.launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = eng.launches - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    value = args.steps * total_instances / (ms * 1e-3)
+
+    # ---- per-kernel times (live CUDA events on the launching stream) -------------------
+    reps = max(3, min(args.steps, 10))
+    kt = {1: [], 2: [], 4: []}
+    for _ in range(reps):
+        for st in (1, 2, 4):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            step(st)
+            b.record()
+            b.synchronize()
+            kt[st].append(a.elapsed_time(b))
+    k_layout, k_paste, k_contour = (statistics.mean(kt[s]) for s in (1, 2, 4))
+    peak, peak_src = measured_peak_gbs()
+    bpi = algorithmic_bytes_per_instance(H, W)
+    achieved = n * bpi / (k_paste * 1e-3) / 1e9
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "paste_kernel_traffic.json")
+    if os.path.exists(tp):
+        try:
+            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+
+    # ---- e2e: the public call with pinned host inputs -----------------------------------
+    h2d = sum(int(b.pred_masks.numel()) * 4 + len(b) * (16 + 4 + 8 + 4 + 4) for b in batch)
+    d2h = n * (20 * 8 + 30 * 8) + 32
+    del planes
+    for _ in range(2):
+        uwcv.measure_instances(batch, (H, W), write_planes=True, gather=world > 1, device=dev)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        table = uwcv.measure_instances(batch, (H, W), write_planes=True, gather=world > 1,
+                                       device=dev)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e_val = args.steps * total_instances / e2e_s
+
+    # ---- CPU baseline (rank 0, N = 1 only) ------------------------------------------------
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        nc = 250
+        sample = synth.blob_instances(0, nc, H, W, seed=1234)
+        t0 = time.perf_counter()
+        done, _ = reference_step(sample, (H, W))
+        dt = time.perf_counter() - t0
+        cpu = {"value": done / dt, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+               "sample": f"1 image 2048x2048 x {nc} instances, detector_postprocess + "
+                         f"4 x GetMask_Contours (oracle restatement), {dt:.1f} s"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": WORKLOAD, "images_per_gpu": n_img,
+                       "instances_per_image": n_inst, "image": f"{H}x{W}",
+                       "instances_per_gpu": n, "mask_output": "full-frame bit-planes in HBM",
+                       "l2": "inputs (200 MB) and outputs (33.5 GB) per step exceed the 126 MB L2",
+                       "collective": "all_gather of the row table" if world > 1 else "none"},
+            "mp_per_sec": args.steps * world * n_img * H * W / 1e6 / (ms * 1e-3),
+            "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "ms_per_step": e2e_s / args.steps * 1e3},
+            "gpu_launches": launches,
+            "kernel_ms": {"layout": k_layout, "paste_measure": k_paste, "contour": k_contour},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                         "kernel": "paste_measure_kernel<true>",
+                         "bytes_per_instance": bpi, "instances_per_launch": n,
+                         "frac_of_nominal_8000": achieved / 8000.0},
+            "clocks": clocks,
+        }
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--images", type=int, default=IMAGES_PER_GPU)
+    ap.add_argument("--instances", type=int, default=INSTANCES_PER_IMAGE)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -93,6 +93,20 @@ int uwcv_paste_measure(const float* masks, const float* boxes, const int32_t* im
                        void* workspace, size_t ws_bytes, int64_t* status, void* stream);
 
 /*
+ * uwcv_paste_measure_stages -- the same call split by kernel, for profiling and for
+ * callers that interleave their own work: `stages` is a bit mask, 1 = tile layout,
+ * 2 = paste + threshold + bit-pack + raw moments, 4 = border trace + descriptors.
+ * Stages must be issued in that order on one stream with identical arguments;
+ * uwcv_paste_measure is stages = 7.
+ */
+int uwcv_paste_measure_stages(const float* masks, const float* boxes, const int32_t* image_idx,
+                              const int32_t* inst_idx, const int64_t* classes,
+                              const float* scores, int64_t N, int H, int W, float thr,
+                              double pixels_per_metric, uint32_t* bitplanes, int64_t* rows_i,
+                              double* rows_f, void* workspace, size_t ws_bytes, int64_t* status,
+                              void* stream, int stages);
+
+/*
  * uwcv_unpack_planes -- expand bit-planes into the Detectron2-literal N x H x W bool
  * tensor (one byte per pixel), for callers that read pred_masks as such
  * (nn_inference.py:326, :376).

@@ -1,0 +1,308 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle.
+
+Bar: bit-exact for masks, pixel areas, bboxes, raw moments, contour counts / points and
+instance counts; float columns within 1e-5 relative (most are expected bit-exact, the
+test reports how many are)."""
+import os
+import zlib
+
+import numpy as np
+import pytest
+import torch
+
+import uwcv
+from uwcv import api, schema, synth
+from oracle import d2, measure as M, pipeline as P
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-5      # north_star tolerance for float measurements
+IC, FC = schema.ICOL, schema.FCOL
+
+
+def compare_tables(table, ri, rf, skip_int=()):
+    assert table.ints.shape == ri.shape and table.floats.shape == rf.shape
+    for name, j in IC.items():
+        if name in skip_int:
+            continue
+        bad = np.flatnonzero(table.ints[:, j] != ri[:, j])
+        assert bad.size == 0, f"int column {name}: {bad.size} rows differ, first {bad[:5]}: " \
+                              f"{table.ints[bad[:5], j]} vs {ri[bad[:5], j]}"
+    exact = 0
+    m00 = np.maximum(ri[:, IC["area_px"]].astype(np.float64), 1.0)
+    for name, j in FC.items():
+        a, b = table.floats[:, j], rf[:, j]
+        assert np.array_equal(np.isnan(a), np.isnan(b)), name
+        ok = ~np.isnan(b)
+        a, b = a[ok], b[ok]
+        exact += int(np.array_equal(a, b))
+        scale = np.abs(b)
+        if name in ("mu30", "mu21", "mu12", "mu03"):
+            # third-order central moments cancel to ~0 for symmetric blobs: floor at the
+            # rounding noise of the subtraction (|m_pq| * eps) relative to m00 * r^3
+            scale = np.maximum(scale, m00[ok] ** 2.5 * 1e-6)
+        if name in ("mu11", "ell_theta"):
+            scale = np.maximum(scale, 1e-6 * (m00[ok] ** 2 if name == "mu11" else 1.0))
+        err = np.abs(a - b)
+        lim = RTOL * scale + 1e-300
+        bad = np.flatnonzero(err > lim)
+        assert bad.size == 0, f"float column {name}: {bad.size} rows off, first {bad[:5]}: " \
+                              f"{a[bad[:5]]} vs {b[bad[:5]]}"
+    return exact
+
+
+def plane_crcs(planes):
+    p = planes.cpu().numpy().view(np.uint32)
+    return np.array([zlib.crc32(p[i].tobytes()) for i in range(p.shape[0])], dtype=np.int64)
+
+
+# ---------------------------------------------------------------------------------------
+def test_golden_blobs_rows_and_planes(golden_dir):
+    g = np.load(os.path.join(golden_dir, "blobs_small.npz"))
+    H, W = int(g["H"]), int(g["W"])
+    batch = [synth.blob_instances(k, 40, 256, 333, seed=77, size_range=(4.0, 90.0)) for k in range(3)]
+    table, planes = uwcv.measure_instances(batch, (H, W), return_planes=True)
+    exact = compare_tables(table, g["rows_i"], g["rows_f"])
+    assert np.array_equal(plane_crcs(planes), g["plane_crc"])
+    print(f"blobs_small: {exact}/{schema.NUM_FLOAT} float columns bit-exact")
+    assert exact >= 24
+
+
+def test_golden_c1_maskrcnn(golden_dir):
+    """Config 1: raw random-init Mask R-CNN head output (sub-pixel boxes, saturated
+    probabilities, empty and multi-component masks)."""
+    g = np.load(os.path.join(golden_dir, "c1_maskrcnn.npz"))
+    inst = uwcv.Instances((1024, 1024))
+    inst.pred_boxes = uwcv.Boxes(torch.from_numpy(g["boxes"]))
+    inst.scores = torch.from_numpy(g["scores"])
+    inst.pred_classes = torch.from_numpy(g["classes"])
+    inst.pred_masks = torch.from_numpy(g["masks"])
+    table, planes = uwcv.measure_instances(inst, (1024, 1024), return_planes=True)
+    assert len(table) == 200
+    exact = compare_tables(table, g["rows_i"], g["rows_f"])
+    assert np.array_equal(plane_crcs(planes), g["plane_crc"])
+    print(f"c1: {exact}/{schema.NUM_FLOAT} float columns bit-exact; "
+          f"{int((table['valid'] == 0).sum())} empty masks, max contours {table['n_contours'].max()}")
+    # cropped mode (no planes) gives the same rows
+    t2 = uwcv.measure_instances(inst, (1024, 1024))
+    assert np.array_equal(t2.ints, table.ints) and np.array_equal(t2.floats, table.floats, equal_nan=True)
+
+
+def test_paste_drop_in_equals_detectron2_restatement():
+    torch.manual_seed(3)
+    H, W = 200, 333                                       # W not a multiple of 32
+    n = 60
+    inst = synth.blob_instances(5, n, H, W, seed=11, size_range=(2.0, 150.0))
+    masks = inst.pred_masks[:, 0]
+    boxes = inst.pred_boxes.tensor
+    ref = d2.paste_masks_in_image(masks, boxes, (H, W))
+    out = uwcv.paste_masks_in_image(masks, boxes, (H, W))
+    assert out.dtype == torch.bool and out.is_cuda and tuple(out.shape) == (len(masks), H, W)
+    assert torch.equal(out.cpu(), ref)
+    # other thresholds
+    for thr in (0.3, 0.7):
+        assert torch.equal(uwcv.paste_masks_in_image(masks, boxes, (H, W), thr).cpu(),
+                           d2.paste_masks_in_image(masks, boxes, (H, W), thr))
+    # known answers
+    ones = uwcv.paste_masks_in_image(torch.ones(1, 28, 28), torch.tensor([[10., 20., 50., 60.]]), (100, 100))
+    assert int(ones.sum()) == 1600 and bool(ones[0, 20:60, 10:50].all())
+    half = uwcv.paste_masks_in_image(torch.full((1, 28, 28), 0.5),
+                                     torch.tensor([[10.5, 20.5, 50.5, 60.5]]), (100, 100))
+    assert int(half.sum()) == 1509
+    assert uwcv.paste_masks_in_image(torch.zeros(0, 28, 28), torch.zeros(0, 4), (8, 8)).shape == (0, 8, 8)
+    with pytest.raises(ValueError):
+        uwcv.paste_masks_in_image(masks, boxes, (H, W), threshold=0.0)
+
+
+def test_paste_edge_boxes():
+    """Sub-pixel, border-clipped, frame-filling and huge-coordinate boxes; saturated maps."""
+    H, W = 96, 160
+    boxes = torch.tensor([
+        [0., 0., 1e-30, 5.],            # positive-but-tiny width
+        [3., 4., 3.001, 9.],
+        [10.2, 10.2, 10.7, 30.],        # 0.5 px wide
+        [0., 0., 160., 96.],            # whole frame
+        [150.5, 80.5, 160., 96.],       # touches the bottom-right corner
+        [0., 0., 7.3, 2.2],
+        [31.5, 0., 32.5, 96.],          # straddles a word boundary
+        [63.9, 10., 96.1, 50.],
+        [20., 95.4, 100., 96.],
+    ])
+    g = torch.Generator().manual_seed(0)
+    masks = torch.rand(len(boxes), 28, 28, generator=g)
+    masks[3] = (masks[3] > 0.5).float()
+    masks[4] = 1.0
+    masks[7] = 0.5
+    ref = d2.paste_masks_in_image(masks, boxes, (H, W))
+    out = uwcv.paste_masks_in_image(masks, boxes, (H, W)).cpu()
+    assert torch.equal(out, ref)
+
+
+def test_detector_postprocess_drop_in():
+    inst = synth.blob_instances(2, 50, 256, 333, seed=5, size_range=(3.0, 120.0))
+    inst.pred_boxes.tensor[3] = torch.tensor([10., 10., 10., 40.])      # empty -> dropped
+    ref = d2.detector_postprocess(P.to_oracle_instances(inst), 320, 416)
+    out = uwcv.detector_postprocess(inst, 320, 416)
+    assert len(out) == len(ref) == 49
+    assert out.image_size == (320, 416)
+    assert torch.equal(out.pred_boxes.tensor.cpu(), ref.pred_boxes.tensor)
+    assert torch.equal(out.pred_masks.cpu(), ref.pred_masks)
+    assert torch.equal(out.pred_classes.cpu(), ref.pred_classes)
+    assert torch.equal(out._fields["scores"].cpu(), ref.scores)
+
+
+def test_measure_classes_of_interest_and_empty():
+    batch = [synth.blob_instances(k, 30, 200, 200, seed=21) for k in range(2)]
+    full = uwcv.measure_instances(batch, (200, 200))
+    for cls in range(4):
+        t = uwcv.measure_instances(batch, (200, 200), classes_of_interest=[cls])
+        sel = full.for_class(cls)
+        skip = IC["inst_idx"]
+        cols = [j for j in range(schema.NUM_INT) if j != skip]
+        assert np.array_equal(t.ints[:, cols], sel.ints[:, cols])
+        assert np.array_equal(t.floats, sel.floats, equal_nan=True)
+        ri, rf = P.oracle_table(batch, (200, 200), classes_of_interest=[cls])
+        compare_tables(t, ri, rf)
+    assert len(uwcv.measure_instances(batch, (200, 200), classes_of_interest=[9])) == 0
+    assert len(uwcv.measure_instances([], (200, 200))) == 0
+    # instance counts per class == what GetCounts intends
+    counts = [sum(uwcv.get_counts(b)[k] for b in batch) for k in range(4)]
+    assert counts == [int((full["class_id"] == k).sum()) for k in range(4)]
+
+
+def test_reference_literal_union_rows_for_disjoint_instances():
+    """When instances of a class do not touch, the reference's union-contour rows
+    (GetMask_Contours) are exactly the per-instance rows sorted left to right."""
+    H = W = 400
+    n = 9
+    inst = uwcv.Instances((H, W))
+    cx = torch.tensor([50., 150., 250.]).repeat(3) + torch.tensor([0., 7., 13.]).repeat_interleave(3)
+    cy = torch.tensor([60., 180., 300.]).repeat_interleave(3)
+    half = torch.linspace(22, 40, n)
+    inst.pred_boxes = uwcv.Boxes(torch.stack([cx - half, cy - half * 0.8, cx + half, cy + half * 0.8], 1))
+    inst.scores = torch.linspace(0.9, 0.5, n)
+    inst.pred_classes = torch.zeros(n, dtype=torch.int64)
+    lin = (torch.arange(28, dtype=torch.float32) + 0.5) / 28 * 2 - 1
+    yy, xx = torch.meshgrid(lin, lin, indexing="ij")
+    ang = torch.linspace(0, 2.5, n)[:, None, None]
+    u = xx * torch.cos(ang) + yy * torch.sin(ang)
+    v = -xx * torch.sin(ang) + yy * torch.cos(ang)
+    inst.pred_masks = torch.sigmoid(9 * (0.8 - torch.sqrt((u / 0.9) ** 2 + (v / 0.55) ** 2)))[:, None]
+    rows_ref = P.reference_literal_rows(inst, (H, W), [0])
+    t = uwcv.measure_instances(inst, (H, W), classes_of_interest=[0])
+    assert (t["n_contours"] == 1).all()
+    order = np.argsort(t["bbox_x0"], kind="stable")
+    mine = t.select(order).reference_rows()
+    assert mine.shape == rows_ref.shape
+    assert np.allclose(mine, rows_ref, rtol=1e-6, atol=0)
+
+
+def test_workspace_overflow_is_reported():
+    eng = api.Engine.get()
+    inst = synth.blob_instances(0, 20, 128, 128, seed=3)
+    b, keep = api.scale_clip_boxes(inst.pred_boxes.tensor, (128, 128), (128, 128))
+    dev = eng.device
+    with pytest.raises(RuntimeError, match="tile words"):
+        old = (eng._ws, eng._cap_n, eng._cap_words)
+        try:
+            eng._ws = torch.empty(eng.L.uwcv_workspace_bytes(20, 8), dtype=torch.uint8, device=dev)
+            eng._cap_n, eng._cap_words = 20, 10 ** 9          # pretend it is big enough
+            eng.run(inst.pred_masks[:, 0].contiguous().to(dev), b.contiguous().to(dev), 128, 128,
+                    n_tile_words=8)
+            eng.check_status()
+        finally:
+            eng._ws, eng._cap_n, eng._cap_words = old
+
+
+# ---------------------------------------------------------------- NMS --------------
+def test_nms_golden_and_batched(golden_dir):
+    g = np.load(os.path.join(golden_dir, "nms_small.npz"))
+    eng = api.Engine.get()
+    dev = eng.device
+    b = torch.from_numpy(g["boxes"]).to(dev)
+    s = torch.from_numpy(g["scores"]).to(dev)
+    c = torch.from_numpy(g["classes"]).to(dev)
+    R = len(b)
+    keep, cnt = eng.nms(b, s, c, [0, R], 0.05, 0.5, -1)
+    k = int(cnt[0])
+    assert np.array_equal(keep[:k].cpu().numpy(), g["keep_thr005"])
+    keep, cnt = eng.nms(b, s, c, [0, R], -1.0, 0.5, 100)
+    assert int(cnt[0]) == 100 and np.array_equal(keep[:100].cpu().numpy(), g["keep_all"][:100])
+    # three images in one call (one of them empty), each equals its own single call
+    off = [0, 700, 700, R]
+    keep, cnt = eng.nms(b, s, c, off, 0.05, 0.5, -1)
+    keep, cnt = keep.cpu().numpy(), cnt.cpu().numpy()
+    assert cnt[1] == 0
+    for lo, hi, n in ((0, 700, cnt[0]), (700, R, cnt[2])):
+        bb, ss, cc = b[lo:hi].cpu(), s[lo:hi].cpu(), c[lo:hi].cpu()
+        ref = d2.batched_nms_vanilla(bb, ss, cc, 0.5)
+        ref = ref[ss[ref] > 0.05].numpy() + lo
+        assert np.array_equal(keep[lo:lo + n], ref)
+
+
+def test_nms_dense_config4_style():
+    """~20 k clustered candidates, 4 classes: keep list == vanilla."""
+    b, s, c = synth.clustered_candidates(5000, 4096, 4096, seed=99)
+    ref = d2.batched_nms_vanilla(b, s, c, 0.5)
+    ref = ref[s[ref] > 0.05].numpy()
+    eng = api.Engine.get()
+    dev = eng.device
+    keep, cnt = eng.nms(b.to(dev), s.to(dev), c.to(dev), [0, len(b)], 0.05, 0.5, 6000)
+    k = int(cnt[0])
+    assert np.array_equal(keep[:k].cpu().numpy(), ref[:6000])
+    print(f"dense NMS: {len(b)} candidates -> {k} kept")
+
+
+def test_fast_rcnn_inference_drop_in():
+    torch.manual_seed(0)
+    R, K = 300, 4
+    xy = torch.rand(R, K, 2) * 300
+    boxes = torch.cat([xy, xy + torch.rand(R, K, 2) * 80 + 1], dim=2).reshape(R, K * 4)
+    scores = torch.rand(R, K + 1)
+    boxes[7, 3] = float("inf")                            # non-finite proposal is dropped
+    ref, ref_rows = d2.fast_rcnn_inference_single_image(boxes, scores, (320, 320), 0.8, 0.5, 100)
+    out, rows = uwcv.fast_rcnn_inference_single_image(boxes, scores, (320, 320), 0.8, 0.5, 100)
+    assert len(out) == len(ref)
+    assert torch.equal(out.pred_boxes.tensor.cpu(), ref.pred_boxes.tensor)
+    assert torch.equal(out.scores.cpu(), ref.scores)
+    assert torch.equal(out.pred_classes.cpu(), ref.pred_classes)
+    # kept proposal rows index the finite-filtered list in the oracle, the original list here
+    valid = torch.isfinite(boxes).all(1) & torch.isfinite(scores).all(1)
+    assert torch.equal(rows.cpu(), torch.arange(R)[valid][ref_rows])
+
+
+# ---------------------------------------------------------------- full size --------
+def test_full_size_properties_and_sampled_parity():
+    """BASELINE config-2 shape (2048 x 2048, 1000 instances / image; 4 images here):
+    size-independent properties on every instance + oracle parity on a sample."""
+    H = W = 2048
+    batch = synth.blob_batch(4, 1000, H, W, seed=1234)
+    table, planes = uwcv.measure_instances(batch, (H, W), return_planes=True)
+    n = len(table)
+    assert n == sum(len(b) for b in batch)
+    p = planes.view(torch.int32)
+    # (1) popcount of every plane == area_px (bits written nowhere else, nothing lost)
+    pc = torch.zeros(n, dtype=torch.int64, device=p.device)
+    for lo in range(0, n, 250):
+        x = p[lo:lo + 250].to(torch.int64) & 0xFFFFFFFF
+        cnt = torch.zeros_like(x)
+        for sh in range(32):
+            cnt += (x >> sh) & 1
+        pc[lo:lo + 250] = cnt.sum(dim=(1, 2))
+    assert np.array_equal(pc.cpu().numpy(), table["area_px"])
+    # (2) bbox encloses the centroid, lies inside the clipped box (+1 px), m00 consistency
+    v = table["valid"] == 1
+    assert (table["bbox_x0"][v] <= table["cx"][v]).all() and (table["cx"][v] <= table["bbox_x1"][v]).all()
+    assert (table["bbox_y0"][v] <= table["cy"][v]).all() and (table["cy"][v] <= table["bbox_y1"][v]).all()
+    assert (table["m10"][v] >= table["bbox_x0"][v] * table["area_px"][v]).all()
+    assert (table["contour_area"][v] <= table["area_px"][v]).all()
+    assert (table["n_contours"][v] >= 1).all() and (table["n_contours"][~v] == 0).all()
+    # (3) linearity: planes of image 0 unpacked and OR-ed == union popcount bound
+    # (4) sampled oracle parity (every 23rd instance of each image)
+    for k, inst in enumerate(batch):
+        idx = torch.arange(0, len(inst), 23)
+        sub = inst[idx]
+        ri, rf = P.oracle_table([sub], (H, W), image_idx_offset=k)
+        rows = np.flatnonzero(table["image_idx"] == k)[idx.numpy()]
+        t = table.select(rows)
+        compare_tables(t, ri, rf, skip_int=("inst_idx",))

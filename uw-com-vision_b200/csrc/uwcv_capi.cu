@@ -57,6 +57,17 @@ int uwcv_paste_measure(const float* masks, const float* boxes, const int32_t* im
                        int64_t N, int H, int W, float thr, double pixels_per_metric,
                        uint32_t* bitplanes, int64_t* rows_i, double* rows_f, void* workspace,
                        size_t ws_bytes, int64_t* status, void* stream) {
+  return uwcv_paste_measure_stages(masks, boxes, image_idx, inst_idx, classes, scores, N, H, W,
+                                   thr, pixels_per_metric, bitplanes, rows_i, rows_f, workspace,
+                                   ws_bytes, status, stream, 7);
+}
+
+int uwcv_paste_measure_stages(const float* masks, const float* boxes, const int32_t* image_idx,
+                              const int32_t* inst_idx, const int64_t* classes,
+                              const float* scores, int64_t N, int H, int W, float thr,
+                              double pixels_per_metric, uint32_t* bitplanes, int64_t* rows_i,
+                              double* rows_f, void* workspace, size_t ws_bytes, int64_t* status,
+                              void* stream, int stages) {
   if (N < 0 || H <= 0 || W <= 0) return UWCV_E_SHAPE;
   if (H > 32768 || W > 32768) return UWCV_E_TOO_LARGE;
   if (!(thr > 0.f)) return UWCV_E_THRESH;
@@ -73,12 +84,14 @@ int uwcv_paste_measure(const float* masks, const float* boxes, const int32_t* im
     return UWCV_E_ALIGN;
   if (ws_bytes < uwcv::workspace_bytes(N, 4)) return UWCV_E_WORKSPACE;
   const uwcv::Workspace ws = uwcv::carve(workspace, ws_bytes, N);
-  if (uwcv::launch_layout(boxes, N, H, W, ws, status, st) != cudaSuccess) return UWCV_E_LAUNCH;
-  if (uwcv::launch_paste_measure(masks, boxes, image_idx, inst_idx, classes, N, H, W, thr,
+  if ((stages & 1) && uwcv::launch_layout(boxes, N, H, W, ws, status, st) != cudaSuccess)
+    return UWCV_E_LAUNCH;
+  if ((stages & 2) &&
+      uwcv::launch_paste_measure(masks, boxes, image_idx, inst_idx, classes, N, H, W, thr,
                                  bitplanes, rows_i, ws, status, num_sms(), st) != cudaSuccess)
     return UWCV_E_LAUNCH;
-  if (uwcv::launch_contour_measure(N, scores, pixels_per_metric, rows_i, rows_f, ws, status, st) !=
-      cudaSuccess)
+  if ((stages & 4) && uwcv::launch_contour_measure(N, scores, pixels_per_metric, rows_i, rows_f,
+                                                   ws, status, st) != cudaSuccess)
     return UWCV_E_LAUNCH;
   return UWCV_OK;
 }

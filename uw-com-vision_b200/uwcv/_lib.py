@@ -38,6 +38,8 @@ def lib() -> C.CDLL:
     L.uwcv_paste_measure.restype = C.c_int
     L.uwcv_paste_measure.argtypes = [vp, vp, vp, vp, vp, vp, i64, i32, i32, f32, f64,
                                      vp, vp, vp, vp, sz, vp, vp]
+    L.uwcv_paste_measure_stages.restype = C.c_int
+    L.uwcv_paste_measure_stages.argtypes = L.uwcv_paste_measure.argtypes + [i32]
     L.uwcv_unpack_planes.restype = C.c_int
     L.uwcv_unpack_planes.argtypes = [vp, i64, i32, i32, vp, vp]
     L.uwcv_nms_workspace_bytes.restype = sz
@@ -50,7 +52,7 @@ def lib() -> C.CDLL:
 
 
 EXPORTS = ("uwcv_version", "uwcv_strerror", "uwcv_plane_row_words", "uwcv_workspace_bytes",
-           "uwcv_paste_measure", "uwcv_unpack_planes", "uwcv_nms_workspace_bytes",
+           "uwcv_paste_measure", "uwcv_paste_measure_stages", "uwcv_unpack_planes", "uwcv_nms_workspace_bytes",
            "uwcv_nms_filter")
 
 

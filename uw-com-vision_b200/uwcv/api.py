@@ -198,7 +198,8 @@ class Engine:
             classes: Optional[torch.Tensor] = None, scores: Optional[torch.Tensor] = None,
             threshold: float = 0.5, pixels_per_metric: float = 0.85,
             planes: Optional[torch.Tensor] = None, n_tile_words: Optional[int] = None,
-            rows_i: Optional[torch.Tensor] = None, rows_f: Optional[torch.Tensor] = None):
+            rows_i: Optional[torch.Tensor] = None, rows_f: Optional[torch.Tensor] = None,
+            stages: int = 7):
         """All tensors on ``self.device``, contiguous: masks [N,28,28] f32, boxes [N,4] f32
         (output space), image_idx/inst_idx int32, classes int64, scores f32,
         planes None or uint32/int32 [N, H, plane_row_words(W)].
@@ -213,13 +214,13 @@ class Engine:
             n_tile_words = tile_words(boxes, H, W)
         ws = self._workspace(n, n_tile_words)
         with torch.cuda.device(dev):
-            rc = self.L.uwcv_paste_measure(
+            rc = self.L.uwcv_paste_measure_stages(
                 _ptr(masks), _ptr(boxes), _ptr(image_idx), _ptr(inst_idx), _ptr(classes),
                 _ptr(scores), n, int(H), int(W), float(threshold), float(pixels_per_metric),
                 _ptr(planes), _ptr(rows_i), _ptr(rows_f), _ptr(ws), ws.numel(),
-                _ptr(self.status), _stream_ptr(dev))
+                _ptr(self.status), _stream_ptr(dev), int(stages))
         _lib.check(rc, "uwcv_paste_measure")
-        self.launches += 3 if n > 0 else 0
+        self.launches += bin(stages & 7).count("1") if n > 0 else 0
         return rows_i, rows_f, self.status
 
     def check_status(self) -> None:
@@ -392,7 +393,7 @@ def measure_instances(instances: Union[object, Sequence[object]],
                       classes_of_interest: Optional[Sequence[int]] = None, *,
                       mask_threshold: float = 0.5, pixels_per_metric: float = 0.85,
                       image_idx_offset: int = 0, return_planes: bool = False,
-                      write_planes: bool = False, device=None):
+                      write_planes: bool = False, gather: bool = False, device=None):
     """Per-instance measurement rows for one image or a batch of images.
 
     ``instances``: a Detectron2-style ``Instances`` (or a list of them, one per image)
@@ -404,7 +405,9 @@ def measure_instances(instances: Union[object, Sequence[object]],
     share the output size.  ``classes_of_interest`` keeps only those classes
     (nn_inference.py:379).  Returns a ``MeasurementTable`` (and the device bit-planes when
     ``return_planes``); an empty selection returns an empty table (the reference prints
-    and returns, nn_inference.py:383-385).
+    and returns, nn_inference.py:383-385).  ``gather=True`` (under torch.distributed, one
+    process per GPU, images sharded over ranks) all-gathers the device rows of every rank
+    before the host read, so each rank returns the whole job's table.
     """
     single = not isinstance(instances, (list, tuple))
     batch: List[object] = [instances] if single else list(instances)
@@ -440,7 +443,11 @@ def measure_instances(instances: Union[object, Sequence[object]],
     d_boxes = boxes.contiguous().to(dev, **nb)
     d_scores = torch.cat(sl).contiguous().to(dev, **nb)
     d_classes = torch.cat(cl).contiguous().to(dev, **nb)
-    d_masks = (ml[0] if len(ml) == 1 else torch.cat(ml)).contiguous().to(dev, **nb)
+    d_masks = torch.empty((n, MASK_SIDE, MASK_SIDE), dtype=torch.float32, device=dev)
+    o = 0
+    for m in ml:                         # one async copy per image: pinned sources stay pinned
+        d_masks[o:o + m.shape[0]].copy_(m, non_blocking=True)
+        o += m.shape[0]
     d_img = torch.cat(il).to(dev, **nb)
     d_inst = torch.cat(jl).to(dev, **nb)
     planes = eng.alloc_planes(n, H, W) if (return_planes or write_planes) else None
@@ -449,6 +456,9 @@ def measure_instances(instances: Union[object, Sequence[object]],
                                      threshold=mask_threshold,
                                      pixels_per_metric=pixels_per_metric, planes=planes,
                                      n_tile_words=words)
+    if gather:
+        from .dist import all_gather_table
+        rows_i, rows_f = all_gather_table(rows_i, rows_f)
     hi, hf = rows_i.cpu(), rows_f.cpu()          # device -> host read of the result
     eng.check_status()
     table = MeasurementTable(hi.numpy(), hf.numpy())

@@ -19,18 +19,23 @@ def shard_indices(n_items: int, rank: int, world: int) -> List[int]:
     return list(range(rank, n_items, world))
 
 
-def all_gather_table(rows_i: torch.Tensor, rows_f: torch.Tensor, group=None
+def all_gather_table(rows_i: torch.Tensor, rows_f: torch.Tensor, group=None, counts=None
                      ) -> Tuple[torch.Tensor, torch.Tensor]:
     """rows_i [r, Ci] int64, rows_f [r, Cf] float64 on this rank's device -> the
-    concatenation over ranks (rank order), with the padding rows removed."""
+    concatenation over ranks (rank order), with the padding rows removed.
+    ``counts`` (list of per-rank row counts), when the caller already knows them, skips
+    the count exchange and its host synchronisation."""
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
         return rows_i, rows_f
     world = dist.get_world_size(group)
     dev = rows_i.device
-    cnt = torch.tensor([rows_i.shape[0]], dtype=torch.int64, device=dev)
-    counts = torch.empty(world, dtype=torch.int64, device=dev)
-    dist.all_gather_into_tensor(counts, cnt, group=group)
-    counts_h = counts.cpu().tolist()
+    if counts is None:
+        cnt = torch.tensor([rows_i.shape[0]], dtype=torch.int64, device=dev)
+        cts = torch.empty(world, dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(cts, cnt, group=group)
+        counts_h = cts.cpu().tolist()
+    else:
+        counts_h = [int(c) for c in counts]
     mx = max(max(counts_h), 1)
     ci, cf = rows_i.shape[1], rows_f.shape[1]
     pi = torch.zeros((mx, ci), dtype=torch.int64, device=dev)
@@ -41,6 +46,8 @@ def all_gather_table(rows_i: torch.Tensor, rows_f: torch.Tensor, group=None
     gf = torch.empty((world * mx, cf), dtype=torch.float64, device=dev)
     dist.all_gather_into_tensor(gi, pi, group=group)
     dist.all_gather_into_tensor(gf, pf, group=group)
+    if all(c == mx for c in counts_h):
+        return gi, gf
     keep = torch.cat([torch.arange(r * mx, r * mx + c, device=dev) for r, c in enumerate(counts_h)])
     return gi[keep], gf[keep]
 
