@@ -63,7 +63,7 @@ def measured_peak_gbs():
 
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
-    Q = ("index,clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+    Q = ("timestamp,clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
@@ -76,7 +76,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                 "-lms", "100", "-i", str(self.index)],
+                 "-lms", "50", "-i", str(self.index)],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -87,20 +87,37 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
+    def window(self, t0: float, t1: float):
+        """Samples whose nvidia-smi timestamp falls inside [t0, t1] (epoch seconds)."""
+        import datetime
+        out = []
+        for ln in list(self.lines):
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                ts = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+            except ValueError:
+                continue
+            if t0 - 0.03 <= ts <= t1 + 0.03:
+                out.append(f)
+        return out
+
     def stop(self):
         if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+            return
+        time.sleep(0.1)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
+
+    def summary(self, fields, window: str):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         sm, mx, reasons = [], [], set()
-        for ln in self.lines:
-            f = [x.strip() for x in ln.split(",")]
-            if len(f) < 7:
-                continue
+        for f in fields:
             try:
                 sm.append(float(f[1])); mx.append(float(f[2]))
             except ValueError:
@@ -111,7 +128,7 @@ class ClockSampler:
                     reasons.add(name)
         return {"sm_mhz": statistics.median(sm) if sm else None,
                 "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "window": window}
 
 
 # ---------------------------------------------------------------------------------------
@@ -239,26 +256,44 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
     for _ in range(max(args.warmup, 3)):
         step()
     barrier()
     eng.check_status()
 
     # ---- timed region: exactly K steps, CUDA events, max over ranks -------------------
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     launches0 = eng.launches
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    wall0 = time.time()
     e0.record()
     for _ in range(args.steps):
         step()
     e1.record()
     barrier()
+    wall1 = time.time()
     ms = e0.elapsed_time(e1)
     launches = eng.launches - launches0
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = None
+    if rank == 0:
+        time.sleep(0.12)
+        fields = sampler.window(wall0, wall1)
+        window = "timed region"
+        if len(fields) < 3:
+            # the timed region is shorter than a few nvidia-smi periods: keep the same load
+            # running (untimed) for about a second and sample the clocks under it
+            c0 = time.time()
+            while time.time() - c0 < 1.0:
+                step()
+                torch.cuda.synchronize(dev)
+            time.sleep(0.12)
+            fields = sampler.window(wall0, time.time())
+            window = "timed region + 1 s continuation of the same steps"
+        sampler.stop()
+        clocks = sampler.summary(fields, window)
     if world > 1:
         t = torch.tensor([ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

@@ -53,7 +53,7 @@ const char* uwcv_strerror(int code);
 int uwcv_plane_row_words(int W);
 
 /* Bytes of workspace uwcv_paste_measure needs for N instances whose tiles hold
- * `tile_words` 32-pixel words in total (20 bytes per word + descriptors).  The exact
+ * `tile_words` 32-pixel words in total (28 bytes per word + descriptors).  The exact
  * word count of a call is reported back in status[1]; a caller that does not know it
  * passes a generous value and checks status[0]. */
 size_t uwcv_workspace_bytes(int64_t N, int64_t tile_words);

@@ -191,10 +191,15 @@ def test_reference_literal_union_rows_for_disjoint_instances():
     rows_ref = P.reference_literal_rows(inst, (H, W), [0])
     t = uwcv.measure_instances(inst, (H, W), classes_of_interest=[0])
     assert (t["n_contours"] == 1).all()
-    order = np.argsort(t["bbox_x0"], kind="stable")
-    mine = t.select(order).reference_rows()
+    mine = t.reference_rows()
     assert mine.shape == rows_ref.shape
-    assert np.allclose(mine, rows_ref, rtol=1e-6, atol=0)
+    # the reference orders rows by boundingRect x (stable over cv2's reverse-raster order);
+    # compare as multisets of rows so that ties in x cannot matter
+    mine = mine[np.lexsort(mine.T[::-1])]
+    rows_ref = rows_ref[np.lexsort(rows_ref.T[::-1])]
+    rel = np.abs(mine - rows_ref) / np.maximum(np.abs(rows_ref), 1e-30)
+    assert rel.max() <= 1e-6, f"max rel err per column {rel.max(axis=0)}"
+    print("union == per-instance rows; exact columns:", int((rel.max(axis=0) == 0).sum()), "/ 9")
 
 
 def test_workspace_overflow_is_reported():

@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol():
     assert L.uwcv_version() >= 100
     assert L.uwcv_plane_row_words(2048) == 64 and L.uwcv_plane_row_words(1000) == 32
     assert L.uwcv_plane_row_words(33) == 4
-    assert L.uwcv_workspace_bytes(10, 1000) >= 10 * 32 + 1000 * 20
+    assert L.uwcv_workspace_bytes(10, 1000) >= 10 * 32 + 1000 * 28
 
 
 def test_argument_validation_without_gpu():

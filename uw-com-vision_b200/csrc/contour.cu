@@ -31,13 +31,46 @@ struct TileView {
   int tw, th;
 };
 
-__device__ __forceinline__ bool fg(const TileView& t, int x, int y) {
-  if ((unsigned)y >= (unsigned)t.th || (unsigned)x >= (unsigned)(t.tw * 32)) return false;
-  return (__ldg(t.M + y * t.tw + (x >> 5)) >> (x & 31)) & 1u;
-}
 // direction s: 0 = east, then counter-clockwise on a y-up plane (1 = x+1, y-1 on screen)
 __device__ __forceinline__ int dir_dx(int s) { return (int)((0x901Au >> (2 * s)) & 3u) - 1; }
 __device__ __forceinline__ int dir_dy(int s) { return (int)((0xA901u >> (2 * s)) & 3u) - 1; }
+
+// 64-pixel window of tile row y starting at word wb (words outside the tile read as zero)
+__device__ __forceinline__ uint64_t load_row64(const TileView& t, int y, int wb) {
+  if ((unsigned)y >= (unsigned)t.th) return 0ull;
+  const uint32_t* row = t.M + y * t.tw;
+  const uint32_t lo = ((unsigned)wb < (unsigned)t.tw) ? __ldg(row + wb) : 0u;
+  const uint32_t hi = ((unsigned)(wb + 1) < (unsigned)t.tw) ? __ldg(row + wb + 1) : 0u;
+  return (uint64_t)lo | ((uint64_t)hi << 32);
+}
+
+// Rows y-1, y, y+1 of the mask around the current border pixel, kept in registers so that
+// the 8-neighbour search is pure ALU work; one 64-bit row is fetched per vertical step.
+struct Window {
+  uint64_t r0, r1, r2;
+  int wb;                                  // first word of the window
+  __device__ __forceinline__ void load(const TileView& t, int x, int y) {
+    wb = (x >> 5) - (((x & 31) < 16) ? 1 : 0);         // x - 32 wb in [16, 48)
+    r0 = load_row64(t, y - 1, wb);
+    r1 = load_row64(t, y, wb);
+    r2 = load_row64(t, y + 1, wb);
+  }
+  // bit s of the result = neighbour in direction s is foreground
+  __device__ __forceinline__ uint32_t neighbours(int x) const {
+    const int sh = x - wb * 32 - 1;                    // in [0, 61]
+    const uint32_t up = (uint32_t)(r0 >> sh) & 7u, mid = (uint32_t)(r1 >> sh) & 7u,
+                   dn = (uint32_t)(r2 >> sh) & 7u;
+    return (mid >> 2) | ((up >> 2) << 1) | (((up >> 1) & 1u) << 2) | ((up & 1u) << 3) |
+           ((mid & 1u) << 4) | ((dn & 1u) << 5) | (((dn >> 1) & 1u) << 6) | ((dn >> 2) << 7);
+  }
+  __device__ __forceinline__ void move(const TileView& t, int x, int y, int dy) {
+    // (x, y) is the new position, dy the vertical part of the step just taken
+    if (dy < 0) { r2 = r1; r1 = r0; r0 = load_row64(t, y - 1, wb); }
+    else if (dy > 0) { r0 = r1; r1 = r2; r2 = load_row64(t, y + 1, wb); }
+    const int sx = x - wb * 32;
+    if (sx < 1 || sx > 62) load(t, x, y);
+  }
+};
 
 struct ContourStat {
   long long area2;    // signed twice-area (shoelace)
@@ -46,26 +79,28 @@ struct ContourStat {
   int ymax;           // last tile row touched
 };
 
-// Follow the outer border that starts at the raster-first pixel (x0, y0) of a component.
-// kMark: pass 1 (write V / G marks).  !kMark: pass 2 (record per-row extremes).
-template <bool kMark>
+// Follow the outer border that starts at the raster-first pixel (x0, y0) of a component:
+// writes the V / G marks and the per-row extremes ext_l / ext_r (rows y0 .. st.ymax).
+// Marks and extremes are written with result-less atomics (RED): no load latency on the
+// serial chain; the same thread's later loads observe them (same-address program order).
 __device__ void follow_border(const TileView& t, int x0, int y0, ContourStat& st,
                               uint32_t* ext_l, uint32_t* ext_r) {
   st.area2 = 0; st.perim = 0.0; st.npts = 0; st.ymax = y0;
-  int s = 4;
-  const int s_stop = 4;
-  do {
-    s = (s - 1) & 7;
-  } while (!fg(t, x0 + dir_dx(s), y0 + dir_dy(s)) && s != s_stop);
-  if (s == s_stop) {                          // isolated pixel
-    if (kMark) {
-      const int o = y0 * t.tw + (x0 >> 5);
-      const uint32_t b = 1u << (x0 & 31);
-      t.V[o] |= b; t.G[o] |= b;
-    } else {
-      ext_l[y0] = min(ext_l[y0], (uint32_t)x0);
-      ext_r[y0] = max(ext_r[y0], (uint32_t)x0);
-    }
+  Window w;
+  w.load(t, x0, y0);
+  uint32_t nb = w.neighbours(x0);
+  ext_l[y0] = (uint32_t)x0; ext_r[y0] = (uint32_t)x0;
+  // first search: clockwise from west (3, 2, 1, 0, 7, 6, 5)
+  int s = -1;
+#pragma unroll
+  for (int i = 0; i < 7; ++i) {
+    const int c = (3 - i) & 7;
+    if (s < 0 && ((nb >> c) & 1u)) s = c;
+  }
+  if (s < 0) {                                // isolated pixel
+    const int o = y0 * t.tw + (x0 >> 5);
+    const uint32_t b = 1u << (x0 & 31);
+    atomicOr(t.V + o, b); atomicOr(t.G + o, b);
     st.npts = 1;
     return;
   }
@@ -75,21 +110,14 @@ __device__ void follow_border(const TileView& t, int x0, int y0, ContourStat& st
   int fvx = 0, fvy = 0, lvx = 0, lvy = 0;     // first / last emitted vertex
   for (;;) {
     const int s_end = s;
-    int x4, y4;
-    do {
-      ++s;
-      x4 = x3 + dir_dx(s & 7);
-      y4 = y3 + dir_dy(s & 7);
-    } while (!fg(t, x4, y4));
-    s &= 7;
-    if (kMark) {
+    // first foreground neighbour counter-clockwise after s_end
+    const uint32_t rot = ((nb | (nb << 8)) >> ((s_end + 1) & 7)) & 0xFFu;
+    s = (s_end + __ffs(rot)) & 7;             // s_end + 1 + (ffs - 1)
+    {
       const int o = y3 * t.tw + (x3 >> 5);
       const uint32_t b = 1u << (x3 & 31);
-      if ((unsigned)(s - 1) < (unsigned)s_end) { t.V[o] |= b; t.G[o] |= b; }
-      else t.V[o] |= b;
-    } else {
-      ext_l[y3] = min(ext_l[y3], (uint32_t)x3);
-      ext_r[y3] = max(ext_r[y3], (uint32_t)x3);
+      atomicOr(t.V + o, b);
+      if ((unsigned)(s - 1) < (unsigned)s_end) atomicOr(t.G + o, b);
     }
     if (s != prev_s) {                        // CHAIN_APPROX_SIMPLE vertex
       if (st.npts == 0) { fvx = x3; fvy = y3; }
@@ -101,10 +129,20 @@ __device__ void follow_border(const TileView& t, int x0, int y0, ContourStat& st
       ++st.npts;
       prev_s = s;
     }
+    const int dy = dir_dy(s);
+    const int x4 = x3 + dir_dx(s), y4 = y3 + dy;
     st.area2 += (long long)x3 * y4 - (long long)y3 * x4;
-    st.ymax = max(st.ymax, y3);
     if (x4 == x0 && y4 == y0 && x3 == x1 && y3 == y1) break;
     x3 = x4; y3 = y4;
+    if (y3 > st.ymax) {                       // rows are first reached in increasing order
+      st.ymax = y3;
+      ext_l[y3] = (uint32_t)x3; ext_r[y3] = (uint32_t)x3;
+    } else {
+      atomicMin(ext_l + y3, (uint32_t)x3);
+      atomicMax(ext_r + y3, (uint32_t)x3);
+    }
+    w.move(t, x3, y3, dy);
+    nb = w.neighbours(x3);
     s = (s + 4) & 7;
   }
   if (st.npts >= 2) {
@@ -188,30 +226,37 @@ __device__ Rect min_area_rect(const Hull& hl) {
       }
     }
     float base_a = orientation, base_b = 0.f;
-    int seq[4] = {bottom, right, top, left};
+    // caliper sides 0..3 = bottom, right, top, left: index, point and outgoing edge kept in
+    // registers; only the side that advances fetches a new hull point (one load per step)
+    int q0 = bottom, q1 = right, q2 = top, q3 = left;
+    float p0x = hl.x(q0), p0y = hl.y(q0), p1x = hl.x(q1), p1y = hl.y(q1);
+    float p2x = hl.x(q2), p2y = hl.y(q2), p3x = hl.x(q3), p3y = hl.y(q3);
+    float e0x = vx(q0), e0y = vy(q0), e1x = vx(q1), e1y = vy(q1);
+    float e2x = vx(q2), e2y = vy(q2), e3x = vx(q3), e3y = vy(q3);
     float minarea = 3.402823466e+38f;
-    int b_left = 0, b_bottom = 0;
+    float bl_x = 0, bl_y = 0, bb_x = 0, bb_y = 0;       // "leftist" and "bottom" points of the best
     float b_a = 0, b_b = 0, b_w = 0, b_h = 0;
     for (int k = 0; k < n; ++k) {
       // edge of each caliper side rotated into side 0's frame
-      float rvx[4], rvy[4];
-      rvx[0] = vx(seq[0]);  rvy[0] = vy(seq[0]);
-      rvx[1] = vy(seq[1]);  rvy[1] = -vx(seq[1]);
-      rvx[2] = -vx(seq[2]); rvy[2] = -vy(seq[2]);
-      rvx[3] = -vy(seq[3]); rvy[3] = vx(seq[3]);
+      const float rvx[4] = {e0x, e1y, -e2x, -e3y};
+      const float rvy[4] = {e0y, -e1x, -e2y, e3x};
       int main_el = 0;
+      float mx_ = rvx[0], my_ = rvy[0];
 #pragma unroll
       for (int i = 1; i < 4; ++i) {
         // firstVecIsRight(rv[i], rv[main]): rotate90CW(rv[i]) . rv[main] < 0
         const float t0 = rvy[i], t1 = -rvx[i];
-        if (__fadd_rn(__fmul_rn(t0, rvx[main_el]), __fmul_rn(t1, rvy[main_el])) < 0.f) main_el = i;
+        if (__fadd_rn(__fmul_rn(t0, mx_), __fmul_rn(t1, my_)) < 0.f) {
+          main_el = i; mx_ = rvx[i]; my_ = rvy[i];
+        }
       }
       {
-        const int pindex = seq[main_el];
-        const double dx = vx(pindex), dy = vy(pindex);
+        const float lx = main_el == 0 ? e0x : main_el == 1 ? e1x : main_el == 2 ? e2x : e3x;
+        const float ly = main_el == 0 ? e0y : main_el == 1 ? e1y : main_el == 2 ? e2y : e3y;
+        const double dx = lx, dy = ly;
         const float inv_len = (float)(1.0 / sqrt(dx * dx + dy * dy));
-        const float lead_x = __fmul_rn(vx(pindex), inv_len);
-        const float lead_y = __fmul_rn(vy(pindex), inv_len);
+        const float lead_x = __fmul_rn(lx, inv_len);
+        const float lead_y = __fmul_rn(ly, inv_len);
         switch (main_el) {
           case 0: base_a = lead_x;  base_b = lead_y;  break;
           case 1: base_a = lead_y;  base_b = -lead_x; break;
@@ -219,23 +264,33 @@ __device__ Rect min_area_rect(const Hull& hl) {
           default: base_a = -lead_y; base_b = lead_x; break;
         }
       }
-      seq[main_el] += 1;
-      if (seq[main_el] == n) seq[main_el] = 0;
-      float dx = hl.x(seq[1]) - hl.x(seq[3]);
-      float dy = hl.y(seq[1]) - hl.y(seq[3]);
+      // advance the chosen side: its point becomes the old edge's end, fetch the next edge
+      {
+        int q = main_el == 0 ? q0 : main_el == 1 ? q1 : main_el == 2 ? q2 : q3;
+        q = (q + 1 == n) ? 0 : q + 1;
+        const int qn = (q + 1 == n) ? 0 : q + 1;
+        const float nx = hl.x(qn), ny = hl.y(qn);
+        if (main_el == 0) { p0x += e0x; p0y += e0y; e0x = nx - p0x; e0y = ny - p0y; q0 = q; }
+        else if (main_el == 1) { p1x += e1x; p1y += e1y; e1x = nx - p1x; e1y = ny - p1y; q1 = q; }
+        else if (main_el == 2) { p2x += e2x; p2y += e2y; e2x = nx - p2x; e2y = ny - p2y; q2 = q; }
+        else { p3x += e3x; p3y += e3y; e3x = nx - p3x; e3y = ny - p3y; q3 = q; }
+      }
+      float dx = p1x - p3x;
+      float dy = p1y - p3y;
       const float width = __fadd_rn(__fmul_rn(dx, base_a), __fmul_rn(dy, base_b));
-      dx = hl.x(seq[2]) - hl.x(seq[0]);
-      dy = hl.y(seq[2]) - hl.y(seq[0]);
+      dx = p2x - p0x;
+      dy = p2y - p0y;
       const float height = __fadd_rn(__fmul_rn(-dx, base_b), __fmul_rn(dy, base_a));
       const float area = __fmul_rn(width, height);
       if (area <= minarea) {
         minarea = area;
-        b_left = seq[3]; b_a = base_a; b_w = width; b_b = base_b; b_h = height; b_bottom = seq[0];
+        bl_x = p3x; bl_y = p3y; b_a = base_a; b_w = width; b_b = base_b; b_h = height;
+        bb_x = p0x; bb_y = p0y;
       }
     }
     const float A1 = b_a, B1 = b_b, A2 = -b_b, B2 = b_a;
-    const float C1 = __fadd_rn(__fmul_rn(A1, hl.x(b_left)), __fmul_rn(hl.y(b_left), B1));
-    const float C2 = __fadd_rn(__fmul_rn(A2, hl.x(b_bottom)), __fmul_rn(hl.y(b_bottom), B2));
+    const float C1 = __fadd_rn(__fmul_rn(A1, bl_x), __fmul_rn(bl_y, B1));
+    const float C2 = __fadd_rn(__fmul_rn(A2, bb_x), __fmul_rn(bb_y, B2));
     const float idet = __fdiv_rn(1.f, __fsub_rn(__fmul_rn(A1, B2), __fmul_rn(A2, B1)));
     o0x = __fmul_rn(__fsub_rn(__fmul_rn(C1, B2), __fmul_rn(C2, B1)), idet);
     o0y = __fmul_rn(__fsub_rn(__fmul_rn(A1, C2), __fmul_rn(A2, C1)), idet);
@@ -362,14 +417,17 @@ contour_measure_kernel(int64_t n, const float* __restrict__ scores, double pixel
     rf[F_ELL_THETA] = 0.5 * atan2(2.0 * b, a - c);
   }
 
-  // ---- pass 1: raster scan + border following, keep the largest contour -------------
+  // ---- raster scan + border following; keep the largest contour and its row extremes ---
   TileView t;
   t.M = ws.M + d.word_off; t.V = ws.V + d.word_off; t.G = ws.G + d.word_off;
   t.tw = d.tw; t.th = d.th;
   int ncont = 0;
   long long best_a2 = -1;
-  int best_x = 0, best_y = 0, best_npts = 0, best_ymax = 0;
+  int best_y = 0, best_npts = 0, best_ymax = 0;
   double best_perim = 0.0;
+  // two sets of per-row extremes (left | right): the contour being traced and the best so far
+  uint32_t* cur = ws.scratch + 4 * d.row_off;
+  uint32_t* best = cur + 2 * d.th;
   // rows outside the pixel bbox cannot hold a start pixel
   const int ylo = (int)ri[I_BY0] - d.y0, yhi = (int)ri[I_BY1] - d.y0;
   for (int y = ylo; y <= yhi; ++y) {
@@ -386,12 +444,13 @@ contour_measure_kernel(int64_t n, const float* __restrict__ scores, double pixel
         const int x = wi * 32 + b;
         if (last_mark_left(t, x, y) <= 0) {
           ContourStat st;
-          follow_border<true>(t, x, y, st, nullptr, nullptr);
+          follow_border(t, x, y, st, cur, cur + d.th);
           ++ncont;
           const long long a2 = st.area2 < 0 ? -st.area2 : st.area2;
           if (a2 > best_a2) {
-            best_a2 = a2; best_x = x; best_y = y; best_npts = st.npts; best_perim = st.perim;
+            best_a2 = a2; best_y = y; best_npts = st.npts; best_perim = st.perim;
             best_ymax = st.ymax;
+            uint32_t* tmp = cur; cur = best; best = tmp;
           }
         }
         const uint32_t above = (b == 31) ? 0u : (0xffffffffu << (b + 1));
@@ -403,26 +462,36 @@ contour_measure_kernel(int64_t n, const float* __restrict__ scores, double pixel
   ri[I_NPTS] = best_npts;
   if (ncont == 0) return;     // cannot happen for a non-empty mask
 
-  // ---- pass 2: per-row extremes of the best contour -> convex hull --------------------
-  uint32_t* ext_r = ws.scratch + 2 * d.row_off;
-  uint32_t* ext_l = ext_r + d.th;
-  for (int y = best_y; y <= best_ymax; ++y) { ext_l[y] = 0xffffu; ext_r[y] = 0u; }
-  {
-    ContourStat st;
-    follow_border<false>(t, best_x, best_y, st, ext_l, ext_r);
-  }
-  // right chain (top -> bottom, clockwise on screen): pop while the turn is not strictly convex
+  // ---- convex hull of the best contour from its per-row extremes -----------------------
+  uint32_t* ext_l = best;
+  uint32_t* ext_r = best + d.th;
+  // right chain (top -> bottom, clockwise on screen): pop while the turn is not strictly
+  // convex.  The two topmost stack entries live in registers.
   int nr = 0, nl = 0;
-  for (int y = best_y; y <= best_ymax; ++y) {
-    const uint32_t p = pk((int)ext_r[y], y);
-    while (nr >= 2 && cross3(ext_r[best_y + nr - 2], ext_r[best_y + nr - 1], p) <= 0) --nr;
-    ext_r[best_y + nr] = p; ++nr;
+  {
+    uint32_t a = 0, b = 0;
+    for (int y = best_y; y <= best_ymax; ++y) {
+      const uint32_t p = pk((int)ext_r[y], y);
+      while (nr >= 2 && cross3(a, b, p) <= 0) {
+        --nr; b = a;
+        if (nr >= 2) a = ext_r[best_y + nr - 2];
+      }
+      ext_r[best_y + nr] = p; ++nr;
+      a = b; b = p;
+    }
   }
   // left chain, also top -> bottom (counter-clockwise on screen): mirrored turn test
-  for (int y = best_y; y <= best_ymax; ++y) {
-    const uint32_t p = pk((int)ext_l[y], y);
-    while (nl >= 2 && cross3(ext_l[best_y + nl - 2], ext_l[best_y + nl - 1], p) >= 0) --nl;
-    ext_l[best_y + nl] = p; ++nl;
+  {
+    uint32_t a = 0, b = 0;
+    for (int y = best_y; y <= best_ymax; ++y) {
+      const uint32_t p = pk((int)ext_l[y], y);
+      while (nl >= 2 && cross3(a, b, p) >= 0) {
+        --nl; b = a;
+        if (nl >= 2) a = ext_l[best_y + nl - 2];
+      }
+      ext_l[best_y + nl] = p; ++nl;
+      a = b; b = p;
+    }
   }
   Hull hl;
   hl.R = ext_r + best_y; hl.nr = nr;

@@ -50,14 +50,14 @@ struct Workspace {
   uint32_t* M;         // [cap_words]  mask bits
   uint32_t* V;         // [cap_words]  border-visited marks
   uint32_t* G;         // [cap_words]  "right neighbour was background" marks (negative marks)
-  uint32_t* scratch;   // [2 * cap_words]  packed (x | y << 16) row extremes / hull chains
+  uint32_t* scratch;   // [4 * cap_words]  two sets of per-row extremes / hull chains (x | y << 16)
   int64_t cap_words;
 };
 
 __host__ __device__ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 __host__ __device__ inline size_t workspace_bytes(int64_t n, int64_t tile_words) {
-  return align_up((size_t)n * sizeof(TileDesc), 256) + (size_t)tile_words * 20 + 256;
+  return align_up((size_t)n * sizeof(TileDesc), 256) + (size_t)tile_words * 28 + 256;
 }
 
 __host__ __device__ inline Workspace carve(void* ws, size_t ws_bytes, int64_t n) {
@@ -65,7 +65,7 @@ __host__ __device__ inline Workspace carve(void* ws, size_t ws_bytes, int64_t n)
   char* p = (char*)ws;
   w.desc = (TileDesc*)p;
   size_t d = align_up((size_t)n * sizeof(TileDesc), 256);
-  int64_t cap = ws_bytes > d + 256 ? (int64_t)((ws_bytes - d - 256) / 20) : 0;
+  int64_t cap = ws_bytes > d + 256 ? (int64_t)((ws_bytes - d - 256) / 28) : 0;
   cap &= ~(int64_t)3;                         // keep every plane 16-byte aligned
   w.cap_words = cap;
   w.M = (uint32_t*)(p + d);
