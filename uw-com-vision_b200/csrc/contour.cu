@@ -1,5 +1,9 @@
 // Kernel 3: external-border trace, contour descriptors, min-area rectangle / Feret,
-// and the floating-point columns of the measurement row.  One thread per instance.
+// and the floating-point columns of the measurement row.  One thread per instance, written
+// warp-converged: every loop with a data-dependent trip count is a warp-uniform loop
+// (`while (__any_sync(...))`) in which each lane advances its own instance by one
+// micro-step, so the 32 instances of a warp run the scan / border-following / hull /
+// calipers code in lock step instead of serialising 32 divergent paths.
 //
 // Replaces nn_inference.py:405-459 (cvtColor + cv2.findContours(RETR_EXTERNAL,
 // CHAIN_APPROX_SIMPLE) + contourArea / arcLength / minAreaRect / boxPoints + the
@@ -72,83 +76,98 @@ struct Window {
   }
 };
 
-struct ContourStat {
-  long long area2;    // signed twice-area (shoelace)
+constexpr unsigned kFull = 0xffffffffu;
+
+// State of one border-following run (Suzuki-Abe outer border from the raster-first pixel
+// (x0, y0) of a component).  Marks (V / G) and per-row extremes are written with result-less
+// atomics (RED): no load latency on the serial chain; the same thread's later loads observe
+// them (same-address program order).
+struct Trace {
+  Window w;
+  uint32_t nb;
+  int x0, y0, x1, y1, x3, y3, s, prev_s;
+  int fvx, fvy, lvx, lvy;                  // first / last emitted CHAIN_APPROX_SIMPLE vertex
+  long long area2;                         // signed twice-area (shoelace)
   double perim;
-  int npts;
-  int ymax;           // last tile row touched
+  int npts, ymax;
+  bool active;
 };
 
-// Follow the outer border that starts at the raster-first pixel (x0, y0) of a component:
-// writes the V / G marks and the per-row extremes ext_l / ext_r (rows y0 .. st.ymax).
-// Marks and extremes are written with result-less atomics (RED): no load latency on the
-// serial chain; the same thread's later loads observe them (same-address program order).
-__device__ void follow_border(const TileView& t, int x0, int y0, ContourStat& st,
-                              uint32_t* ext_l, uint32_t* ext_r) {
-  st.area2 = 0; st.perim = 0.0; st.npts = 0; st.ymax = y0;
-  Window w;
-  w.load(t, x0, y0);
-  uint32_t nb = w.neighbours(x0);
+__device__ __forceinline__ void trace_begin(const TileView& t, Trace& c, int x0, int y0,
+                                            uint32_t* ext_l, uint32_t* ext_r) {
+  c.area2 = 0; c.perim = 0.0; c.npts = 0; c.ymax = y0;
+  c.x0 = x0; c.y0 = y0; c.x3 = x0; c.y3 = y0;
+  c.fvx = c.fvy = c.lvx = c.lvy = 0;
+  c.w.load(t, x0, y0);
+  c.nb = c.w.neighbours(x0);
   ext_l[y0] = (uint32_t)x0; ext_r[y0] = (uint32_t)x0;
   // first search: clockwise from west (3, 2, 1, 0, 7, 6, 5)
   int s = -1;
 #pragma unroll
   for (int i = 0; i < 7; ++i) {
-    const int c = (3 - i) & 7;
-    if (s < 0 && ((nb >> c) & 1u)) s = c;
+    const int d = (3 - i) & 7;
+    if (s < 0 && ((c.nb >> d) & 1u)) s = d;
   }
   if (s < 0) {                                // isolated pixel
     const int o = y0 * t.tw + (x0 >> 5);
     const uint32_t b = 1u << (x0 & 31);
     atomicOr(t.V + o, b); atomicOr(t.G + o, b);
-    st.npts = 1;
+    c.npts = 1;
+    c.active = false;
+    c.s = 0; c.prev_s = 0; c.x1 = x0; c.y1 = y0;
     return;
   }
-  const int x1 = x0 + dir_dx(s), y1 = y0 + dir_dy(s);
-  int x3 = x0, y3 = y0;
-  int prev_s = s ^ 4;
-  int fvx = 0, fvy = 0, lvx = 0, lvy = 0;     // first / last emitted vertex
-  for (;;) {
-    const int s_end = s;
-    // first foreground neighbour counter-clockwise after s_end
-    const uint32_t rot = ((nb | (nb << 8)) >> ((s_end + 1) & 7)) & 0xFFu;
-    s = (s_end + __ffs(rot)) & 7;             // s_end + 1 + (ffs - 1)
-    {
-      const int o = y3 * t.tw + (x3 >> 5);
-      const uint32_t b = 1u << (x3 & 31);
-      atomicOr(t.V + o, b);
-      if ((unsigned)(s - 1) < (unsigned)s_end) atomicOr(t.G + o, b);
-    }
-    if (s != prev_s) {                        // CHAIN_APPROX_SIMPLE vertex
-      if (st.npts == 0) { fvx = x3; fvy = y3; }
-      else {
-        const float dx = (float)(x3 - lvx), dy = (float)(y3 - lvy);
-        st.perim += (double)sqrtf(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)));
-      }
-      lvx = x3; lvy = y3;
-      ++st.npts;
-      prev_s = s;
-    }
-    const int dy = dir_dy(s);
-    const int x4 = x3 + dir_dx(s), y4 = y3 + dy;
-    st.area2 += (long long)x3 * y4 - (long long)y3 * x4;
-    if (x4 == x0 && y4 == y0 && x3 == x1 && y3 == y1) break;
-    x3 = x4; y3 = y4;
-    if (y3 > st.ymax) {                       // rows are first reached in increasing order
-      st.ymax = y3;
-      ext_l[y3] = (uint32_t)x3; ext_r[y3] = (uint32_t)x3;
-    } else {
-      atomicMin(ext_l + y3, (uint32_t)x3);
-      atomicMax(ext_r + y3, (uint32_t)x3);
-    }
-    w.move(t, x3, y3, dy);
-    nb = w.neighbours(x3);
-    s = (s + 4) & 7;
+  c.x1 = x0 + dir_dx(s); c.y1 = y0 + dir_dy(s);
+  c.s = s;
+  c.prev_s = s ^ 4;
+  c.active = true;
+}
+
+__device__ __forceinline__ void trace_step(const TileView& t, Trace& c, uint32_t* ext_l,
+                                           uint32_t* ext_r) {
+  const int s_end = c.s;
+  // first foreground neighbour counter-clockwise after s_end
+  const uint32_t rot = ((c.nb | (c.nb << 8)) >> ((s_end + 1) & 7)) & 0xFFu;
+  const int s = (s_end + __ffs(rot)) & 7;     // s_end + 1 + (ffs - 1)
+  const int x3 = c.x3, y3 = c.y3;
+  {
+    const int o = y3 * t.tw + (x3 >> 5);
+    const uint32_t b = 1u << (x3 & 31);
+    atomicOr(t.V + o, b);
+    if ((unsigned)(s - 1) < (unsigned)s_end) atomicOr(t.G + o, b);
   }
-  if (st.npts >= 2) {
-    const float dx = (float)(fvx - lvx), dy = (float)(fvy - lvy);
-    st.perim += (double)sqrtf(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)));
+  if (s != c.prev_s) {                        // CHAIN_APPROX_SIMPLE vertex
+    if (c.npts == 0) { c.fvx = x3; c.fvy = y3; }
+    else {
+      const float dx = (float)(x3 - c.lvx), dy = (float)(y3 - c.lvy);
+      c.perim += (double)sqrtf(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)));
+    }
+    c.lvx = x3; c.lvy = y3;
+    ++c.npts;
+    c.prev_s = s;
   }
+  const int dy = dir_dy(s);
+  const int x4 = x3 + dir_dx(s), y4 = y3 + dy;
+  c.area2 += (long long)x3 * y4 - (long long)y3 * x4;
+  if (x4 == c.x0 && y4 == c.y0 && x3 == c.x1 && y3 == c.y1) {
+    if (c.npts >= 2) {                        // closing segment last vertex -> first vertex
+      const float dx = (float)(c.fvx - c.lvx), dyy = (float)(c.fvy - c.lvy);
+      c.perim += (double)sqrtf(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dyy, dyy)));
+    }
+    c.active = false;
+    return;
+  }
+  c.x3 = x4; c.y3 = y4;
+  if (y4 > c.ymax) {                          // rows are first reached in increasing order
+    c.ymax = y4;
+    ext_l[y4] = (uint32_t)x4; ext_r[y4] = (uint32_t)x4;
+  } else {
+    atomicMin(ext_l + y4, (uint32_t)x4);
+    atomicMax(ext_r + y4, (uint32_t)x4);
+  }
+  c.w.move(t, x4, y4, dy);
+  c.nb = c.w.neighbours(x4);
+  c.s = (s + 4) & 7;
 }
 
 // sign of the last marked pixel left of (x, y): 0 none, +1 positive mark, -1 negative mark
@@ -193,50 +212,64 @@ struct Hull {
 
 struct Rect { float cx, cy, w, h, angle; };
 
-// OpenCV rotcalipers.cpp::rotatingCalipers(CALIPERS_MINAREARECT) + minAreaRect epilogue
+// OpenCV rotcalipers.cpp::rotatingCalipers(CALIPERS_MINAREARECT) + minAreaRect epilogue.
+// Called by all 32 lanes of a warp (lanes without work pass n == 0): its loops are
+// warp-uniform.
 __device__ Rect min_area_rect(const Hull& hl) {
   const double kPi = 3.1415926535897932384626433832795;
   Rect r;
+  r.cx = r.cy = 0.f;
   const int n = hl.n;
   float o0x = 0, o0y = 0, o1x = 0, o1y = 0, o2x = 0, o2y = 0;
   float w = 0.f, h = 0.f;
   double ang = 0.0;
-  if (n > 2) {
+  const bool big = n > 2;
+  const int nn = big ? n : 0;               // trip count of the calipers loops for this lane
+  if (__any_sync(kFull, big)) {
     int left = 0, bottom = 0, right = 0, top = 0;
-    float left_x, right_x, top_y, bottom_y;
-    left_x = right_x = hl.x(0);
-    top_y = bottom_y = hl.y(0);
-    for (int i = 0; i < n; ++i) {
-      const float px = hl.x(i), py = hl.y(i);
-      if (px < left_x) { left_x = px; left = i; }
-      if (px > right_x) { right_x = px; right = i; }
-      if (py > top_y) { top_y = py; top = i; }
-      if (py < bottom_y) { bottom_y = py; bottom = i; }
+    float left_x = 0, right_x = 0, top_y = 0, bottom_y = 0;
+    if (big) { left_x = right_x = hl.x(0); top_y = bottom_y = hl.y(0); }
+    for (int i = 0; __any_sync(kFull, i < nn); ++i) {
+      if (i < nn) {
+        const float px = hl.x(i), py = hl.y(i);
+        if (px < left_x) { left_x = px; left = i; }
+        if (px > right_x) { right_x = px; right = i; }
+        if (py > top_y) { top_y = py; top = i; }
+        if (py < bottom_y) { bottom_y = py; bottom = i; }
+      }
     }
     auto vx = [&](int i) { const int j = (i + 1 == n) ? 0 : i + 1; return hl.x(j) - hl.x(i); };
     auto vy = [&](int i) { const int j = (i + 1 == n) ? 0 : i + 1; return hl.y(j) - hl.y(i); };
     float orientation = 0.f;
     {
-      double ax = vx(n - 1), ay = vy(n - 1);
-      for (int i = 0; i < n; ++i) {
-        const double bx = vx(i), by = vy(i);
-        const double convexity = ax * by - ay * bx;
-        if (convexity != 0) { orientation = convexity > 0 ? 1.f : -1.f; break; }
-        ax = bx; ay = by;
+      double ax = 0, ay = 0;
+      if (big) { ax = vx(n - 1); ay = vy(n - 1); }
+      for (int i = 0; __any_sync(kFull, i < nn && orientation == 0.f); ++i) {
+        if (i < nn && orientation == 0.f) {
+          const double bx = vx(i), by = vy(i);
+          const double convexity = ax * by - ay * bx;
+          if (convexity != 0) orientation = convexity > 0 ? 1.f : -1.f;
+          ax = bx; ay = by;
+        }
       }
     }
     float base_a = orientation, base_b = 0.f;
     // caliper sides 0..3 = bottom, right, top, left: index, point and outgoing edge kept in
     // registers; only the side that advances fetches a new hull point (one load per step)
     int q0 = bottom, q1 = right, q2 = top, q3 = left;
-    float p0x = hl.x(q0), p0y = hl.y(q0), p1x = hl.x(q1), p1y = hl.y(q1);
-    float p2x = hl.x(q2), p2y = hl.y(q2), p3x = hl.x(q3), p3y = hl.y(q3);
-    float e0x = vx(q0), e0y = vy(q0), e1x = vx(q1), e1y = vy(q1);
-    float e2x = vx(q2), e2y = vy(q2), e3x = vx(q3), e3y = vy(q3);
+    float p0x = 0, p0y = 0, p1x = 0, p1y = 0, p2x = 0, p2y = 0, p3x = 0, p3y = 0;
+    float e0x = 0, e0y = 0, e1x = 0, e1y = 0, e2x = 0, e2y = 0, e3x = 0, e3y = 0;
+    if (big) {
+      p0x = hl.x(q0); p0y = hl.y(q0); p1x = hl.x(q1); p1y = hl.y(q1);
+      p2x = hl.x(q2); p2y = hl.y(q2); p3x = hl.x(q3); p3y = hl.y(q3);
+      e0x = vx(q0); e0y = vy(q0); e1x = vx(q1); e1y = vy(q1);
+      e2x = vx(q2); e2y = vy(q2); e3x = vx(q3); e3y = vy(q3);
+    }
     float minarea = 3.402823466e+38f;
     float bl_x = 0, bl_y = 0, bb_x = 0, bb_y = 0;       // "leftist" and "bottom" points of the best
     float b_a = 0, b_b = 0, b_w = 0, b_h = 0;
-    for (int k = 0; k < n; ++k) {
+    for (int k = 0; __any_sync(kFull, k < nn); ++k) {
+      if (k >= nn) continue;
       // edge of each caliper side rotated into side 0's frame
       const float rvx[4] = {e0x, e1y, -e2x, -e3y};
       const float rvy[4] = {e0y, -e1x, -e2y, e3x};
@@ -288,6 +321,7 @@ __device__ Rect min_area_rect(const Hull& hl) {
         bb_x = p0x; bb_y = p0y;
       }
     }
+    if (big) {
     const float A1 = b_a, B1 = b_b, A2 = -b_b, B2 = b_a;
     const float C1 = __fadd_rn(__fmul_rn(A1, bl_x), __fmul_rn(bl_y, B1));
     const float C2 = __fadd_rn(__fmul_rn(A2, bb_x), __fmul_rn(bb_y, B2));
@@ -303,6 +337,9 @@ __device__ Rect min_area_rect(const Hull& hl) {
     if (o1y == 0.f) ang = o1x >= 0.f ? 0.0 : kPi;
     else if (o1x == 0.f) ang = o1y > 0.f ? kPi * 0.5 : -kPi * 0.5;
     else ang = atan2((double)o1y, (double)o1x);
+    }
+  }
+  if (big) {
   } else if (n == 2) {
     r.cx = __fmul_rn(__fadd_rn(hl.x(0), hl.x(1)), 0.5f);
     r.cy = __fmul_rn(__fadd_rn(hl.y(0), hl.y(1)), 0.5f);
@@ -374,24 +411,33 @@ __device__ void feret_extents(const Rect& r, float& dA, float& dB) {
 constexpr int kContourThreads = 64;
 
 __global__ void __launch_bounds__(kContourThreads)
-contour_measure_kernel(int64_t n, const float* __restrict__ scores, double pixels_per_metric,
-                       int64_t* __restrict__ rows_i, double* __restrict__ rows_f, Workspace ws,
+contour_measure_kernel(int64_t n, int lanes, const float* __restrict__ scores,
+                       double pixels_per_metric, int64_t* __restrict__ rows_i,
+                       double* __restrict__ rows_f, Workspace ws,
                        const int64_t* __restrict__ status) {
-  if (status[0] != 0) return;
-  const int64_t inst = (int64_t)blockIdx.x * kContourThreads + threadIdx.x;
-  if (inst >= n) return;
+  if (status[0] != 0) return;                            // uniform over the grid
+  // `lanes` instances per warp: the kernel is bound by the latency of each lane's serial
+  // chain, not by issue slots, so small batches are spread over more warps
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * kContourThreads + threadIdx.x) >> 5;
+  const int64_t inst = warp * lanes + lane;
+  const bool live = lane < lanes && inst < n;
   const double kPi = 3.141592653589793;
-  const TileDesc d = ws.desc[inst];
-  int64_t* ri = rows_i + inst * kNumInt;
-  double* rf = rows_f + inst * kNumFloat;
-  for (int k = 0; k < kNumFloat; ++k) rf[k] = 0.0;
-  rf[F_SCORE] = scores ? (double)scores[inst] : 0.0;
-  const long long m00i = ri[I_AREA];
-  if (m00i <= 0 || d.th == 0) return;
+  TileDesc d;
+  d.wx0 = d.y0 = d.tw = d.th = 0; d.word_off = d.row_off = 0;
+  if (live) d = ws.desc[inst];
+  int64_t* ri = rows_i + (live ? inst : 0) * kNumInt;
+  double* rf = rows_f + (live ? inst : 0) * kNumFloat;
+  bool work = false;                                     // this lane has a non-empty mask
+  if (live) {
+    for (int k = 0; k < kNumFloat; ++k) rf[k] = 0.0;
+    rf[F_SCORE] = scores ? (double)scores[inst] : 0.0;
+    work = ri[I_AREA] > 0 && d.th > 0;
+  }
 
   // ---- central moments (OpenCV completeMomentState) ---------------------------------
-  {
-    const double m00 = (double)m00i, m10 = (double)ri[I_M10], m01 = (double)ri[I_M01];
+  if (work) {
+    const double m00 = (double)ri[I_AREA], m10 = (double)ri[I_M10], m01 = (double)ri[I_M01];
     const double m20 = (double)ri[I_M20], m11 = (double)ri[I_M11], m02 = (double)ri[I_M02];
     const double m30 = (double)ri[I_M30], m21 = (double)ri[I_M21], m12 = (double)ri[I_M12];
     const double m03 = (double)ri[I_M03];
@@ -418,98 +464,150 @@ contour_measure_kernel(int64_t n, const float* __restrict__ scores, double pixel
   }
 
   // ---- raster scan + border following; keep the largest contour and its row extremes ---
+  // Per-lane state machine: each iteration of the warp-uniform loop advances a lane either
+  // by one 64-pixel scan step (two tile words, the next pair prefetched) or by one border
+  // step, so no lane waits for another lane's contour.
   TileView t;
   t.M = ws.M + d.word_off; t.V = ws.V + d.word_off; t.G = ws.G + d.word_off;
   t.tw = d.tw; t.th = d.th;
   int ncont = 0;
   long long best_a2 = -1;
-  int best_y = 0, best_npts = 0, best_ymax = 0;
+  int best_y = 0, best_npts = 0, best_ymax = -1;
   double best_perim = 0.0;
   // two sets of per-row extremes (left | right): the contour being traced and the best so far
   uint32_t* cur = ws.scratch + 4 * d.row_off;
   uint32_t* best = cur + 2 * d.th;
   // rows outside the pixel bbox cannot hold a start pixel
-  const int ylo = (int)ri[I_BY0] - d.y0, yhi = (int)ri[I_BY1] - d.y0;
-  for (int y = ylo; y <= yhi; ++y) {
-    const int row = y * t.tw;
-    uint32_t carry = 0;
-    for (int wi = 0; wi < t.tw; ++wi) {
-      const uint32_t m = __ldg(t.M + row + wi);
-      const uint32_t start_mask = m & ~((m << 1) | carry);   // foreground with background on the left
-      carry = m >> 31;
-      if (!start_mask) continue;
-      uint32_t cand = start_mask & ~t.V[row + wi];
-      while (cand) {
-        const int b = __ffs(cand) - 1;
-        const int x = wi * 32 + b;
-        if (last_mark_left(t, x, y) <= 0) {
-          ContourStat st;
-          follow_border(t, x, y, st, cur, cur + d.th);
-          ++ncont;
-          const long long a2 = st.area2 < 0 ? -st.area2 : st.area2;
-          if (a2 > best_a2) {
-            best_a2 = a2; best_y = y; best_npts = st.npts; best_perim = st.perim;
-            best_ymax = st.ymax;
-            uint32_t* tmp = cur; cur = best; best = tmp;
-          }
+  int y = work ? (int)ri[I_BY0] - d.y0 : 0;
+  const int yhi = work ? (int)ri[I_BY1] - d.y0 : -1;
+  int wi = 0;
+  uint64_t carry = 0, start_mask = 0, cand = 0;
+  int cy_ = 0, cwi = 0;                                  // row / first word of the candidates
+  int sy = 0;
+  enum { kScan = 0, kTrace = 1, kDone = 2 };
+  int state = work ? kScan : kDone;
+  Trace tr;
+  tr.active = false;
+  auto load_pair = [&](const uint32_t* plane, int yy, int w0) -> uint64_t {
+    const uint32_t* row = plane + yy * t.tw;
+    const uint32_t lo = row[w0];
+    const uint32_t hi = (w0 + 1 < t.tw) ? row[w0 + 1] : 0u;
+    return (uint64_t)lo | ((uint64_t)hi << 32);
+  };
+  uint64_t m_next = (state == kScan && y <= yhi) ? load_pair(t.M, y, 0) : 0ull;
+  while (__any_sync(kFull, state != kDone)) {
+    bool finished = false;                               // a contour was completed this iteration
+    if (state == kScan) {
+      if (cand == 0) {
+        if (y > yhi) {
+          state = kDone;
+        } else {
+          const uint64_t m = m_next;
+          start_mask = m & ~((m << 1) | carry);          // foreground with background on the left
+          carry = m >> 63;
+          cy_ = y; cwi = wi;
+          wi += 2;
+          if (wi >= t.tw) { wi = 0; ++y; carry = 0; }
+          if (y <= yhi) m_next = load_pair(t.M, y, wi);  // prefetch the next pair
+          cand = start_mask ? (start_mask & ~load_pair(t.V, cy_, cwi)) : 0ull;
         }
-        const uint32_t above = (b == 31) ? 0u : (0xffffffffu << (b + 1));
-        cand = start_mask & ~t.V[row + wi] & above;
+      } else {
+        const int b = __ffsll((long long)cand) - 1;
+        const int x = cwi * 32 + b;
+        // candidates above b are re-derived afterwards (a trace marks pixels of this row)
+        start_mask &= (b == 63) ? 0ull : (~0ull << (b + 1));
+        if (last_mark_left(t, x, cy_) <= 0) {
+          sy = cy_;
+          trace_begin(t, tr, x, cy_, cur, cur + d.th);
+          cand = 0;
+          if (tr.active) state = kTrace; else finished = true;
+        } else {
+          cand = start_mask & ~load_pair(t.V, cy_, cwi);
+        }
       }
+    } else if (state == kTrace) {
+      trace_step(t, tr, cur, cur + d.th);
+      if (!tr.active) { finished = true; state = kScan; }
+    }
+    if (finished) {
+      ++ncont;
+      const long long a2 = tr.area2 < 0 ? -tr.area2 : tr.area2;
+      if (a2 > best_a2) {
+        best_a2 = a2; best_y = sy; best_npts = tr.npts; best_perim = tr.perim;
+        best_ymax = tr.ymax;
+        uint32_t* tmp = cur; cur = best; best = tmp;
+      }
+      cand = start_mask & ~load_pair(t.V, cy_, cwi);
     }
   }
-  ri[I_NCONT] = ncont;
-  ri[I_NPTS] = best_npts;
-  if (ncont == 0) return;     // cannot happen for a non-empty mask
+  if (work) { ri[I_NCONT] = ncont; ri[I_NPTS] = best_npts; }
+  const bool have = work && ncont > 0;
 
   // ---- convex hull of the best contour from its per-row extremes -----------------------
   uint32_t* ext_l = best;
   uint32_t* ext_r = best + d.th;
+  const int ylast = have ? best_ymax : best_y - 1;
   // right chain (top -> bottom, clockwise on screen): pop while the turn is not strictly
-  // convex.  The two topmost stack entries live in registers.
+  // convex; one pop or one push per iteration, the two topmost entries live in registers
   int nr = 0, nl = 0;
   {
-    uint32_t a = 0, b = 0;
-    for (int y = best_y; y <= best_ymax; ++y) {
-      const uint32_t p = pk((int)ext_r[y], y);
-      while (nr >= 2 && cross3(a, b, p) <= 0) {
-        --nr; b = a;
-        if (nr >= 2) a = ext_r[best_y + nr - 2];
+    uint32_t a = 0, b = 0, p = 0;
+    int yy = best_y;
+    bool need = true;
+    while (__any_sync(kFull, yy <= ylast)) {
+      if (yy <= ylast) {
+        if (need) { p = pk((int)ext_r[yy], yy); need = false; }
+        if (nr >= 2 && cross3(a, b, p) <= 0) {
+          --nr; b = a;
+          if (nr >= 2) a = ext_r[best_y + nr - 2];
+        } else {
+          ext_r[best_y + nr] = p; ++nr;
+          a = b; b = p;
+          ++yy; need = true;
+        }
       }
-      ext_r[best_y + nr] = p; ++nr;
-      a = b; b = p;
     }
   }
   // left chain, also top -> bottom (counter-clockwise on screen): mirrored turn test
   {
-    uint32_t a = 0, b = 0;
-    for (int y = best_y; y <= best_ymax; ++y) {
-      const uint32_t p = pk((int)ext_l[y], y);
-      while (nl >= 2 && cross3(a, b, p) >= 0) {
-        --nl; b = a;
-        if (nl >= 2) a = ext_l[best_y + nl - 2];
+    uint32_t a = 0, b = 0, p = 0;
+    int yy = best_y;
+    bool need = true;
+    while (__any_sync(kFull, yy <= ylast)) {
+      if (yy <= ylast) {
+        if (need) { p = pk((int)ext_l[yy], yy); need = false; }
+        if (nl >= 2 && cross3(a, b, p) >= 0) {
+          --nl; b = a;
+          if (nl >= 2) a = ext_l[best_y + nl - 2];
+        } else {
+          ext_l[best_y + nl] = p; ++nl;
+          a = b; b = p;
+          ++yy; need = true;
+        }
       }
-      ext_l[best_y + nl] = p; ++nl;
-      a = b; b = p;
     }
   }
   Hull hl;
   hl.R = ext_r + best_y; hl.nr = nr;
   hl.L = ext_l + best_y; hl.nl = nl;
-  hl.skip_r0 = (hl.R[0] == hl.L[0]) ? 1 : 0;                      // single-pixel top row
-  hl.skip_lb = (hl.R[nr - 1] == hl.L[nl - 1]) ? 1 : 0;            // single-pixel bottom row
-  hl.n = (nr - hl.skip_r0) + (nl - hl.skip_lb);
+  hl.skip_r0 = 0; hl.skip_lb = 0; hl.n = 0;
   hl.ox = d.wx0 * 32; hl.oy = d.y0;
   hl.swap2 = false;
-  if (hl.n <= 0) {            // a single pixel: both chains hold the same point
-    hl.skip_r0 = 0; hl.skip_lb = 1; hl.n = 1;
+  if (have) {
+    hl.skip_r0 = (hl.R[0] == hl.L[0]) ? 1 : 0;                      // single-pixel top row
+    hl.skip_lb = (hl.R[nr - 1] == hl.L[nl - 1]) ? 1 : 0;            // single-pixel bottom row
+    hl.n = (nr - hl.skip_r0) + (nl - hl.skip_lb);
+    if (hl.n <= 0) {            // a single pixel: both chains hold the same point
+      hl.skip_r0 = 0; hl.skip_lb = 1; hl.n = 1;
+    }
+    if (hl.n == 2) {
+      const uint32_t p0 = hl.raw(0), p1 = hl.raw(1);
+      const bool p0_larger = pkx(p0) > pkx(p1) || (pkx(p0) == pkx(p1) && pky(p0) > pky(p1));
+      hl.swap2 = !p0_larger;
+    }
   }
-  if (hl.n == 2) {
-    const uint32_t p0 = hl.raw(0), p1 = hl.raw(1);
-    const bool p0_larger = pkx(p0) > pkx(p1) || (pkx(p0) == pkx(p1) && pky(p0) > pky(p1));
-    hl.swap2 = !p0_larger;
-  }
-  const Rect rect = min_area_rect(hl);
+  const Rect rect = min_area_rect(hl);                   // warp-uniform loops inside
+  if (!have) return;
   float dA, dB;
   feret_extents(rect, dA, dB);
 
@@ -542,11 +640,20 @@ contour_measure_kernel(int64_t n, const float* __restrict__ scores, double pixel
 
 cudaError_t launch_contour_measure(int64_t n, const float* scores, double ppm, int64_t* rows_i,
                                    double* rows_f, const Workspace& ws, const int64_t* status,
-                                   cudaStream_t stream) {
+                                   int num_sms, cudaStream_t stream) {
   if (n == 0) return cudaSuccess;
-  const unsigned grid = (unsigned)((n + kContourThreads - 1) / kContourThreads);
-  contour_measure_kernel<<<grid, kContourThreads, 0, stream>>>(n, scores, ppm, rows_i, rows_f, ws,
-                                                               status);
+  int per_sm = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, contour_measure_kernel,
+                                                    kContourThreads, 0) != cudaSuccess || per_sm < 1)
+    per_sm = 8;
+  // as many warps as can be resident at once, each carrying ceil(n / warps) instances
+  const int64_t resident_warps = (int64_t)num_sms * per_sm * (kContourThreads / 32);
+  int lanes = (int)((n + resident_warps - 1) / resident_warps);
+  lanes = lanes < 1 ? 1 : (lanes > 32 ? 32 : lanes);
+  const int64_t warps = (n + lanes - 1) / lanes;
+  const unsigned grid = (unsigned)((warps * 32 + kContourThreads - 1) / kContourThreads);
+  contour_measure_kernel<<<grid, kContourThreads, 0, stream>>>(n, lanes, scores, ppm, rows_i,
+                                                               rows_f, ws, status);
   return cudaPeekAtLastError();
 }
 

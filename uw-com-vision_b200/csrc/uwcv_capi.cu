@@ -8,7 +8,7 @@ cudaError_t launch_paste_measure(const float*, const float*, const int32_t*, con
                                  const int64_t*, int64_t, int, int, float, uint32_t*, int64_t*,
                                  const Workspace&, const int64_t*, int, cudaStream_t);
 cudaError_t launch_contour_measure(int64_t, const float*, double, int64_t*, double*,
-                                   const Workspace&, const int64_t*, cudaStream_t);
+                                   const Workspace&, const int64_t*, int, cudaStream_t);
 cudaError_t launch_unpack(const uint32_t*, int64_t, int, int, uint8_t*, int, cudaStream_t);
 size_t nms_workspace_bytes_host(const int64_t*, int);
 cudaError_t launch_nms(const float*, const float*, const int64_t*, const int64_t*, int, float,
@@ -91,7 +91,7 @@ int uwcv_paste_measure_stages(const float* masks, const float* boxes, const int3
                                  bitplanes, rows_i, ws, status, num_sms(), st) != cudaSuccess)
     return UWCV_E_LAUNCH;
   if ((stages & 4) && uwcv::launch_contour_measure(N, scores, pixels_per_metric, rows_i, rows_f,
-                                                   ws, status, st) != cudaSuccess)
+                                                   ws, status, num_sms(), st) != cudaSuccess)
     return UWCV_E_LAUNCH;
   return UWCV_OK;
 }
