@@ -319,7 +319,7 @@ def run_ours(args):
     tp = os.path.join(ROOT, "profiles", "paste_kernel_traffic.json")
     if os.path.exists(tp):
         try:
-            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+            traffic = json.load(open(tp))["dram_bytes_per_instance"] * n
         except Exception:
             traffic = None
 

@@ -80,6 +80,11 @@ def tile_words(boxes: torch.Tensor, H: int, W: int) -> int:
     output-space boxes (host mirror of csrc/paste_measure.cu::tile_geometry)."""
     if boxes.numel() == 0:
         return 0
+    return int(tile_words_each(boxes, H, W).sum().item())
+
+
+def tile_words_each(boxes: torch.Tensor, H: int, W: int) -> torch.Tensor:
+    """Per-instance tile words (int64 tensor on the device of ``boxes``)."""
     b = boxes.detach().to(torch.float32)
     x0, y0, x1, y1 = b[:, 0], b[:, 1], b[:, 2], b[:, 3]
     bw, bh = x1 - x0, y1 - y0
@@ -95,8 +100,7 @@ def tile_words(boxes: torch.Tensor, H: int, W: int) -> int:
     pyb = gb.clamp(min=0, max=H - 1).nan_to_num(0).long()
     tw = (pxb >> 5) - (pxa >> 5) + 1
     th = pyb - pya + 1
-    words = torch.where(ok, tw * th, torch.zeros_like(tw))
-    return int(words.sum().item())
+    return torch.where(ok, tw * th, torch.zeros_like(tw))
 
 
 # ----------------------------------------------------------------------------------
@@ -182,6 +186,20 @@ class Engine:
         self._cap_n = 0
         self.status = torch.zeros(4, dtype=torch.int64, device=device)
         self.launches = 0            # kernels enqueued by this engine (for bench accounting)
+        self.h2d_stream = torch.cuda.Stream(device)
+        self.d2h_stream = torch.cuda.Stream(device)
+        self._pin_i: Optional[torch.Tensor] = None
+        self._pin_f: Optional[torch.Tensor] = None
+        self._pin_s: Optional[torch.Tensor] = None
+
+    def pinned_rows(self, n: int, nchunks: int):
+        """Cached pinned host buffers for the device->host read of the row tables."""
+        if self._pin_i is None or self._pin_i.shape[0] < n:
+            self._pin_i = torch.empty((n, NUM_INT), dtype=torch.int64).pin_memory()
+            self._pin_f = torch.empty((n, NUM_FLOAT), dtype=torch.float64).pin_memory()
+        if self._pin_s is None or self._pin_s.shape[0] < nchunks:
+            self._pin_s = torch.empty((nchunks, 4), dtype=torch.int64).pin_memory()
+        return self._pin_i[:n], self._pin_f[:n], self._pin_s[:nchunks]
 
     def _workspace(self, n: int, words: int) -> torch.Tensor:
         if self._ws is None or n > self._cap_n or words > self._cap_words:
@@ -199,7 +217,7 @@ class Engine:
             threshold: float = 0.5, pixels_per_metric: float = 0.85,
             planes: Optional[torch.Tensor] = None, n_tile_words: Optional[int] = None,
             rows_i: Optional[torch.Tensor] = None, rows_f: Optional[torch.Tensor] = None,
-            stages: int = 7):
+            stages: int = 7, status: Optional[torch.Tensor] = None):
         """All tensors on ``self.device``, contiguous: masks [N,28,28] f32, boxes [N,4] f32
         (output space), image_idx/inst_idx int32, classes int64, scores f32,
         planes None or uint32/int32 [N, H, plane_row_words(W)].
@@ -213,21 +231,33 @@ class Engine:
         if n_tile_words is None:
             n_tile_words = tile_words(boxes, H, W)
         ws = self._workspace(n, n_tile_words)
+        status = self.status if status is None else status
         with torch.cuda.device(dev):
             rc = self.L.uwcv_paste_measure_stages(
                 _ptr(masks), _ptr(boxes), _ptr(image_idx), _ptr(inst_idx), _ptr(classes),
                 _ptr(scores), n, int(H), int(W), float(threshold), float(pixels_per_metric),
                 _ptr(planes), _ptr(rows_i), _ptr(rows_f), _ptr(ws), ws.numel(),
-                _ptr(self.status), _stream_ptr(dev), int(stages))
+                _ptr(status), _stream_ptr(dev), int(stages))
         _lib.check(rc, "uwcv_paste_measure")
         self.launches += bin(stages & 7).count("1") if n > 0 else 0
-        return rows_i, rows_f, self.status
+        return rows_i, rows_f, status
 
     def check_status(self) -> None:
         """Synchronising read of the device status word; raises on workspace overflow."""
         st = self.status.cpu()
         if int(st[0]) != 0:
             raise _lib.UwcvError(int(st[0]), f"uwcv_paste_measure (needs {int(st[1])} tile words)")
+
+    def scratch_planes(self, n: int, H: int, W: int) -> torch.Tensor:
+        """Engine-owned plane buffer for callers that want the Detectron2-literal masks
+        written to HBM but do not take ownership (reused by the next call)."""
+        wpr = self.L.uwcv_plane_row_words(int(W))
+        need = n * H * wpr
+        buf = getattr(self, "_planes", None)
+        if buf is None or buf.numel() < need:
+            self._planes = None
+            self._planes = buf = torch.empty(need, dtype=torch.int32, device=self.device)
+        return buf[:need].view(n, H, wpr)
 
     def alloc_planes(self, n: int, H: int, W: int) -> torch.Tensor:
         wpr = self.L.uwcv_plane_row_words(int(W))
@@ -393,7 +423,8 @@ def measure_instances(instances: Union[object, Sequence[object]],
                       classes_of_interest: Optional[Sequence[int]] = None, *,
                       mask_threshold: float = 0.5, pixels_per_metric: float = 0.85,
                       image_idx_offset: int = 0, return_planes: bool = False,
-                      write_planes: bool = False, gather: bool = False, device=None):
+                      write_planes: bool = False, gather: bool = False,
+                      pipeline_chunks: int = 4, device=None, _exact_words: bool = False):
     """Per-instance measurement rows for one image or a batch of images.
 
     ``instances``: a Detectron2-style ``Instances`` (or a list of them, one per image)
@@ -419,7 +450,33 @@ def measure_instances(instances: Union[object, Sequence[object]],
         tuple(int(v) for v in batch[0].image_size)
 
     bl, sl, cl, ml, il, jl = [], [], [], [], [], []
-    for k, inst in enumerate(batch):
+    sizes = {tuple(int(v) for v in inst.image_size) for inst in batch}
+    if output_size is None and len(sizes) > 1:
+        raise ValueError("all images of one call must share the output size")
+    if len(sizes) == 1 and classes_of_interest is None and len(batch) > 1 and \
+            all(not _as_box_tensor(i.pred_boxes).is_cuda for i in batch):
+        # fast host path: one scale / clip / non-empty over the concatenated boxes
+        lens = [len(i) for i in batch]
+        allb = torch.cat([_as_box_tensor(i.pred_boxes) for i in batch])
+        b_all, keep_all = scale_clip_boxes(allb, batch[0].image_size, (H, W))
+        if bool(keep_all.all()):
+            bl = [b_all]
+            sl = [i.scores.to(torch.float32) for i in batch]
+            cl = [i.pred_classes.to(torch.int64) for i in batch]
+            ml = [(i.pred_masks[:, 0] if i.pred_masks.dim() == 4 else i.pred_masks)
+                  .to(torch.float32).reshape(-1, MASK_SIDE, MASK_SIDE) for i in batch]
+            lt = torch.tensor(lens, dtype=torch.int64)
+            il = [torch.repeat_interleave(
+                torch.arange(len(batch), dtype=torch.int32) + image_idx_offset, lt)]
+            offs = torch.cumsum(lt, 0) - lt
+            jl = [(torch.arange(int(lt.sum()), dtype=torch.int64)
+                   - torch.repeat_interleave(offs, lt)).to(torch.int32)]
+            counts_fast = lens
+        else:
+            counts_fast = None
+    else:
+        counts_fast = None
+    for k, inst in enumerate(batch if counts_fast is None else []):
         boxes, scores, classes, masks = _gather_fields(inst, classes_of_interest)
         out_sz = (H, W)
         if output_size is None and tuple(int(v) for v in inst.image_size) != out_sz:
@@ -438,31 +495,103 @@ def measure_instances(instances: Union[object, Sequence[object]],
     n = int(boxes.shape[0])
     if n == 0:
         return (MeasurementTable.empty(), None) if return_planes else MeasurementTable.empty()
-    words = tile_words(boxes, H, W)
+    # Workspace sizing: the exact tile-word count is only computed for the first call (or
+    # after an overflow); afterwards the cached capacity is reused and the device status
+    # word reports an overflow, in which case the call is repeated with the exact size.
+    need_exact = _exact_words or eng._ws is None or gather
+    words_each = tile_words_each(boxes, H, W) if need_exact else None
+    # ---- chunk the batch by image: H2D of chunk c+1 overlaps the kernels of chunk c, and
+    #      the D2H of chunk c's rows overlaps the kernels of chunk c+1 (three streams)
+    counts = counts_fast if counts_fast is not None else [int(b.shape[0]) for b in bl]
+    nchunks = max(1, min(int(pipeline_chunks), len(batch)))
+    per = (len(batch) + nchunks - 1) // nchunks
+    bounds = []                                   # (first image, last image + 1, lo row, hi row)
+    lo = 0
+    for c in range(nchunks):
+        i0, i1 = c * per, min(len(batch), (c + 1) * per)
+        if i0 >= i1:
+            break
+        hi = lo + sum(counts[i0:i1])
+        bounds.append((i0, i1, lo, hi))
+        lo = hi
+    nchunks = len(bounds)
+    starts = [0]
+    for k in counts:
+        starts.append(starts[-1] + k)
+    main = torch.cuda.current_stream(dev)
     nb = dict(non_blocking=True)
-    d_boxes = boxes.contiguous().to(dev, **nb)
-    d_scores = torch.cat(sl).contiguous().to(dev, **nb)
-    d_classes = torch.cat(cl).contiguous().to(dev, **nb)
-    d_masks = torch.empty((n, MASK_SIDE, MASK_SIDE), dtype=torch.float32, device=dev)
-    o = 0
-    for m in ml:                         # one async copy per image: pinned sources stay pinned
-        d_masks[o:o + m.shape[0]].copy_(m, non_blocking=True)
-        o += m.shape[0]
-    d_img = torch.cat(il).to(dev, **nb)
-    d_inst = torch.cat(jl).to(dev, **nb)
-    planes = eng.alloc_planes(n, H, W) if (return_planes or write_planes) else None
-    rows_i, rows_f, status = eng.run(d_masks, d_boxes, H, W, image_idx=d_img, inst_idx=d_inst,
-                                     classes=d_classes, scores=d_scores,
-                                     threshold=mask_threshold,
-                                     pixels_per_metric=pixels_per_metric, planes=planes,
-                                     n_tile_words=words)
-    if gather:
-        from .dist import all_gather_table
-        rows_i, rows_f = all_gather_table(rows_i, rows_f)
-    hi, hf = rows_i.cpu(), rows_f.cpu()          # device -> host read of the result
-    eng.check_status()
-    table = MeasurementTable(hi.numpy(), hf.numpy())
+    with torch.cuda.device(dev):
+        d_masks = torch.empty((n, MASK_SIDE, MASK_SIDE), dtype=torch.float32, device=dev)
+        rows_i = torch.empty((n, NUM_INT), dtype=torch.int64, device=dev)
+        rows_f = torch.empty((n, NUM_FLOAT), dtype=torch.float64, device=dev)
+        status = torch.zeros((nchunks, 4), dtype=torch.int64, device=dev)
+        if return_planes:
+            planes = eng.alloc_planes(n, H, W)            # handed to the caller
+        elif write_planes:
+            planes = eng.scratch_planes(n, H, W)          # engine-owned, reused across calls
+        else:
+            planes = None
+        eng.h2d_stream.wait_stream(main)
+        eng.d2h_stream.wait_stream(main)
+        ev_in = [torch.cuda.Event() for _ in bounds]
+        with torch.cuda.stream(eng.h2d_stream):
+            d_boxes = boxes.contiguous().to(dev, **nb)
+            d_scores = torch.cat(sl).contiguous().to(dev, **nb)
+            d_classes = torch.cat(cl).contiguous().to(dev, **nb)
+            d_img = torch.cat(il).to(dev, **nb)
+            d_inst = torch.cat(jl).to(dev, **nb)
+            for c, (i0, i1, lo, hi) in enumerate(bounds):
+                for i in range(i0, i1):             # pinned sources stay pinned: async copies
+                    d_masks[starts[i]:starts[i + 1]].copy_(ml[i], non_blocking=True)
+                ev_in[c].record(eng.h2d_stream)
+        if words_each is not None:
+            words_c = [int(words_each[lo:hi].sum().item()) for (_, _, lo, hi) in bounds]
+        else:
+            words_c = [eng._cap_words] * len(bounds)
+        eng._workspace(max(hi - lo for (_, _, lo, hi) in bounds), max(words_c))
+        gathered = gather and dist_is_multi()
+        hp_i, hp_f, hp_s = eng.pinned_rows(n, nchunks)
+        for c, (i0, i1, lo, hi) in enumerate(bounds):
+            main.wait_event(ev_in[c])
+            eng.run(d_masks[lo:hi], d_boxes[lo:hi], H, W, image_idx=d_img[lo:hi],
+                    inst_idx=d_inst[lo:hi], classes=d_classes[lo:hi], scores=d_scores[lo:hi],
+                    threshold=mask_threshold, pixels_per_metric=pixels_per_metric,
+                    planes=None if planes is None else planes[lo:hi], n_tile_words=words_c[c],
+                    rows_i=rows_i[lo:hi], rows_f=rows_f[lo:hi], status=status[c])
+            if not gathered:
+                ev = torch.cuda.Event()
+                ev.record(main)
+                with torch.cuda.stream(eng.d2h_stream):
+                    eng.d2h_stream.wait_event(ev)
+                    hp_i[lo:hi].copy_(rows_i[lo:hi], non_blocking=True)
+                    hp_f[lo:hi].copy_(rows_f[lo:hi], non_blocking=True)
+                    hp_s[c].copy_(status[c], non_blocking=True)
+        if gathered:
+            from .dist import all_gather_table
+            g_i, g_f = all_gather_table(rows_i, rows_f)
+            hi_, hf_, st = g_i.cpu(), g_f.cpu(), status.cpu()
+        else:
+            eng.d2h_stream.synchronize()
+            main.wait_stream(eng.d2h_stream)
+            hi_, hf_, st = hp_i.clone(), hp_f.clone(), hp_s.clone()
+        main.synchronize()                              # buffers of the side streams are done
+    for c in range(nchunks):
+        if int(st[c, 0]) != 0:
+            if int(st[c, 0]) == _lib.E_CAPACITY and not _exact_words:
+                return measure_instances(
+                    instances, output_size, classes_of_interest, mask_threshold=mask_threshold,
+                    pixels_per_metric=pixels_per_metric, image_idx_offset=image_idx_offset,
+                    return_planes=return_planes, write_planes=write_planes, gather=gather,
+                    pipeline_chunks=pipeline_chunks, device=device, _exact_words=True)
+            raise _lib.UwcvError(int(st[c, 0]),
+                                 f"uwcv_paste_measure (chunk {c} needs {int(st[c, 1])} tile words)")
+    table = MeasurementTable(hi_.numpy(), hf_.numpy())
     return (table, planes) if return_planes else table
+
+
+def dist_is_multi() -> bool:
+    import torch.distributed as dist
+    return dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
 
 
 def get_counts(instances) -> List[int]:
