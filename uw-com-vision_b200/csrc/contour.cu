@@ -170,18 +170,15 @@ __device__ __forceinline__ void trace_step(const TileView& t, Trace& c, uint32_t
   c.s = (s + 4) & 7;
 }
 
-// sign of the last marked pixel left of (x, y): 0 none, +1 positive mark, -1 negative mark
-__device__ int last_mark_left(const TileView& t, int x, int y) {
-  int wi = x >> 5;
-  uint32_t keep = (x & 31) ? ((1u << (x & 31)) - 1u) : 0u;
+// sign of the last marked pixel in words [0, wi) of row y: 0 none, +1 positive, -1 negative
+__device__ int last_mark_before(const TileView& t, int wi, int y) {
   const int row = y * t.tw;
-  for (; wi >= 0; --wi) {
-    const uint32_t v = t.V[row + wi] & keep;
+  for (--wi; wi >= 0; --wi) {
+    const uint32_t v = t.V[row + wi];
     if (v) {
       const int b = 31 - __clz(v);
       return ((t.G[row + wi] >> b) & 1u) ? -1 : +1;
     }
-    keep = 0xffffffffu;
   }
   return 0;
 }
@@ -481,7 +478,7 @@ contour_measure_kernel(int64_t n, int lanes, const float* __restrict__ scores,
   int y = work ? (int)ri[I_BY0] - d.y0 : 0;
   const int yhi = work ? (int)ri[I_BY1] - d.y0 : -1;
   int wi = 0;
-  uint64_t carry = 0, start_mask = 0, cand = 0;
+  uint64_t carry = 0, start_mask = 0, cand = 0, vpair = 0, gpair = 0;
   int cy_ = 0, cwi = 0;                                  // row / first word of the candidates
   int sy = 0;
   enum { kScan = 0, kTrace = 1, kDone = 2 };
@@ -494,11 +491,16 @@ contour_measure_kernel(int64_t n, int lanes, const float* __restrict__ scores,
     const uint32_t hi = (w0 + 1 < t.tw) ? row[w0 + 1] : 0u;
     return (uint64_t)lo | ((uint64_t)hi << 32);
   };
+  auto sign_of_top = [](uint64_t v, uint64_t g) -> int {      // v != 0
+    const int top = 63 - __clzll((long long)v);
+    return ((g >> top) & 1ull) ? -1 : +1;
+  };
   uint64_t m_next = (state == kScan && y <= yhi) ? load_pair(t.M, y, 0) : 0ull;
+  bool fresh = true;                                     // the next scan step opens a new pair
   while (__any_sync(kFull, state != kDone)) {
     bool finished = false;                               // a contour was completed this iteration
     if (state == kScan) {
-      if (cand == 0) {
+      if (fresh) {
         if (y > yhi) {
           state = kDone;
         } else {
@@ -509,20 +511,33 @@ contour_measure_kernel(int64_t n, int lanes, const float* __restrict__ scores,
           wi += 2;
           if (wi >= t.tw) { wi = 0; ++y; carry = 0; }
           if (y <= yhi) m_next = load_pair(t.M, y, wi);  // prefetch the next pair
-          cand = start_mask ? (start_mask & ~load_pair(t.V, cy_, cwi)) : 0ull;
+          // marks are only consulted where the pair holds start candidates (V), and their
+          // signs only where a candidate is still unvisited (G)
+          vpair = start_mask ? load_pair(t.V, cy_, cwi) : 0ull;
+          cand = start_mask & ~vpair;
+          gpair = cand ? load_pair(t.G, cy_, cwi) : 0ull;
+          fresh = cand == 0;
         }
-      } else {
-        const int b = __ffsll((long long)cand) - 1;
-        const int x = cwi * 32 + b;
-        // candidates above b are re-derived afterwards (a trace marks pixels of this row)
-        start_mask &= (b == 63) ? 0ull : (~0ull << (b + 1));
-        if (last_mark_left(t, x, cy_) <= 0) {
+      }
+      if (state == kScan && !fresh) {
+        // resolve the candidates of this pair in registers: a candidate starts an external
+        // border unless the last marked pixel to its left carries a positive mark
+        bool start = false;
+        int b = 0;
+        while (cand) {
+          b = __ffsll((long long)cand) - 1;
+          cand &= cand - 1;
+          const uint64_t below = vpair & ((1ull << b) - 1ull);
+          // last marked pixel to the left: in this pair, else search the earlier words
+          const int sgn = below ? sign_of_top(below, gpair) : last_mark_before(t, cwi, cy_);
+          if (sgn <= 0) { start = true; break; }
+        }
+        if (start) {
           sy = cy_;
-          trace_begin(t, tr, x, cy_, cur, cur + d.th);
-          cand = 0;
+          trace_begin(t, tr, cwi * 32 + b, cy_, cur, cur + d.th);
           if (tr.active) state = kTrace; else finished = true;
         } else {
-          cand = start_mask & ~load_pair(t.V, cy_, cwi);
+          fresh = true;
         }
       }
     } else if (state == kTrace) {
@@ -537,7 +552,9 @@ contour_measure_kernel(int64_t n, int lanes, const float* __restrict__ scores,
         best_ymax = tr.ymax;
         uint32_t* tmp = cur; cur = best; best = tmp;
       }
-      cand = start_mask & ~load_pair(t.V, cy_, cwi);
+      // the trace marked pixels of this row (never to the left of its start): reload
+      vpair = load_pair(t.V, cy_, cwi); gpair = load_pair(t.G, cy_, cwi);
+      cand &= ~vpair;
     }
   }
   if (work) { ri[I_NCONT] = ncont; ri[I_NPTS] = best_npts; }
