@@ -312,6 +312,17 @@ def run_ours(args):
             b.synchronize()
             kt[st].append(a.elapsed_time(b))
     k_layout, k_paste, k_contour = (statistics.mean(kt[s]) for s in (1, 2, 4))
+    # context for the roofline: what a plain device memset of the same plane buffer reaches
+    # (a write-only stream; the measured peak in MEASURED_PEAKS.json is a read+write copy)
+    mt = []
+    for _ in range(3):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        planes.zero_()
+        b.record()
+        b.synchronize()
+        mt.append(a.elapsed_time(b))
+    memset_gbs = planes.numel() * 4 / (min(mt) * 1e-3) / 1e9
     peak, peak_src = measured_peak_gbs()
     bpi = algorithmic_bytes_per_instance(H, W)
     achieved = n * bpi / (k_paste * 1e-3) / 1e9
@@ -374,7 +385,8 @@ def run_ours(args):
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "kernel": "paste_measure_kernel<true>",
                          "bytes_per_instance": bpi, "instances_per_launch": n,
-                         "frac_of_nominal_8000": achieved / 8000.0},
+                         "frac_of_nominal_8000": achieved / 8000.0,
+                         "memset_same_buffer_gbs": memset_gbs},
             "clocks": clocks,
         }
         if cpu is not None:

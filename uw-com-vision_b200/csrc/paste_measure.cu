@@ -18,12 +18,13 @@
 // bulk stores (cp.async.bulk shared->global) from a zeroed shared-memory buffer;
 // the rows of the tile band are written with ordinary stores.  Algorithmic bytes per
 // instance: 3136 (probabilities) + 16 (box) read, H*W/8 + rows written.
+#include <cstdlib>
 #include "uwcv_common.cuh"
 
 namespace uwcv {
 
 // ---------------------------------------------------------------------------------
-// kernel 0: tile geometry + exclusive prefix sums (single CTA)
+// kernel 0: tile geometry + exclusive prefix sums (two passes over ceil(N / 1024) CTAs)
 // ---------------------------------------------------------------------------------
 __device__ __forceinline__ void tile_geometry(const float* __restrict__ box, int H, int W,
                                               int& wx0, int& y0, int& tw, int& th) {
@@ -49,53 +50,78 @@ __device__ __forceinline__ void tile_geometry(const float* __restrict__ box, int
   th = pyb - pya + 1;
 }
 
-constexpr int kLayoutThreads = 1024;
+// block-wide exclusive scan of two int64 values (Hillis-Steele over 1024 threads)
+__device__ __forceinline__ void block_scan2(int64_t& a, int64_t& b, int64_t& total_a,
+                                            int64_t& total_b, int64_t* sa, int64_t* sb) {
+  const int t = threadIdx.x;
+  const int64_t va = a, vb = b;
+  sa[t] = va; sb[t] = vb;
+  __syncthreads();
+  for (int off = 1; off < kLayoutThreads; off <<= 1) {
+    int64_t x = 0, y = 0;
+    if (t >= off) { x = sa[t - off]; y = sb[t - off]; }
+    __syncthreads();
+    sa[t] += x; sb[t] += y;
+    __syncthreads();
+  }
+  a = sa[t] - va; b = sb[t] - vb;
+  total_a = sa[kLayoutThreads - 1]; total_b = sb[kLayoutThreads - 1];
+}
 
+// pass A: one instance per thread -- geometry, CTA-local exclusive offsets, CTA totals
 __global__ void __launch_bounds__(kLayoutThreads)
-layout_kernel(const float* __restrict__ boxes, int64_t n, int H, int W,
-              TileDesc* __restrict__ desc, int64_t cap_words, int64_t* __restrict__ status) {
+layout_local_kernel(const float* __restrict__ boxes, int64_t n, int H, int W,
+                    TileDesc* __restrict__ desc, int64_t* __restrict__ block_sums) {
+  __shared__ int64_t s_words[kLayoutThreads];
+  __shared__ int64_t s_rows[kLayoutThreads];
+  const int64_t i = (int64_t)blockIdx.x * kLayoutThreads + threadIdx.x;
+  int wx0 = 0, y0 = 0, tw = 0, th = 0;
+  if (i < n) tile_geometry(boxes + 4 * i, H, W, wx0, y0, tw, th);
+  int64_t words = (int64_t)tw * th, rows = th, tw_total, tr_total;
+  block_scan2(words, rows, tw_total, tr_total, s_words, s_rows);
+  if (i < n) {
+    TileDesc d;
+    d.wx0 = wx0; d.y0 = y0; d.tw = tw; d.th = th;
+    d.word_off = words; d.row_off = rows;
+    desc[i] = d;
+  }
+  if (threadIdx.x == 0) {
+    block_sums[2 * blockIdx.x] = tw_total;
+    block_sums[2 * blockIdx.x + 1] = tr_total;
+  }
+}
+
+// pass B: every CTA sums the totals of the CTAs before it and rebases its descriptors;
+// CTA 0 also publishes the grand totals / overflow flag in the status word
+__global__ void __launch_bounds__(kLayoutThreads)
+layout_rebase_kernel(int64_t n, int nblk, TileDesc* __restrict__ desc,
+                     const int64_t* __restrict__ block_sums, int64_t cap_words,
+                     int64_t* __restrict__ status) {
   __shared__ int64_t s_words[kLayoutThreads];
   __shared__ int64_t s_rows[kLayoutThreads];
   const int t = threadIdx.x;
-  const int64_t per = (n + kLayoutThreads - 1) / kLayoutThreads;
-  const int64_t lo = (int64_t)t * per;
-  const int64_t hi = lo + per < n ? lo + per : n;
-  int64_t words = 0, rows = 0;
-  for (int64_t i = lo; i < hi; ++i) {
-    int wx0, y0, tw, th;
-    tile_geometry(boxes + 4 * i, H, W, wx0, y0, tw, th);
-    words += (int64_t)tw * th;
-    rows += th;
-  }
-  s_words[t] = words;
-  s_rows[t] = rows;
+  const int upto = blockIdx.x == 0 ? nblk : (int)blockIdx.x;     // CTA 0 needs the grand total
+  int64_t a = 0, b = 0;
+  for (int k = t; k < upto; k += kLayoutThreads) { a += block_sums[2 * k]; b += block_sums[2 * k + 1]; }
+  s_words[t] = a; s_rows[t] = b;
   __syncthreads();
-  // Hillis-Steele inclusive scan over the 1024 partials
-  for (int off = 1; off < kLayoutThreads; off <<= 1) {
-    int64_t a = 0, b = 0;
-    if (t >= off) { a = s_words[t - off]; b = s_rows[t - off]; }
-    __syncthreads();
-    s_words[t] += a;
-    s_rows[t] += b;
+  for (int off = kLayoutThreads / 2; off > 0; off >>= 1) {
+    if (t < off) { s_words[t] += s_words[t + off]; s_rows[t] += s_rows[t + off]; }
     __syncthreads();
   }
-  int64_t woff = s_words[t] - words, roff = s_rows[t] - rows;
-  const int64_t total_words = s_words[kLayoutThreads - 1];
-  const int64_t total_rows = s_rows[kLayoutThreads - 1];
-  for (int64_t i = lo; i < hi; ++i) {
-    int wx0, y0, tw, th;
-    tile_geometry(boxes + 4 * i, H, W, wx0, y0, tw, th);
-    TileDesc d;
-    d.wx0 = wx0; d.y0 = y0; d.tw = tw; d.th = th;
-    d.word_off = woff; d.row_off = roff;
-    desc[i] = d;
-    woff += (int64_t)tw * th;
-    roff += th;
+  const int64_t base_w = s_words[0], base_r = s_rows[0];
+  if (blockIdx.x == 0) {
+    if (t == 0) {
+      status[1] = base_w;
+      status[2] = base_r;
+      status[0] = (base_w > cap_words) ? (int64_t)E_CAPACITY : 0;
+    }
+    return;                                              // offsets of CTA 0 need no rebase
   }
-  if (t == 0) {
-    status[1] = total_words;
-    status[2] = total_rows;
-    status[0] = (total_words > cap_words) ? (int64_t)E_CAPACITY : 0;
+  const int64_t i = (int64_t)blockIdx.x * kLayoutThreads + t;
+  if (i < n) {
+    desc[i].word_off += base_w;
+    desc[i].row_off += base_r;
   }
 }
 
@@ -104,7 +130,7 @@ layout_kernel(const float* __restrict__ boxes, int64_t n, int H, int W,
 // ---------------------------------------------------------------------------------
 constexpr int kPasteThreads = 256;
 constexpr int kPasteWarps = kPasteThreads / 32;
-constexpr int kZeroBytes = 16384;            // shared zero source for the bulk stores
+constexpr int kZeroBytesDefault = 16384;     // shared zero source for the bulk stores
 
 __device__ __forceinline__ void bulk_store_zero(void* gdst, uint32_t smem_src, uint32_t bytes) {
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
@@ -142,8 +168,9 @@ paste_measure_kernel(const float* __restrict__ masks, const float* __restrict__ 
                      const int32_t* __restrict__ image_idx, const int32_t* __restrict__ inst_idx,
                      const int64_t* __restrict__ classes, int64_t n, int H, int W, float thr,
                      uint32_t* __restrict__ planes, int64_t* __restrict__ rows_i,
-                     Workspace ws, const int64_t* __restrict__ status) {
-  __shared__ __align__(128) unsigned char s_zero[kPlanes ? kZeroBytes : 16];
+                     Workspace ws, const int64_t* __restrict__ status, int zero_bytes,
+                     int rot_mul) {
+  extern __shared__ __align__(128) unsigned char s_zero[];     // zero_bytes (planes only)
   __shared__ __align__(16) float s_mask[kMaskPitch * kMaskPitch];
   __shared__ unsigned long long s_acc[10];
   __shared__ int s_bbox[4];
@@ -155,7 +182,7 @@ paste_measure_kernel(const float* __restrict__ masks, const float* __restrict__ 
   const int64_t plane_words = (int64_t)H * wpr;
 
   if (kPlanes) {
-    for (int k = tid; k < kZeroBytes / 16; k += kPasteThreads)
+    for (int k = tid; k < zero_bytes / 16; k += kPasteThreads)
       reinterpret_cast<uint4*>(s_zero)[k] = make_uint4(0, 0, 0, 0);
     fence_proxy_async_smem();                       // generic-proxy zeros -> visible to TMA
   }
@@ -175,13 +202,21 @@ paste_measure_kernel(const float* __restrict__ masks, const float* __restrict__ 
       const int band_lo = d.th > 0 ? d.y0 : H;              // empty tile: whole plane is zero
       const int band_hi = d.th > 0 ? d.y0 + d.th : H;
       char* base = reinterpret_cast<char*>(plane);
-      int64_t seg_lo[2] = {0, (int64_t)band_hi * wpr * 4};
-      int64_t seg_hi[2] = {(int64_t)band_lo * wpr * 4, plane_words * 4};
-      for (int sgi = 0; sgi < 2; ++sgi)
-        for (int64_t o = seg_lo[sgi]; o < seg_hi[sgi]; o += kZeroBytes) {
-          int64_t rem = seg_hi[sgi] - o;
-          bulk_store_zero(base + o, zero_smem, (uint32_t)(rem < kZeroBytes ? rem : kZeroBytes));
-        }
+      const int64_t seg_lo[2] = {0, (int64_t)band_hi * wpr * 4};
+      const int64_t seg_hi[2] = {(int64_t)band_lo * wpr * 4, plane_words * 4};
+      const int c0 = (int)((seg_hi[0] - seg_lo[0] + zero_bytes - 1) / zero_bytes);
+      const int c1 = (int)((seg_hi[1] - seg_lo[1] + zero_bytes - 1) / zero_bytes);
+      const int nc = c0 + c1;
+      // chunks are issued starting at a per-instance rotation so that the CTAs that run
+      // concurrently do not all walk the same plane-relative offsets (DRAM channel spread)
+      int k = nc > 0 ? (int)(((int64_t)inst * rot_mul) % nc) : 0;
+      for (int j = 0; j < nc; ++j) {
+        const int sgi = k < c0 ? 0 : 1;
+        const int64_t o = seg_lo[sgi] + (int64_t)(sgi == 0 ? k : k - c0) * zero_bytes;
+        const int64_t rem = seg_hi[sgi] - o;
+        bulk_store_zero(base + o, zero_smem, (uint32_t)(rem < zero_bytes ? rem : zero_bytes));
+        if (++k == nc) k = 0;
+      }
       bulk_commit();
     }
 
@@ -320,7 +355,10 @@ paste_measure_kernel(const float* __restrict__ masks, const float* __restrict__ 
 // ---------------------------------------------------------------------------------
 cudaError_t launch_layout(const float* boxes, int64_t n, int H, int W, const Workspace& ws,
                           int64_t* status, cudaStream_t stream) {
-  layout_kernel<<<1, kLayoutThreads, 0, stream>>>(boxes, n, H, W, ws.desc, ws.cap_words, status);
+  const int nblk = (int)layout_blocks(n);
+  layout_local_kernel<<<nblk, kLayoutThreads, 0, stream>>>(boxes, n, H, W, ws.desc, ws.block_sums);
+  layout_rebase_kernel<<<nblk, kLayoutThreads, 0, stream>>>(n, nblk, ws.desc, ws.block_sums,
+                                                            ws.cap_words, status);
   return cudaPeekAtLastError();
 }
 
@@ -332,23 +370,34 @@ cudaError_t launch_paste_measure(const float* masks, const float* boxes, const i
   if (n == 0) return cudaSuccess;
   int per_sm = 0;
   cudaError_t e;
+  // tuning knobs (defaults chosen on B200, see profiles/): zero-source size and rotation
+  int zero_bytes = kZeroBytesDefault, rot_mul = 0;
+  if (const char* v = getenv("UWCV_ZERO_KB")) zero_bytes = atoi(v) * 1024;
+  if (const char* v = getenv("UWCV_PASTE_ROT")) rot_mul = atoi(v);
+  if (zero_bytes < 1024 || zero_bytes > 160 * 1024 || (zero_bytes & 1023)) zero_bytes = kZeroBytesDefault;
+  const size_t dyn = planes ? (size_t)zero_bytes : 0;
   if (planes) {
+    if (dyn > 40 * 1024)
+      cudaFuncSetAttribute(paste_measure_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           (int)dyn);
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, paste_measure_kernel<true>,
-                                                      kPasteThreads, 0);
+                                                      kPasteThreads, dyn);
   } else {
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, paste_measure_kernel<false>,
-                                                      kPasteThreads, 0);
+                                                      kPasteThreads, dyn);
   }
   if (e != cudaSuccess) return e;
   if (per_sm < 1) per_sm = 1;
   int64_t grid = (int64_t)num_sms * per_sm;           // persistent: a whole number of waves
   if (grid > n) grid = n;
   if (planes)
-    paste_measure_kernel<true><<<(unsigned)grid, kPasteThreads, 0, stream>>>(
-        masks, boxes, image_idx, inst_idx, classes, n, H, W, thr, planes, rows_i, ws, status);
+    paste_measure_kernel<true><<<(unsigned)grid, kPasteThreads, dyn, stream>>>(
+        masks, boxes, image_idx, inst_idx, classes, n, H, W, thr, planes, rows_i, ws, status,
+        zero_bytes, rot_mul);
   else
-    paste_measure_kernel<false><<<(unsigned)grid, kPasteThreads, 0, stream>>>(
-        masks, boxes, image_idx, inst_idx, classes, n, H, W, thr, planes, rows_i, ws, status);
+    paste_measure_kernel<false><<<(unsigned)grid, kPasteThreads, dyn, stream>>>(
+        masks, boxes, image_idx, inst_idx, classes, n, H, W, thr, planes, rows_i, ws, status,
+        zero_bytes, rot_mul);
   return cudaPeekAtLastError();
 }
 

@@ -45,8 +45,11 @@ struct __align__(16) TileDesc {
 };
 
 // Workspace carve-up, computed identically on host and device.
+constexpr int kLayoutThreads = 1024;   // instances per layout CTA
+
 struct Workspace {
   TileDesc* desc;      // [N]
+  int64_t* block_sums; // [2 * ceil(N / 1024)]  per-CTA (tile words, tile rows) of the layout
   uint32_t* M;         // [cap_words]  mask bits
   uint32_t* V;         // [cap_words]  border-visited marks
   uint32_t* G;         // [cap_words]  "right neighbour was background" marks (negative marks)
@@ -56,15 +59,22 @@ struct Workspace {
 
 __host__ __device__ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+__host__ __device__ inline size_t layout_blocks(int64_t n) {
+  return (size_t)((n + kLayoutThreads - 1) / kLayoutThreads);
+}
+__host__ __device__ inline size_t header_bytes(int64_t n) {
+  return align_up((size_t)n * sizeof(TileDesc), 256) + align_up(layout_blocks(n) * 16 + 16, 256);
+}
 __host__ __device__ inline size_t workspace_bytes(int64_t n, int64_t tile_words) {
-  return align_up((size_t)n * sizeof(TileDesc), 256) + (size_t)tile_words * 28 + 256;
+  return header_bytes(n) + (size_t)tile_words * 28 + 256;
 }
 
 __host__ __device__ inline Workspace carve(void* ws, size_t ws_bytes, int64_t n) {
   Workspace w;
   char* p = (char*)ws;
   w.desc = (TileDesc*)p;
-  size_t d = align_up((size_t)n * sizeof(TileDesc), 256);
+  w.block_sums = (int64_t*)(p + align_up((size_t)n * sizeof(TileDesc), 256));
+  size_t d = header_bytes(n);
   int64_t cap = ws_bytes > d + 256 ? (int64_t)((ws_bytes - d - 256) / 28) : 0;
   cap &= ~(int64_t)3;                         // keep every plane 16-byte aligned
   w.cap_words = cap;

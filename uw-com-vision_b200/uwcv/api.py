@@ -239,7 +239,8 @@ class Engine:
                 _ptr(planes), _ptr(rows_i), _ptr(rows_f), _ptr(ws), ws.numel(),
                 _ptr(status), _stream_ptr(dev), int(stages))
         _lib.check(rc, "uwcv_paste_measure")
-        self.launches += bin(stages & 7).count("1") if n > 0 else 0
+        if n > 0:        # layout = 2 kernels, paste = 1, contour = 1
+            self.launches += 2 * (stages & 1) + ((stages >> 1) & 1) + ((stages >> 2) & 1)
         return rows_i, rows_f, status
 
     def check_status(self) -> None:
