@@ -129,7 +129,11 @@ layout_rebase_kernel(int64_t n, int nblk, TileDesc* __restrict__ desc,
 // kernel 1+2: paste + threshold + bit-pack + raw moments / bbox
 // ---------------------------------------------------------------------------------
 constexpr int kPasteThreads = 256;
-constexpr int kPasteWarps = kPasteThreads / 32;
+constexpr int kPasteWarps = 7;                       // compute warps; warp 7 only issues TMA fills
+constexpr int kComputeThreads = kPasteWarps * 32;    // 224
+__device__ __forceinline__ void compute_barrier() {  // named barrier over the compute warps
+  asm volatile("bar.sync 1, %0;" ::"n"(kComputeThreads) : "memory");
+}
 constexpr int kZeroBytesDefault = 16384;     // shared zero source for the bulk stores
 
 __device__ __forceinline__ void bulk_store_zero(void* gdst, uint32_t smem_src, uint32_t bytes) {
@@ -169,7 +173,7 @@ paste_measure_kernel(const float* __restrict__ masks, const float* __restrict__ 
                      const int64_t* __restrict__ classes, int64_t n, int H, int W, float thr,
                      uint32_t* __restrict__ planes, int64_t* __restrict__ rows_i,
                      Workspace ws, const int64_t* __restrict__ status, int zero_bytes,
-                     int rot_mul) {
+                     int rot_mul, int fill_mode, int debug_skip) {
   extern __shared__ __align__(128) unsigned char s_zero[];     // zero_bytes (planes only)
   __shared__ __align__(16) float s_mask[kMaskPitch * kMaskPitch];
   __shared__ unsigned long long s_acc[10];
@@ -191,50 +195,65 @@ paste_measure_kernel(const float* __restrict__ masks, const float* __restrict__ 
   __syncthreads();
   const uint32_t zero_smem = (uint32_t)__cvta_generic_to_shared(s_zero);
 
+  // ---- warp 7: zero rows above / below every band of this CTA's instances ---------------
+  // One thread streams TMA bulk stores (shared zero buffer -> plane) for the whole instance
+  // list, decoupled from the compute warps: the two never touch the same bytes, so no
+  // ordering is needed and the fill runs at the speed of the TMA / HBM write path while the
+  // other seven warps paste, pack and reduce.
+  if (warp == kPasteWarps) {
+    if (kPlanes && lane == 0 && fill_mode == 0) {
+      for (int64_t inst = blockIdx.x; inst < n; inst += gridDim.x) {
+        const TileDesc d = ws.desc[inst];
+        char* base = reinterpret_cast<char*>(planes + inst * plane_words);
+        const int band_lo = d.th > 0 ? d.y0 : H;            // empty tile: whole plane is zero
+        const int band_hi = d.th > 0 ? d.y0 + d.th : H;
+        const int64_t seg_lo[2] = {0, (int64_t)band_hi * wpr * 4};
+        const int64_t seg_hi[2] = {(int64_t)band_lo * wpr * 4, plane_words * 4};
+        for (int sgi = 0; sgi < 2; ++sgi)
+          for (int64_t o = seg_lo[sgi]; o < seg_hi[sgi]; o += zero_bytes) {
+            const int64_t rem = seg_hi[sgi] - o;
+            bulk_store_zero(base + o, zero_smem, (uint32_t)(rem < zero_bytes ? rem : zero_bytes));
+          }
+        bulk_commit();
+      }
+      bulk_wait_read_all();                            // the zero source must outlive the copies
+    }
+    return;
+  }
+
   for (int64_t inst = blockIdx.x; inst < n; inst += gridDim.x) {
     const TileDesc d = ws.desc[inst];
     const float bx0 = boxes[4 * inst + 0], by0 = boxes[4 * inst + 1];
     const float bx1 = boxes[4 * inst + 2], by1 = boxes[4 * inst + 3];
     uint32_t* plane = kPlanes ? planes + inst * plane_words : nullptr;
 
-    // ---- zero rows above and below the band: TMA bulk stores by one thread --------
-    if (kPlanes && tid == 0) {
-      const int band_lo = d.th > 0 ? d.y0 : H;              // empty tile: whole plane is zero
+    // fill_mode 1 (profiling): zero rows by 16-byte LSU stores from the compute warps
+    if (kPlanes && fill_mode == 1) {
+      const int band_lo = d.th > 0 ? d.y0 : H;
       const int band_hi = d.th > 0 ? d.y0 + d.th : H;
-      char* base = reinterpret_cast<char*>(plane);
-      const int64_t seg_lo[2] = {0, (int64_t)band_hi * wpr * 4};
-      const int64_t seg_hi[2] = {(int64_t)band_lo * wpr * 4, plane_words * 4};
-      const int c0 = (int)((seg_hi[0] - seg_lo[0] + zero_bytes - 1) / zero_bytes);
-      const int c1 = (int)((seg_hi[1] - seg_lo[1] + zero_bytes - 1) / zero_bytes);
-      const int nc = c0 + c1;
-      // chunks are issued starting at a per-instance rotation so that the CTAs that run
-      // concurrently do not all walk the same plane-relative offsets (DRAM channel spread)
-      int k = nc > 0 ? (int)(((int64_t)inst * rot_mul) % nc) : 0;
-      for (int j = 0; j < nc; ++j) {
-        const int sgi = k < c0 ? 0 : 1;
-        const int64_t o = seg_lo[sgi] + (int64_t)(sgi == 0 ? k : k - c0) * zero_bytes;
-        const int64_t rem = seg_hi[sgi] - o;
-        bulk_store_zero(base + o, zero_smem, (uint32_t)(rem < zero_bytes ? rem : zero_bytes));
-        if (++k == nc) k = 0;
-      }
-      bulk_commit();
+      uint4* base = reinterpret_cast<uint4*>(plane);
+      const int64_t hi0 = (int64_t)band_lo * wpr / 4;
+      const int64_t lo1 = (int64_t)band_hi * wpr / 4, hi1 = plane_words / 4;
+      const uint4 z = make_uint4(0, 0, 0, 0);
+      for (int64_t o = tid; o < hi0; o += kComputeThreads) __stcs(base + o, z);
+      for (int64_t o = lo1 + tid; o < hi1; o += kComputeThreads) __stcs(base + o, z);
     }
 
     // ---- stage the 28x28 probabilities into the zero-framed copy --------------------
     const float* msrc = masks + inst * (kMaskSide * kMaskSide);
-    for (int k = tid; k < kMaskSide * kMaskSide; k += kPasteThreads) {
+    for (int k = tid; k < kMaskSide * kMaskSide; k += kComputeThreads) {
       int r = k / kMaskSide, c = k - r * kMaskSide;
       s_mask[(r + kPad) * kMaskPitch + c + kPad] = __ldg(msrc + k);
     }
     if (tid < 10) s_acc[tid] = 0ull;
     if (tid == 0) { s_bbox[0] = INT_MAX; s_bbox[1] = INT_MAX; s_bbox[2] = -1; s_bbox[3] = -1; }
-    __syncthreads();
+    compute_barrier();
 
     // ---- zero the non-tile words of the band rows (ordinary stores) ----------------
-    if (kPlanes && d.th > 0) {
+    if (kPlanes && d.th > 0 && !(debug_skip & 2)) {
       const int outside = wpr - d.tw;
       const int total = outside * d.th;
-      for (int k = tid; k < total; k += kPasteThreads) {
+      for (int k = tid; k < total; k += kComputeThreads) {
         int r = k / outside, c = k - r * outside;
         if (c >= d.wx0) c += d.tw;
         plane[(int64_t)(d.y0 + r) * wpr + c] = 0u;
@@ -249,7 +268,7 @@ paste_measure_kernel(const float* __restrict__ masks, const float* __restrict__ 
     uint32_t* tV = ws.V + d.word_off;
     uint32_t* tG = ws.G + d.word_off;
 
-    for (int g = warp; g * 32 < d.th; g += kPasteWarps) {
+    for (int g = warp; g * 32 < d.th && !(debug_skip & 1); g += kPasteWarps) {
       const int rbase = g * 32;
       int rowb; float rn, rs;
       axis_coord(d.y0 + rbase + lane, by0, by1, rowb, rn, rs);
@@ -324,7 +343,7 @@ paste_measure_kernel(const float* __restrict__ masks, const float* __restrict__ 
       atomicMin(&s_bbox[0], xmin); atomicMin(&s_bbox[1], ymin);
       atomicMax(&s_bbox[2], xmax); atomicMax(&s_bbox[3], ymax);
     }
-    __syncthreads();
+    compute_barrier();
     // ---- integer part of the row --------------------------------------------------------
     if (tid < kNumInt) {
       long long v = 0;
@@ -345,9 +364,8 @@ paste_measure_kernel(const float* __restrict__ masks, const float* __restrict__ 
       }
       rows_i[inst * kNumInt + tid] = v;
     }
-    __syncthreads();                                 // s_mask / s_acc are rewritten next round
+    compute_barrier();                                 // s_mask / s_acc are rewritten next round
   }
-  if (kPlanes && tid == 0) bulk_wait_read_all();     // shared zero source must outlive the copies
 }
 
 // ---------------------------------------------------------------------------------
@@ -371,7 +389,9 @@ cudaError_t launch_paste_measure(const float* masks, const float* boxes, const i
   int per_sm = 0;
   cudaError_t e;
   // tuning knobs (defaults chosen on B200, see profiles/): zero-source size and rotation
-  int zero_bytes = kZeroBytesDefault, rot_mul = 0;
+  int zero_bytes = kZeroBytesDefault, rot_mul = 0, fill_mode = 0, debug_skip = 0;
+  if (const char* v = getenv("UWCV_DEBUG_SKIP")) debug_skip = atoi(v);   // profiling only
+  if (const char* v = getenv("UWCV_FILL")) fill_mode = atoi(v);
   if (const char* v = getenv("UWCV_ZERO_KB")) zero_bytes = atoi(v) * 1024;
   if (const char* v = getenv("UWCV_PASTE_ROT")) rot_mul = atoi(v);
   if (zero_bytes < 1024 || zero_bytes > 160 * 1024 || (zero_bytes & 1023)) zero_bytes = kZeroBytesDefault;
@@ -393,11 +413,11 @@ cudaError_t launch_paste_measure(const float* masks, const float* boxes, const i
   if (planes)
     paste_measure_kernel<true><<<(unsigned)grid, kPasteThreads, dyn, stream>>>(
         masks, boxes, image_idx, inst_idx, classes, n, H, W, thr, planes, rows_i, ws, status,
-        zero_bytes, rot_mul);
+        zero_bytes, rot_mul, fill_mode, debug_skip);
   else
     paste_measure_kernel<false><<<(unsigned)grid, kPasteThreads, dyn, stream>>>(
         masks, boxes, image_idx, inst_idx, classes, n, H, W, thr, planes, rows_i, ws, status,
-        zero_bytes, rot_mul);
+        zero_bytes, rot_mul, fill_mode, debug_skip);
   return cudaPeekAtLastError();
 }
 
