@@ -311,3 +311,67 @@ def test_full_size_properties_and_sampled_parity():
         rows = np.flatnonzero(table["image_idx"] == k)[idx.numpy()]
         t = table.select(rows)
         compare_tables(t, ri, rf, skip_int=("inst_idx",))
+
+
+def test_random_box_fuzz_against_grid_sample():
+    """400 random boxes (extreme aspect ratios, sub-pixel, off-frame, frame-sized) with
+    random / binary / constant probability maps: bit-exact against the oracle paste."""
+    g = torch.Generator().manual_seed(2024)
+    H, W = 144, 208
+    n = 400
+    cx = torch.rand(n, generator=g) * (W + 40) - 20
+    cy = torch.rand(n, generator=g) * (H + 40) - 20
+    w = torch.exp(torch.rand(n, generator=g) * 9 - 3)          # 0.05 .. 400 px
+    h = torch.exp(torch.rand(n, generator=g) * 9 - 3)
+    boxes = torch.stack([cx - w / 2, cy - h / 2, cx + w / 2, cy + h / 2], 1)
+    boxes[:, 0::2] = boxes[:, 0::2].clamp(0, W)
+    boxes[:, 1::2] = boxes[:, 1::2].clamp(0, H)
+    keep = ((boxes[:, 2] - boxes[:, 0]) > 0) & ((boxes[:, 3] - boxes[:, 1]) > 0)
+    boxes = boxes[keep].contiguous()
+    n = len(boxes)
+    masks = torch.rand(n, 28, 28, generator=g)
+    masks[::5] = (masks[::5] > 0.5).float()
+    masks[1::7] = 0.5
+    masks[2::11] = 1.0
+    masks[3::13] = 0.0
+    ref = d2.paste_masks_in_image(masks, boxes, (H, W))
+    out = uwcv.paste_masks_in_image(masks, boxes, (H, W)).cpu()
+    bad = (out != ref).flatten(1).any(1).nonzero().flatten()
+    assert bad.numel() == 0, f"instances with differing masks: {bad[:10].tolist()}, boxes {boxes[bad[:3]]}"
+    assert n > 300
+
+
+def test_config4_dense_pipeline():
+    """BASELINE config-4 shape: 4096 x 4096 micrograph, ~20 k clustered candidates ->
+    score filter + per-class NMS on the GPU -> ~5-6 k small overlapping survivors ->
+    paste + measure (full-frame planes would need 10.5 GB: cropped contract here) ->
+    properties on all rows + oracle parity on a sample."""
+    H = W = 4096
+    b, s, c = synth.clustered_candidates(5000, H, W, seed=99)
+    eng = api.Engine.get()
+    dev = eng.device
+    keep, cnt = eng.nms(b.to(dev), s.to(dev), c.to(dev), [0, len(b)], 0.05, 0.5, 6000)
+    k = int(cnt[0])
+    keep = keep[:k].cpu()
+    ref = d2.batched_nms_vanilla(b, s, c, 0.5)
+    ref = ref[s[ref] > 0.05][:6000]
+    assert torch.equal(keep, ref)
+    g = torch.Generator().manual_seed(8)
+    inst = uwcv.Instances((H, W))
+    inst.pred_boxes = uwcv.Boxes(b[keep])
+    inst.scores = s[keep]
+    inst.pred_classes = c[keep]
+    inst.pred_masks = synth.blob_probs(k, g)[:, None]
+    table = uwcv.measure_instances(inst, (H, W))
+    assert len(table) == k and k > 4000
+    v = table["valid"] == 1
+    assert v.mean() > 0.95
+    assert (table["bbox_x1"][v] < W).all() and (table["bbox_y1"][v] < H).all()
+    assert (table["area_px"][v] >= table["contour_area"][v]).all()
+    counts = uwcv.get_counts(inst)
+    recs = uwcv.group_by_class(table)
+    assert [r["count"] for r in recs] == counts
+    idx = torch.arange(0, k, 41)
+    ri, rf = P.oracle_table([inst[idx]], (H, W))
+    compare_tables(table.select(idx.numpy()), ri, rf, skip_int=("inst_idx",))
+    print(f"config 4: {len(b)} candidates -> {k} instances, {int(v.sum())} non-empty")
