@@ -114,6 +114,50 @@ int uwcv_paste_measure_stages(const float* masks, const float* boxes, const int3
 int uwcv_unpack_planes(const uint32_t* bitplanes, int64_t N, int H, int W, uint8_t* out,
                        void* stream);
 
+/*
+ * Union / connected-component mode -- the reference-literal GetMask_Contours
+ * (nn_inference.py:394-459): the masks of the selected class are OR-ed into one image and
+ * EVERY external contour of that union is measured (touching instances merge).
+ *
+ * Call order: uwcv_paste_measure_stages(stages = 3, bitplanes = NULL) on the selected
+ * instances, then group them on the host (instances of one image whose 1-pixel-dilated pixel
+ * boxes, rows_i columns bbox_*, overlap belong to one group), then uwcv_union_measure.
+ *
+ *   paste_workspace / paste_ws_bytes / N   exactly as passed to uwcv_paste_measure_stages
+ *   member_group   [N] int32: group of every instance, -1 = not part of any group (empty mask)
+ *   group_desc     [G] uwcv_tile: word-aligned window of the frame covering the group's pixel
+ *                  boxes; word_off = offset of the group's tile in group_planes (tw * th words)
+ *   group_image    [G] int32: image index reported in the rows
+ *   group_planes   [3 * group_words] uint32 scratch (mask / visited / sign planes)
+ *   rec_workspace  >= uwcv_union_workspace_bytes(rec_cap, ext_rows_cap)
+ *   rec_cap        capacity in contours; ext_rows_cap capacity in (contour, row) pairs
+ *   rows_i  [rec_cap, 10] int64 out: image_idx, group, start_x, start_y (raster-first pixel of
+ *           the component), brect_x, brect_y, brect_w, brect_h (cv2.boundingRect), n_points, valid
+ *   rows_f  [rec_cap, 16] float64 out: contour_area, perimeter, rect cx, cy, w, h, angle, Feret,
+ *           Aspect_Ratio, Roundness, Circularity, Sphericity, Length, Width, CircularED, Chords
+ *   counters [4] int64 out (device): [0] contours found, [1] 0 or UWCV_E_CAPACITY (no row is
+ *           valid then; retry with counters[0] / counters[2] as capacities), [2] extreme rows needed
+ * Rows are in discovery order; the reference's order is a stable sort by brect_x of the rows
+ * taken in decreasing (start_y, start_x) order, and it drops contour_area < 100.
+ */
+typedef struct uwcv_tile {
+  int32_t wx0;        /* first 32-pixel word column */
+  int32_t y0;         /* first pixel row            */
+  int32_t tw;         /* width in words             */
+  int32_t th;         /* height in rows             */
+  int64_t word_off;   /* offset of the tile's first word */
+  int64_t reserved;
+} uwcv_tile;
+
+size_t uwcv_union_workspace_bytes(int64_t rec_cap, int64_t ext_rows_cap);
+
+int uwcv_union_measure(const void* paste_workspace, size_t paste_ws_bytes, int64_t N,
+                       const int32_t* member_group, const uwcv_tile* group_desc,
+                       const int32_t* group_image, int64_t G, uint32_t* group_planes,
+                       int64_t group_words, void* rec_workspace, size_t rec_ws_bytes,
+                       int64_t rec_cap, int64_t ext_rows_cap, double pixels_per_metric,
+                       int64_t* rows_i, double* rows_f, int64_t* counters, void* stream);
+
 /* Bytes of workspace for uwcv_nms_filter; image_off is a HOST array [B + 1]. */
 size_t uwcv_nms_workspace_bytes(const int64_t* image_off, int B);
 

@@ -375,3 +375,34 @@ def test_config4_dense_pipeline():
     ri, rf = P.oracle_table([inst[idx]], (H, W))
     compare_tables(table.select(idx.numpy()), ri, rf, skip_int=("inst_idx",))
     print(f"config 4: {len(b)} candidates -> {k} instances, {int(v.sum())} non-empty")
+
+
+def test_union_mode_equals_reference_literal_rows():
+    """f1: reference-literal GetMask_Contours (union of the class masks, every external
+    contour, left-to-right) for overlapping / touching / multi-blob instances."""
+    H, W = 384, 512
+    batch = []
+    for k in range(3):
+        inst = synth.blob_instances(k, 120, H, W, seed=300, size_range=(10.0, 110.0))
+        batch.append(inst)
+    total = 0
+    for cls in range(4):
+        ut = uwcv.measure_union(batch, (H, W), classes_of_interest=[cls])
+        for k, inst in enumerate(batch):
+            try:
+                ref = P.reference_literal_rows(inst, (H, W), [cls])
+            except ValueError:
+                ref = np.zeros((0, 9))
+            ref = np.zeros((0, 9)) if ref is None else ref
+            mine = ut.reference_rows(image_idx=k)
+            assert mine.shape == ref.shape, (cls, k, mine.shape, ref.shape)
+            if len(ref):
+                rel = np.abs(mine - ref) / np.maximum(np.abs(ref), 1e-30)
+                assert rel.max() <= 1e-6, (cls, k, rel.max(axis=0))
+            total += len(ref)
+    assert total > 60
+    # union over all classes at once (classes_of_interest=None == every class)
+    ut = uwcv.measure_union(batch[0], (H, W))
+    ref = P.reference_literal_rows(batch[0], (H, W), [0, 1, 2, 3])
+    assert np.allclose(ut.reference_rows(), ref, rtol=1e-6, atol=0)
+    print(f"union mode: {total} reference rows matched")

@@ -213,6 +213,13 @@ paste_measure_kernel(const float* __restrict__ masks, const float* __restrict__ 
           for (int64_t o = seg_lo[sgi]; o < seg_hi[sgi]; o += zero_bytes) {
             const int64_t rem = seg_hi[sgi] - o;
             bulk_store_zero(base + o, zero_smem, (uint32_t)(rem < zero_bytes ? rem : zero_bytes));
+            if (rot_mul > 0) {                       // bounded number of bulk stores in flight
+              bulk_commit();
+              if (rot_mul == 1) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+              else if (rot_mul == 2) asm volatile("cp.async.bulk.wait_group.read 2;" ::: "memory");
+              else if (rot_mul == 4) asm volatile("cp.async.bulk.wait_group.read 4;" ::: "memory");
+              else asm volatile("cp.async.bulk.wait_group.read 8;" ::: "memory");
+            }
           }
         bulk_commit();
       }

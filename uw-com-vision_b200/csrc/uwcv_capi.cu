@@ -11,6 +11,10 @@ cudaError_t launch_contour_measure(int64_t, const float*, double, int64_t*, doub
                                    const Workspace&, const int64_t*, int, cudaStream_t);
 cudaError_t launch_unpack(const uint32_t*, int64_t, int, int, uint8_t*, int, cudaStream_t);
 size_t nms_workspace_bytes_host(const int64_t*, int);
+size_t union_workspace_bytes_host(int64_t, int64_t);
+cudaError_t launch_union(int64_t, const Workspace&, const int32_t*, const TileDesc*, const int32_t*,
+                         int64_t, uint32_t*, int64_t, void*, int64_t, int64_t, double, int64_t*,
+                         double*, int64_t*, int, cudaStream_t);
 cudaError_t launch_nms(const float*, const float*, const int64_t*, const int64_t*, int, float,
                        double, int, int64_t*, int32_t*, void*, cudaStream_t);
 }  // namespace uwcv
@@ -104,6 +108,42 @@ int uwcv_unpack_planes(const uint32_t* bitplanes, int64_t N, int H, int W, uint8
   if (misaligned(bitplanes)) return UWCV_E_ALIGN;
   return uwcv::launch_unpack(bitplanes, N, H, W, out, num_sms(),
                              reinterpret_cast<cudaStream_t>(stream)) == cudaSuccess
+             ? UWCV_OK : UWCV_E_LAUNCH;
+}
+
+size_t uwcv_union_workspace_bytes(int64_t rec_cap, int64_t ext_rows_cap) {
+  if (rec_cap < 0) rec_cap = 0;
+  if (ext_rows_cap < 0) ext_rows_cap = 0;
+  return uwcv::union_workspace_bytes_host(rec_cap, ext_rows_cap);
+}
+
+int uwcv_union_measure(const void* paste_workspace, size_t paste_ws_bytes, int64_t N,
+                       const int32_t* member_group, const uwcv_tile* group_desc,
+                       const int32_t* group_image, int64_t G, uint32_t* group_planes,
+                       int64_t group_words, void* rec_workspace, size_t rec_ws_bytes,
+                       int64_t rec_cap, int64_t ext_rows_cap, double pixels_per_metric,
+                       int64_t* rows_i, double* rows_f, int64_t* counters, void* stream) {
+  static_assert(sizeof(uwcv_tile) == sizeof(uwcv::TileDesc), "uwcv_tile mirrors TileDesc");
+  if (N < 0 || G < 0 || group_words < 0 || rec_cap < 0 || ext_rows_cap < 0) return UWCV_E_SHAPE;
+  if (!(pixels_per_metric > 0.0)) return UWCV_E_SHAPE;
+  if (!counters) return UWCV_E_NULL;
+  if (N > 0 && G > 0) {
+    if (!paste_workspace || !member_group || !group_desc || !group_image || !group_planes ||
+        !rec_workspace || !rows_i || !rows_f)
+      return UWCV_E_NULL;
+    if (misaligned(paste_workspace) || misaligned(group_desc) || misaligned(group_planes) ||
+        misaligned(rec_workspace) || misaligned(rows_i) || misaligned(rows_f))
+      return UWCV_E_ALIGN;
+    if (rec_ws_bytes < uwcv::union_workspace_bytes_host(rec_cap, ext_rows_cap))
+      return UWCV_E_WORKSPACE;
+    if (paste_ws_bytes < uwcv::workspace_bytes(N, 4)) return UWCV_E_WORKSPACE;
+  }
+  const uwcv::Workspace ws = uwcv::carve(const_cast<void*>(paste_workspace), paste_ws_bytes, N);
+  return uwcv::launch_union(N, ws, member_group,
+                            reinterpret_cast<const uwcv::TileDesc*>(group_desc), group_image, G,
+                            group_planes, group_words, rec_workspace, rec_cap, ext_rows_cap,
+                            pixels_per_metric, rows_i, rows_f, counters, num_sms(),
+                            reinterpret_cast<cudaStream_t>(stream)) == cudaSuccess
              ? UWCV_OK : UWCV_E_LAUNCH;
 }
 

@@ -42,6 +42,11 @@ def lib() -> C.CDLL:
     L.uwcv_paste_measure_stages.argtypes = L.uwcv_paste_measure.argtypes + [i32]
     L.uwcv_unpack_planes.restype = C.c_int
     L.uwcv_unpack_planes.argtypes = [vp, i64, i32, i32, vp, vp]
+    L.uwcv_union_workspace_bytes.restype = sz
+    L.uwcv_union_workspace_bytes.argtypes = [i64, i64]
+    L.uwcv_union_measure.restype = C.c_int
+    L.uwcv_union_measure.argtypes = [vp, sz, i64, vp, vp, vp, i64, vp, i64, vp, sz, i64, i64, f64,
+                                     vp, vp, vp, vp]
     L.uwcv_nms_workspace_bytes.restype = sz
     L.uwcv_nms_workspace_bytes.argtypes = [C.POINTER(C.c_int64), i32]
     L.uwcv_nms_filter.restype = C.c_int
@@ -52,7 +57,8 @@ def lib() -> C.CDLL:
 
 
 EXPORTS = ("uwcv_version", "uwcv_strerror", "uwcv_plane_row_words", "uwcv_workspace_bytes",
-           "uwcv_paste_measure", "uwcv_paste_measure_stages", "uwcv_unpack_planes", "uwcv_nms_workspace_bytes",
+           "uwcv_paste_measure", "uwcv_paste_measure_stages", "uwcv_unpack_planes",
+           "uwcv_union_workspace_bytes", "uwcv_union_measure", "uwcv_nms_workspace_bytes",
            "uwcv_nms_filter")
 
 
