@@ -158,8 +158,9 @@ int uwcv_union_measure(const void* paste_workspace, size_t paste_ws_bytes, int64
                        int64_t rec_cap, int64_t ext_rows_cap, double pixels_per_metric,
                        int64_t* rows_i, double* rows_f, int64_t* counters, void* stream);
 
-/* Bytes of workspace for uwcv_nms_filter; image_off is a HOST array [B + 1]. */
-size_t uwcv_nms_workspace_bytes(const int64_t* image_off, int B);
+/* Bytes of workspace for uwcv_nms_filter; image_off is a HOST array [B + 1];
+ * num_classes <= 0 means 128. */
+size_t uwcv_nms_workspace_bytes(const int64_t* image_off, int B, int num_classes);
 
 /*
  * uwcv_nms_filter -- batched score filter + per-class NMS + top-k.
@@ -170,8 +171,11 @@ size_t uwcv_nms_workspace_bytes(const int64_t* image_off, int B);
  *
  *   boxes      [R, 4] float32 XYXY (already clipped), candidates of image b are rows
  *              image_off[b] .. image_off[b+1]-1
- *   scores     [R] float32,  classes [R] int64
- *   image_off  HOST pointer, [B + 1] int64, image_off[0] = 0, non-decreasing
+ *   scores     [R] float32,  classes [R] int64 in [0, num_classes) (others are dropped)
+ *   image_off  HOST pointer, [B + 1] int64, image_off[0] = 0, non-decreasing; at most
+ *              262144 candidates per image
+ *   num_classes  K of the box head (<= 8192; <= 0 means 128): the serial part of NMS runs
+ *              once per (image, class) in parallel
  *   score_thr  keep candidates with score > score_thr (float32 compare)
  *   iou_thr    suppress when (double)iou > iou_thr
  *   topk       per image, < 0 = unlimited
@@ -180,9 +184,9 @@ size_t uwcv_nms_workspace_bytes(const int64_t* image_off, int B);
  *   keep_count [B] int32 out
  */
 int uwcv_nms_filter(const float* boxes, const float* scores, const int64_t* classes,
-                    const int64_t* image_off, int B, float score_thr, double iou_thr, int topk,
-                    int64_t* keep, int32_t* keep_count, void* workspace, size_t ws_bytes,
-                    void* stream);
+                    const int64_t* image_off, int B, int num_classes, float score_thr,
+                    double iou_thr, int topk, int64_t* keep, int32_t* keep_count, void* workspace,
+                    size_t ws_bytes, void* stream);
 
 #ifdef __cplusplus
 }

@@ -53,9 +53,9 @@ def test_argument_validation_without_gpu():
     assert L.uwcv_unpack_planes(None, 1, 8, 8, None, None) == -1
     assert L.uwcv_unpack_planes(None, 0, 8, 8, None, None) == 0
     off = (C.c_int64 * 2)(0, -5)
-    assert L.uwcv_nms_filter(None, None, None, off, 1, 0.5, 0.5, 10, None, C.addressof(st), None, 0, None) == -2
+    assert L.uwcv_nms_filter(None, None, None, off, 1, 4, 0.5, 0.5, 10, None, C.addressof(st), None, 0, None) == -2
     off = (C.c_int64 * 2)(1, 5)
-    assert L.uwcv_nms_filter(None, None, None, off, 1, 0.5, 0.5, 10, None, C.addressof(st), None, 0, None) == -2
+    assert L.uwcv_nms_filter(None, None, None, off, 1, 4, 0.5, 0.5, 10, None, C.addressof(st), None, 0, None) == -2
 
 
 def test_no_cpu_fallback():

@@ -10,12 +10,12 @@ cudaError_t launch_paste_measure(const float*, const float*, const int32_t*, con
 cudaError_t launch_contour_measure(int64_t, const float*, double, int64_t*, double*,
                                    const Workspace&, const int64_t*, int, cudaStream_t);
 cudaError_t launch_unpack(const uint32_t*, int64_t, int, int, uint8_t*, int, cudaStream_t);
-size_t nms_workspace_bytes_host(const int64_t*, int);
+size_t nms_workspace_bytes_host(const int64_t*, int, int);
 size_t union_workspace_bytes_host(int64_t, int64_t);
 cudaError_t launch_union(int64_t, const Workspace&, const int32_t*, const TileDesc*, const int32_t*,
                          int64_t, uint32_t*, int64_t, void*, int64_t, int64_t, double, int64_t*,
                          double*, int64_t*, int, cudaStream_t);
-cudaError_t launch_nms(const float*, const float*, const int64_t*, const int64_t*, int, float,
+cudaError_t launch_nms(const float*, const float*, const int64_t*, const int64_t*, int, int, float,
                        double, int, int64_t*, int32_t*, void*, cudaStream_t);
 }  // namespace uwcv
 
@@ -147,16 +147,19 @@ int uwcv_union_measure(const void* paste_workspace, size_t paste_ws_bytes, int64
              ? UWCV_OK : UWCV_E_LAUNCH;
 }
 
-size_t uwcv_nms_workspace_bytes(const int64_t* image_off, int B) {
+size_t uwcv_nms_workspace_bytes(const int64_t* image_off, int B, int num_classes) {
   if (!image_off || B <= 0) return 256;
-  return uwcv::nms_workspace_bytes_host(image_off, B);
+  if (num_classes <= 0) num_classes = 128;
+  return uwcv::nms_workspace_bytes_host(image_off, B, num_classes);
 }
 
 int uwcv_nms_filter(const float* boxes, const float* scores, const int64_t* classes,
-                    const int64_t* image_off, int B, float score_thr, double iou_thr, int topk,
-                    int64_t* keep, int32_t* keep_count, void* workspace, size_t ws_bytes,
-                    void* stream) {
+                    const int64_t* image_off, int B, int num_classes, float score_thr,
+                    double iou_thr, int topk, int64_t* keep, int32_t* keep_count, void* workspace,
+                    size_t ws_bytes, void* stream) {
   if (B < 0) return UWCV_E_SHAPE;
+  if (num_classes <= 0) num_classes = 128;
+  if (num_classes > 8192) return UWCV_E_TOO_LARGE;
   if (B == 0) return UWCV_OK;
   if (!image_off || !keep_count) return UWCV_E_NULL;
   if (image_off[0] != 0) return UWCV_E_SHAPE;
@@ -170,9 +173,9 @@ int uwcv_nms_filter(const float* boxes, const float* scores, const int64_t* clas
   if (R > 0 && (!boxes || !scores || !classes || !keep)) return UWCV_E_NULL;
   if (!workspace) return UWCV_E_NULL;
   if (misaligned(boxes) || misaligned(workspace)) return UWCV_E_ALIGN;
-  if (ws_bytes < uwcv::nms_workspace_bytes_host(image_off, B)) return UWCV_E_WORKSPACE;
+  if (ws_bytes < uwcv::nms_workspace_bytes_host(image_off, B, num_classes)) return UWCV_E_WORKSPACE;
   if (topk < 0) topk = 0x7fffffff;
-  return uwcv::launch_nms(boxes, scores, classes, image_off, B, score_thr, iou_thr, topk, keep,
+  return uwcv::launch_nms(boxes, scores, classes, image_off, B, num_classes, score_thr, iou_thr, topk, keep,
                           keep_count, workspace, reinterpret_cast<cudaStream_t>(stream)) ==
                  cudaSuccess
              ? UWCV_OK : UWCV_E_LAUNCH;

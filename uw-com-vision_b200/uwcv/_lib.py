@@ -48,9 +48,9 @@ def lib() -> C.CDLL:
     L.uwcv_union_measure.argtypes = [vp, sz, i64, vp, vp, vp, i64, vp, i64, vp, sz, i64, i64, f64,
                                      vp, vp, vp, vp]
     L.uwcv_nms_workspace_bytes.restype = sz
-    L.uwcv_nms_workspace_bytes.argtypes = [C.POINTER(C.c_int64), i32]
+    L.uwcv_nms_workspace_bytes.argtypes = [C.POINTER(C.c_int64), i32, i32]
     L.uwcv_nms_filter.restype = C.c_int
-    L.uwcv_nms_filter.argtypes = [vp, vp, vp, C.POINTER(C.c_int64), i32, f32, f64, i32,
+    L.uwcv_nms_filter.argtypes = [vp, vp, vp, C.POINTER(C.c_int64), i32, i32, f32, f64, i32,
                                   vp, vp, vp, sz, vp]
     _lib = L
     return L

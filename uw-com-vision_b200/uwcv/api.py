@@ -275,8 +275,10 @@ class Engine:
         return out
 
     def nms(self, boxes: torch.Tensor, scores: torch.Tensor, classes: torch.Tensor,
-            image_off: Sequence[int], score_thresh: float, nms_thresh: float, topk: int):
-        """boxes [R,4] f32, scores [R] f32, classes [R] i64 on device; image_off host ints [B+1].
+            image_off: Sequence[int], score_thresh: float, nms_thresh: float, topk: int,
+            num_classes: int = 0):
+        """boxes [R,4] f32, scores [R] f32, classes [R] i64 on device; image_off host ints [B+1];
+        num_classes = K of the box head (0: 128).
         Returns (keep [R] int64, keep_count [B] int32) device tensors."""
         B = len(image_off) - 1
         off = (C.c_int64 * (B + 1))(*[int(v) for v in image_off])
@@ -284,15 +286,15 @@ class Engine:
         dev = self.device
         keep = torch.empty(max(R, 1), dtype=torch.int64, device=dev)
         cnt = torch.zeros(max(B, 1), dtype=torch.int32, device=dev)
-        nbytes = self.L.uwcv_nms_workspace_bytes(off, B)
+        nbytes = self.L.uwcv_nms_workspace_bytes(off, B, int(num_classes))
         ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
         with torch.cuda.device(dev):
             rc = self.L.uwcv_nms_filter(_ptr(boxes), _ptr(scores), _ptr(classes), off, B,
-                                        float(score_thresh), float(nms_thresh), int(topk),
+                                        int(num_classes), float(score_thresh), float(nms_thresh), int(topk),
                                         _ptr(keep), _ptr(cnt), _ptr(ws), ws.numel(),
                                         _stream_ptr(dev))
         _lib.check(rc, "uwcv_nms_filter")
-        self.launches += 4 if R > 0 else 3
+        self.launches += 5 if R > 0 else 3
         self._nms_ws = ws           # keep alive until the stream has consumed it
         return keep, cnt
 
@@ -390,7 +392,7 @@ def fast_rcnn_inference_single_image(boxes: torch.Tensor, scores: torch.Tensor,
     cand_cls = torch.arange(K, device=dev, dtype=torch.int64).repeat(R)
     eng = Engine.get(dev)
     keep, cnt = eng.nms(cand_boxes, cand_scores, cand_cls, [0, R * K], score_thresh, nms_thresh,
-                        topk_per_image)
+                        topk_per_image, num_classes=K)
     k = int(cnt[0].item())
     keep = keep[:k]
     res = Instances(tuple(image_shape))
