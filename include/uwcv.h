@@ -107,6 +107,19 @@ int uwcv_paste_measure_stages(const float* masks, const float* boxes, const int3
                               void* stream, int stages);
 
 /*
+ * uwcv_paste_measure_range -- as uwcv_paste_measure_stages, restricted to the instances
+ * [first, first + count) of the N-instance call (stage 1, the layout, always covers all N).
+ * Lets a caller start pasting the first images of a batch while the mask probabilities of
+ * the later ones are still in flight from the host, and trace all of them in one launch.
+ */
+int uwcv_paste_measure_range(const float* masks, const float* boxes, const int32_t* image_idx,
+                             const int32_t* inst_idx, const int64_t* classes, const float* scores,
+                             int64_t N, int H, int W, float thr, double pixels_per_metric,
+                             uint32_t* bitplanes, int64_t* rows_i, double* rows_f, void* workspace,
+                             size_t ws_bytes, int64_t* status, void* stream, int stages,
+                             int64_t first, int64_t count);
+
+/*
  * uwcv_unpack_planes -- expand bit-planes into the Detectron2-literal N x H x W bool
  * tensor (one byte per pixel), for callers that read pred_masks as such
  * (nn_inference.py:326, :376).

@@ -32,7 +32,7 @@ constexpr int kContourThreads = 64;
 static_assert(F_CHORDS - F_CAREA == 15, "describe_contour writes 16 contiguous float columns");
 
 __global__ void __launch_bounds__(kContourThreads)
-contour_measure_kernel(int64_t n, int lanes, const float* __restrict__ scores,
+contour_measure_kernel(int64_t first, int64_t n, int lanes, const float* __restrict__ scores,
                        double pixels_per_metric, int64_t* __restrict__ rows_i,
                        double* __restrict__ rows_f, Workspace ws,
                        const int64_t* __restrict__ status) {
@@ -41,7 +41,7 @@ contour_measure_kernel(int64_t n, int lanes, const float* __restrict__ scores,
   // chain, not by issue slots, so small batches are spread over more warps
   const int lane = threadIdx.x & 31;
   const int64_t warp = ((int64_t)blockIdx.x * kContourThreads + threadIdx.x) >> 5;
-  const int64_t inst = warp * lanes + lane;
+  const int64_t inst = first + warp * lanes + lane;
   const bool live = lane < lanes && inst < n;
   const double kPi = 3.141592653589793;
   TileDesc d;
@@ -189,10 +189,11 @@ contour_measure_kernel(int64_t n, int lanes, const float* __restrict__ scores,
                    best_perim, pixels_per_metric, rf + F_CAREA);
 }
 
-cudaError_t launch_contour_measure(int64_t n, const float* scores, double ppm, int64_t* rows_i,
-                                   double* rows_f, const Workspace& ws, const int64_t* status,
-                                   int num_sms, cudaStream_t stream) {
-  if (n == 0) return cudaSuccess;
+cudaError_t launch_contour_measure(int64_t first, int64_t count, const float* scores, double ppm,
+                                   int64_t* rows_i, double* rows_f, const Workspace& ws,
+                                   const int64_t* status, int num_sms, cudaStream_t stream) {
+  if (count == 0) return cudaSuccess;
+  const int64_t n = count;                               // sizing below is per launched range
   int per_sm = 0;
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, contour_measure_kernel,
                                                     kContourThreads, 0) != cudaSuccess || per_sm < 1)
@@ -203,8 +204,8 @@ cudaError_t launch_contour_measure(int64_t n, const float* scores, double ppm, i
   lanes = lanes < 1 ? 1 : (lanes > 32 ? 32 : lanes);
   const int64_t warps = (n + lanes - 1) / lanes;
   const unsigned grid = (unsigned)((warps * 32 + kContourThreads - 1) / kContourThreads);
-  contour_measure_kernel<<<grid, kContourThreads, 0, stream>>>(n, lanes, scores, ppm, rows_i,
-                                                               rows_f, ws, status);
+  contour_measure_kernel<<<grid, kContourThreads, 0, stream>>>(first, first + count, lanes, scores,
+                                                               ppm, rows_i, rows_f, ws, status);
   return cudaPeekAtLastError();
 }
 

@@ -173,7 +173,7 @@ paste_measure_kernel(const float* __restrict__ masks, const float* __restrict__ 
                      const int64_t* __restrict__ classes, int64_t n, int H, int W, float thr,
                      uint32_t* __restrict__ planes, int64_t* __restrict__ rows_i,
                      Workspace ws, const int64_t* __restrict__ status, int zero_bytes,
-                     int rot_mul, int fill_mode, int debug_skip) {
+                     int rot_mul, int fill_mode, int debug_skip, int64_t first) {
   extern __shared__ __align__(128) unsigned char s_zero[];     // zero_bytes (planes only)
   __shared__ __align__(16) float s_mask[kMaskPitch * kMaskPitch];
   __shared__ unsigned long long s_acc[10];
@@ -202,7 +202,7 @@ paste_measure_kernel(const float* __restrict__ masks, const float* __restrict__ 
   // other seven warps paste, pack and reduce.
   if (warp == kPasteWarps) {
     if (kPlanes && lane == 0 && fill_mode == 0) {
-      for (int64_t inst = blockIdx.x; inst < n; inst += gridDim.x) {
+      for (int64_t inst = first + blockIdx.x; inst < n; inst += gridDim.x) {
         const TileDesc d = ws.desc[inst];
         char* base = reinterpret_cast<char*>(planes + inst * plane_words);
         const int band_lo = d.th > 0 ? d.y0 : H;            // empty tile: whole plane is zero
@@ -228,7 +228,7 @@ paste_measure_kernel(const float* __restrict__ masks, const float* __restrict__ 
     return;
   }
 
-  for (int64_t inst = blockIdx.x; inst < n; inst += gridDim.x) {
+  for (int64_t inst = first + blockIdx.x; inst < n; inst += gridDim.x) {
     const TileDesc d = ws.desc[inst];
     const float bx0 = boxes[4 * inst + 0], by0 = boxes[4 * inst + 1];
     const float bx1 = boxes[4 * inst + 2], by1 = boxes[4 * inst + 3];
@@ -387,12 +387,14 @@ cudaError_t launch_layout(const float* boxes, int64_t n, int H, int W, const Wor
   return cudaPeekAtLastError();
 }
 
+// instances [first, first + count) of the call (kernel argument n = first + count: the end)
 cudaError_t launch_paste_measure(const float* masks, const float* boxes, const int32_t* image_idx,
-                                 const int32_t* inst_idx, const int64_t* classes, int64_t n, int H,
-                                 int W, float thr, uint32_t* planes, int64_t* rows_i,
-                                 const Workspace& ws, const int64_t* status, int num_sms,
-                                 cudaStream_t stream) {
-  if (n == 0) return cudaSuccess;
+                                 const int32_t* inst_idx, const int64_t* classes, int64_t first,
+                                 int64_t count, int H, int W, float thr, uint32_t* planes,
+                                 int64_t* rows_i, const Workspace& ws, const int64_t* status,
+                                 int num_sms, cudaStream_t stream) {
+  if (count == 0) return cudaSuccess;
+  const int64_t n = first + count;
   int per_sm = 0;
   cudaError_t e;
   // tuning knobs (defaults chosen on B200, see profiles/): zero-source size and rotation
@@ -415,16 +417,21 @@ cudaError_t launch_paste_measure(const float* masks, const float* boxes, const i
   }
   if (e != cudaSuccess) return e;
   if (per_sm < 1) per_sm = 1;
+  // UWCV_PASTE_CTAS (profiling) caps the CTAs per SM: 1 -> 4 780, 2 -> 5 590, 3 -> 5 640 GB/s
+  if (const char* v = getenv("UWCV_PASTE_CTAS")) {
+    const int cap = atoi(v);
+    if (cap >= 1 && cap < per_sm) per_sm = cap;
+  }
   int64_t grid = (int64_t)num_sms * per_sm;           // persistent: a whole number of waves
-  if (grid > n) grid = n;
+  if (grid > count) grid = count;
   if (planes)
     paste_measure_kernel<true><<<(unsigned)grid, kPasteThreads, dyn, stream>>>(
         masks, boxes, image_idx, inst_idx, classes, n, H, W, thr, planes, rows_i, ws, status,
-        zero_bytes, rot_mul, fill_mode, debug_skip);
+        zero_bytes, rot_mul, fill_mode, debug_skip, first);
   else
     paste_measure_kernel<false><<<(unsigned)grid, kPasteThreads, dyn, stream>>>(
         masks, boxes, image_idx, inst_idx, classes, n, H, W, thr, planes, rows_i, ws, status,
-        zero_bytes, rot_mul, fill_mode, debug_skip);
+        zero_bytes, rot_mul, fill_mode, debug_skip, first);
   return cudaPeekAtLastError();
 }
 

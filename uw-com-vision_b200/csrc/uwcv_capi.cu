@@ -5,9 +5,9 @@
 namespace uwcv {
 cudaError_t launch_layout(const float*, int64_t, int, int, const Workspace&, int64_t*, cudaStream_t);
 cudaError_t launch_paste_measure(const float*, const float*, const int32_t*, const int32_t*,
-                                 const int64_t*, int64_t, int, int, float, uint32_t*, int64_t*,
-                                 const Workspace&, const int64_t*, int, cudaStream_t);
-cudaError_t launch_contour_measure(int64_t, const float*, double, int64_t*, double*,
+                                 const int64_t*, int64_t, int64_t, int, int, float, uint32_t*,
+                                 int64_t*, const Workspace&, const int64_t*, int, cudaStream_t);
+cudaError_t launch_contour_measure(int64_t, int64_t, const float*, double, int64_t*, double*,
                                    const Workspace&, const int64_t*, int, cudaStream_t);
 cudaError_t launch_unpack(const uint32_t*, int64_t, int, int, uint8_t*, int, cudaStream_t);
 size_t nms_workspace_bytes_host(const int64_t*, int, int);
@@ -61,9 +61,9 @@ int uwcv_paste_measure(const float* masks, const float* boxes, const int32_t* im
                        int64_t N, int H, int W, float thr, double pixels_per_metric,
                        uint32_t* bitplanes, int64_t* rows_i, double* rows_f, void* workspace,
                        size_t ws_bytes, int64_t* status, void* stream) {
-  return uwcv_paste_measure_stages(masks, boxes, image_idx, inst_idx, classes, scores, N, H, W,
-                                   thr, pixels_per_metric, bitplanes, rows_i, rows_f, workspace,
-                                   ws_bytes, status, stream, 7);
+  return uwcv_paste_measure_range(masks, boxes, image_idx, inst_idx, classes, scores, N, H, W,
+                                  thr, pixels_per_metric, bitplanes, rows_i, rows_f, workspace,
+                                  ws_bytes, status, stream, 7, 0, N);
 }
 
 int uwcv_paste_measure_stages(const float* masks, const float* boxes, const int32_t* image_idx,
@@ -72,10 +72,22 @@ int uwcv_paste_measure_stages(const float* masks, const float* boxes, const int3
                               double pixels_per_metric, uint32_t* bitplanes, int64_t* rows_i,
                               double* rows_f, void* workspace, size_t ws_bytes, int64_t* status,
                               void* stream, int stages) {
+  return uwcv_paste_measure_range(masks, boxes, image_idx, inst_idx, classes, scores, N, H, W,
+                                  thr, pixels_per_metric, bitplanes, rows_i, rows_f, workspace,
+                                  ws_bytes, status, stream, stages, 0, N);
+}
+
+int uwcv_paste_measure_range(const float* masks, const float* boxes, const int32_t* image_idx,
+                             const int32_t* inst_idx, const int64_t* classes, const float* scores,
+                             int64_t N, int H, int W, float thr, double pixels_per_metric,
+                             uint32_t* bitplanes, int64_t* rows_i, double* rows_f, void* workspace,
+                             size_t ws_bytes, int64_t* status, void* stream, int stages,
+                             int64_t first, int64_t count) {
   if (N < 0 || H <= 0 || W <= 0) return UWCV_E_SHAPE;
   if (H > 32768 || W > 32768) return UWCV_E_TOO_LARGE;
   if (!(thr > 0.f)) return UWCV_E_THRESH;
   if (!(pixels_per_metric > 0.0)) return UWCV_E_SHAPE;
+  if (first < 0 || count < 0 || first + count > N) return UWCV_E_SHAPE;
   if (!status) return UWCV_E_NULL;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (N == 0) {
@@ -91,11 +103,11 @@ int uwcv_paste_measure_stages(const float* masks, const float* boxes, const int3
   if ((stages & 1) && uwcv::launch_layout(boxes, N, H, W, ws, status, st) != cudaSuccess)
     return UWCV_E_LAUNCH;
   if ((stages & 2) &&
-      uwcv::launch_paste_measure(masks, boxes, image_idx, inst_idx, classes, N, H, W, thr,
-                                 bitplanes, rows_i, ws, status, num_sms(), st) != cudaSuccess)
+      uwcv::launch_paste_measure(masks, boxes, image_idx, inst_idx, classes, first, count, H, W,
+                                 thr, bitplanes, rows_i, ws, status, num_sms(), st) != cudaSuccess)
     return UWCV_E_LAUNCH;
-  if ((stages & 4) && uwcv::launch_contour_measure(N, scores, pixels_per_metric, rows_i, rows_f,
-                                                   ws, status, num_sms(), st) != cudaSuccess)
+  if ((stages & 4) && uwcv::launch_contour_measure(first, count, scores, pixels_per_metric, rows_i,
+                                                   rows_f, ws, status, num_sms(), st) != cudaSuccess)
     return UWCV_E_LAUNCH;
   return UWCV_OK;
 }

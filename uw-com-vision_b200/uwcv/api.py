@@ -201,15 +201,22 @@ class Engine:
             self._pin_s = torch.empty((nchunks, 4), dtype=torch.int64).pin_memory()
         return self._pin_i[:n], self._pin_f[:n], self._pin_s[:nchunks]
 
-    def _workspace(self, n: int, words: int) -> torch.Tensor:
+    def _workspace(self, n: int, words: int, slot: int = 0) -> torch.Tensor:
+        """Workspace `slot` (0: default; 1: a second buffer of the same capacity for callers
+        that keep two calls in flight)."""
         if self._ws is None or n > self._cap_n or words > self._cap_words:
             cap_n = max(n, self._cap_n)
             cap_w = max(int(words * 1.25) + 1024, self._cap_words)
             nbytes = self.L.uwcv_workspace_bytes(cap_n, cap_w)
             self._ws = None
+            self._ws2 = None
             self._ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
             self._cap_n, self._cap_words = cap_n, cap_w
-        return self._ws
+        if slot == 0:
+            return self._ws
+        if getattr(self, "_ws2", None) is None or self._ws2.numel() != self._ws.numel():
+            self._ws2 = torch.empty(self._ws.numel(), dtype=torch.uint8, device=self.device)
+        return self._ws2
 
     def run(self, masks: torch.Tensor, boxes: torch.Tensor, H: int, W: int, *,
             image_idx: Optional[torch.Tensor] = None, inst_idx: Optional[torch.Tensor] = None,
@@ -217,7 +224,8 @@ class Engine:
             threshold: float = 0.5, pixels_per_metric: float = 0.85,
             planes: Optional[torch.Tensor] = None, n_tile_words: Optional[int] = None,
             rows_i: Optional[torch.Tensor] = None, rows_f: Optional[torch.Tensor] = None,
-            stages: int = 7, status: Optional[torch.Tensor] = None):
+            stages: int = 7, status: Optional[torch.Tensor] = None, ws_slot: int = 0,
+            first: int = 0, count: Optional[int] = None):
         """All tensors on ``self.device``, contiguous: masks [N,28,28] f32, boxes [N,4] f32
         (output space), image_idx/inst_idx int32, classes int64, scores f32,
         planes None or uint32/int32 [N, H, plane_row_words(W)].
@@ -230,14 +238,15 @@ class Engine:
             rows_f = torch.empty((n, NUM_FLOAT), dtype=torch.float64, device=dev)
         if n_tile_words is None:
             n_tile_words = tile_words(boxes, H, W)
-        ws = self._workspace(n, n_tile_words)
+        ws = self._workspace(n, n_tile_words, ws_slot)
         status = self.status if status is None else status
         with torch.cuda.device(dev):
-            rc = self.L.uwcv_paste_measure_stages(
+            rc = self.L.uwcv_paste_measure_range(
                 _ptr(masks), _ptr(boxes), _ptr(image_idx), _ptr(inst_idx), _ptr(classes),
                 _ptr(scores), n, int(H), int(W), float(threshold), float(pixels_per_metric),
                 _ptr(planes), _ptr(rows_i), _ptr(rows_f), _ptr(ws), ws.numel(),
-                _ptr(status), _stream_ptr(dev), int(stages))
+                _ptr(status), _stream_ptr(dev), int(stages), int(first),
+                int(n - first if count is None else count))
         _lib.check(rc, "uwcv_paste_measure")
         if n > 0:        # layout = 2 kernels, paste = 1, contour = 1
             self.launches += 2 * (stages & 1) + ((stages >> 1) & 1) + ((stages >> 2) & 1)
@@ -543,6 +552,8 @@ def measure_instances(instances: Union[object, Sequence[object]],
             d_classes = torch.cat(cl).contiguous().to(dev, **nb)
             d_img = torch.cat(il).to(dev, **nb)
             d_inst = torch.cat(jl).to(dev, **nb)
+            ev_small = torch.cuda.Event()
+            ev_small.record(eng.h2d_stream)
             for c, (i0, i1, lo, hi) in enumerate(bounds):
                 for i in range(i0, i1):             # pinned sources stay pinned: async copies
                     d_masks[starts[i]:starts[i + 1]].copy_(ml[i], non_blocking=True)
@@ -551,24 +562,31 @@ def measure_instances(instances: Union[object, Sequence[object]],
             words_c = [int(words_each[lo:hi].sum().item()) for (_, _, lo, hi) in bounds]
         else:
             words_c = [eng._cap_words] * len(bounds)
-        eng._workspace(max(hi - lo for (_, _, lo, hi) in bounds), max(words_c))
+        eng._workspace(n, sum(words_c) if words_each is not None else eng._cap_words)
         gathered = gather and dist_is_multi()
-        hp_i, hp_f, hp_s = eng.pinned_rows(n, nchunks)
+        hp_i, hp_f, hp_s = eng.pinned_rows(n, 1)
+        status = status[:1]
+        common = dict(image_idx=d_img, inst_idx=d_inst, classes=d_classes, scores=d_scores,
+                      threshold=mask_threshold, pixels_per_metric=pixels_per_metric,
+                      planes=planes, n_tile_words=sum(words_c) if words_each is not None
+                      else eng._cap_words, rows_i=rows_i, rows_f=rows_f, status=status[0])
+        # layout for the whole call as soon as the boxes are on the device; paste chunk by chunk
+        # as the mask probabilities arrive; one border-trace launch over all instances (its
+        # duration is set by the longest serial chain, not by the instance count)
+        main.wait_event(ev_small)
+        eng.run(d_masks, d_boxes, H, W, stages=1, **common)
         for c, (i0, i1, lo, hi) in enumerate(bounds):
             main.wait_event(ev_in[c])
-            eng.run(d_masks[lo:hi], d_boxes[lo:hi], H, W, image_idx=d_img[lo:hi],
-                    inst_idx=d_inst[lo:hi], classes=d_classes[lo:hi], scores=d_scores[lo:hi],
-                    threshold=mask_threshold, pixels_per_metric=pixels_per_metric,
-                    planes=None if planes is None else planes[lo:hi], n_tile_words=words_c[c],
-                    rows_i=rows_i[lo:hi], rows_f=rows_f[lo:hi], status=status[c])
-            if not gathered:
-                ev = torch.cuda.Event()
-                ev.record(main)
-                with torch.cuda.stream(eng.d2h_stream):
-                    eng.d2h_stream.wait_event(ev)
-                    hp_i[lo:hi].copy_(rows_i[lo:hi], non_blocking=True)
-                    hp_f[lo:hi].copy_(rows_f[lo:hi], non_blocking=True)
-                    hp_s[c].copy_(status[c], non_blocking=True)
+            eng.run(d_masks, d_boxes, H, W, stages=2, first=lo, count=hi - lo, **common)
+        eng.run(d_masks, d_boxes, H, W, stages=4, **common)
+        if not gathered:
+            ev = torch.cuda.Event()
+            ev.record(main)
+            with torch.cuda.stream(eng.d2h_stream):
+                eng.d2h_stream.wait_event(ev)
+                hp_i.copy_(rows_i, non_blocking=True)
+                hp_f.copy_(rows_f, non_blocking=True)
+                hp_s[0].copy_(status[0], non_blocking=True)
         if gathered:
             from .dist import all_gather_table
             g_i, g_f = all_gather_table(rows_i, rows_f)
@@ -578,7 +596,7 @@ def measure_instances(instances: Union[object, Sequence[object]],
             main.wait_stream(eng.d2h_stream)
             hi_, hf_, st = hp_i.clone(), hp_f.clone(), hp_s.clone()
         main.synchronize()                              # buffers of the side streams are done
-    for c in range(nchunks):
+    for c in range(1):
         if int(st[c, 0]) != 0:
             if int(st[c, 0]) == _lib.E_CAPACITY and not _exact_words:
                 return measure_instances(
@@ -587,7 +605,7 @@ def measure_instances(instances: Union[object, Sequence[object]],
                     return_planes=return_planes, write_planes=write_planes, gather=gather,
                     pipeline_chunks=pipeline_chunks, device=device, _exact_words=True)
             raise _lib.UwcvError(int(st[c, 0]),
-                                 f"uwcv_paste_measure (chunk {c} needs {int(st[c, 1])} tile words)")
+                                 f"uwcv_paste_measure (needs {int(st[c, 1])} tile words)")
     table = MeasurementTable(hi_.numpy(), hf_.numpy())
     return (table, planes) if return_planes else table
 
