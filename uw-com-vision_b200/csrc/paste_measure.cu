@@ -246,6 +246,14 @@ paste_measure_kernel(const float* __restrict__ masks, const float* __restrict__ 
       for (int64_t o = lo1 + tid; o < hi1; o += kComputeThreads) __stcs(base + o, z);
     }
 
+    // ---- zero the band rows: whole rows as 16-byte stores (complete sectors); the tile words
+    //      are stored over them after the barrier below
+    if (kPlanes && d.th > 0 && !(debug_skip & 2)) {
+      uint4* band = reinterpret_cast<uint4*>(plane + (int64_t)d.y0 * wpr);
+      const int total = d.th * (wpr / 4);
+      for (int k = tid; k < total; k += kComputeThreads) band[k] = make_uint4(0, 0, 0, 0);
+    }
+
     // ---- stage the 28x28 probabilities into the zero-framed copy --------------------
     const float* msrc = masks + inst * (kMaskSide * kMaskSide);
     for (int k = tid; k < kMaskSide * kMaskSide; k += kComputeThreads) {
@@ -256,24 +264,11 @@ paste_measure_kernel(const float* __restrict__ masks, const float* __restrict__ 
     if (tid == 0) { s_bbox[0] = INT_MAX; s_bbox[1] = INT_MAX; s_bbox[2] = -1; s_bbox[3] = -1; }
     compute_barrier();
 
-    // ---- zero the non-tile words of the band rows (ordinary stores) ----------------
-    if (kPlanes && d.th > 0 && !(debug_skip & 2)) {
-      const int outside = wpr - d.tw;
-      const int total = outside * d.th;
-      for (int k = tid; k < total; k += kComputeThreads) {
-        int r = k / outside, c = k - r * outside;
-        if (c >= d.wx0) c += d.tw;
-        plane[(int64_t)(d.y0 + r) * wpr + c] = 0u;
-      }
-    }
-
     // ---- the tile: each warp takes groups of 32 rows --------------------------------
     long long m00 = 0, m10 = 0, m01 = 0, m20 = 0, m11 = 0, m02 = 0, m30 = 0, m21 = 0, m12 = 0,
               m03 = 0;
     int xmin = INT_MAX, xmax = -1, ymin = INT_MAX, ymax = -1;
     uint32_t* tM = ws.M + d.word_off;
-    uint32_t* tV = ws.V + d.word_off;
-    uint32_t* tG = ws.G + d.word_off;
 
     for (int g = warp; g * 32 < d.th && !(debug_skip & 1); g += kPasteWarps) {
       const int rbase = g * 32;
@@ -310,7 +305,7 @@ paste_measure_kernel(const float* __restrict__ masks, const float* __restrict__ 
         // lane r holds the word of row rbase + r
         if (lane < nrows) {
           const int64_t o = (int64_t)(rbase + lane) * d.tw + strip;
-          tM[o] = myword; tV[o] = 0u; tG[o] = 0u;
+          tM[o] = myword;
           if (kPlanes) plane[(int64_t)(d.y0 + rbase + lane) * wpr + d.wx0 + strip] = myword;
           if (myword) { ymin = min(ymin, d.y0 + rbase + lane); ymax = max(ymax, d.y0 + rbase + lane); }
         }
@@ -375,15 +370,32 @@ paste_measure_kernel(const float* __restrict__ masks, const float* __restrict__ 
   }
 }
 
+// pass C: the visited / sign planes of the border trace start at zero (only the words the
+// layout handed out: status[1], known on the device)
+__global__ void __launch_bounds__(256)
+zero_marks_kernel(uint32_t* __restrict__ V, uint32_t* __restrict__ G,
+                  const int64_t* __restrict__ status) {
+  if (status[0] != 0) return;
+  const int64_t n16 = (status[1] + 3) / 4;
+  uint4* v = reinterpret_cast<uint4*>(V);
+  uint4* g = reinterpret_cast<uint4*>(G);
+  const uint4 z = make_uint4(0, 0, 0, 0);
+  for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n16;
+       k += (int64_t)gridDim.x * blockDim.x) {
+    v[k] = z; g[k] = z;
+  }
+}
+
 // ---------------------------------------------------------------------------------
 // host-side launchers (called from the C ABI)
 // ---------------------------------------------------------------------------------
 cudaError_t launch_layout(const float* boxes, int64_t n, int H, int W, const Workspace& ws,
-                          int64_t* status, cudaStream_t stream) {
+                          int64_t* status, int num_sms, cudaStream_t stream) {
   const int nblk = (int)layout_blocks(n);
   layout_local_kernel<<<nblk, kLayoutThreads, 0, stream>>>(boxes, n, H, W, ws.desc, ws.block_sums);
   layout_rebase_kernel<<<nblk, kLayoutThreads, 0, stream>>>(n, nblk, ws.desc, ws.block_sums,
                                                             ws.cap_words, status);
+  zero_marks_kernel<<<num_sms * 4, 256, 0, stream>>>(ws.V, ws.G, status);
   return cudaPeekAtLastError();
 }
 

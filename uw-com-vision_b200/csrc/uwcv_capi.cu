@@ -3,7 +3,8 @@
 #include "uwcv_common.cuh"
 
 namespace uwcv {
-cudaError_t launch_layout(const float*, int64_t, int, int, const Workspace&, int64_t*, cudaStream_t);
+cudaError_t launch_layout(const float*, int64_t, int, int, const Workspace&, int64_t*, int,
+                          cudaStream_t);
 cudaError_t launch_paste_measure(const float*, const float*, const int32_t*, const int32_t*,
                                  const int64_t*, int64_t, int64_t, int, int, float, uint32_t*,
                                  int64_t*, const Workspace&, const int64_t*, int, cudaStream_t);
@@ -100,7 +101,7 @@ int uwcv_paste_measure_range(const float* masks, const float* boxes, const int32
     return UWCV_E_ALIGN;
   if (ws_bytes < uwcv::workspace_bytes(N, 4)) return UWCV_E_WORKSPACE;
   const uwcv::Workspace ws = uwcv::carve(workspace, ws_bytes, N);
-  if ((stages & 1) && uwcv::launch_layout(boxes, N, H, W, ws, status, st) != cudaSuccess)
+  if ((stages & 1) && uwcv::launch_layout(boxes, N, H, W, ws, status, num_sms(), st) != cudaSuccess)
     return UWCV_E_LAUNCH;
   if ((stages & 2) &&
       uwcv::launch_paste_measure(masks, boxes, image_idx, inst_idx, classes, first, count, H, W,

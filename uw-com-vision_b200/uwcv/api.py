@@ -248,8 +248,8 @@ class Engine:
                 _ptr(status), _stream_ptr(dev), int(stages), int(first),
                 int(n - first if count is None else count))
         _lib.check(rc, "uwcv_paste_measure")
-        if n > 0:        # layout = 2 kernels, paste = 1, contour = 1
-            self.launches += 2 * (stages & 1) + ((stages >> 1) & 1) + ((stages >> 2) & 1)
+        if n > 0:        # layout = 3 kernels, paste = 1, contour = 1
+            self.launches += 3 * (stages & 1) + ((stages >> 1) & 1) + ((stages >> 2) & 1)
         return rows_i, rows_f, status
 
     def check_status(self) -> None:
