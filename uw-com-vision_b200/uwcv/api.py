@@ -187,10 +187,23 @@ class Engine:
         self.status = torch.zeros(4, dtype=torch.int64, device=device)
         self.launches = 0            # kernels enqueued by this engine (for bench accounting)
         self.h2d_stream = torch.cuda.Stream(device)
+        self.small_stream = torch.cuda.Stream(device)
         self.d2h_stream = torch.cuda.Stream(device)
+        self._dev_bufs = {}
         self._pin_i: Optional[torch.Tensor] = None
         self._pin_f: Optional[torch.Tensor] = None
         self._pin_s: Optional[torch.Tensor] = None
+
+    def device_buffer(self, name: str, shape, dtype) -> torch.Tensor:
+        """Engine-owned device scratch, reused across (synchronous) calls."""
+        need = 1
+        for v in shape:
+            need *= int(v)
+        buf = self._dev_bufs.get(name)
+        if buf is None or buf.dtype != dtype or buf.numel() < need:
+            self._dev_bufs[name] = None
+            buf = self._dev_bufs[name] = torch.empty(max(need, 1), dtype=dtype, device=self.device)
+        return buf[:need].view(*shape)
 
     def pinned_rows(self, n: int, nchunks: int):
         """Cached pinned host buffers for the device->host read of the row tables."""
@@ -467,16 +480,21 @@ def measure_instances(instances: Union[object, Sequence[object]],
         raise ValueError("all images of one call must share the output size")
     if len(sizes) == 1 and classes_of_interest is None and len(batch) > 1 and \
             all(not _as_box_tensor(i.pred_boxes).is_cuda for i in batch):
-        # fast host path: one scale / clip / non-empty over the concatenated boxes
+        # fast host path: one scale / clip / non-empty over the concatenated boxes; the mask
+        # probabilities start moving to the device first (optimistically: no box is dropped)
         lens = [len(i) for i in batch]
+        ml0 = [(i.pred_masks[:, 0] if i.pred_masks.dim() == 4 else i.pred_masks)
+               .to(torch.float32).reshape(-1, MASK_SIDE, MASK_SIDE) for i in batch]
+        import os
+        early = None if os.environ.get("UWCV_NO_EARLY") else \
+            _issue_mask_copies(eng, dev, ml0, lens, pipeline_chunks)
         allb = torch.cat([_as_box_tensor(i.pred_boxes) for i in batch])
         b_all, keep_all = scale_clip_boxes(allb, batch[0].image_size, (H, W))
         if bool(keep_all.all()):
             bl = [b_all]
             sl = [i.scores.to(torch.float32) for i in batch]
             cl = [i.pred_classes.to(torch.int64) for i in batch]
-            ml = [(i.pred_masks[:, 0] if i.pred_masks.dim() == 4 else i.pred_masks)
-                  .to(torch.float32).reshape(-1, MASK_SIDE, MASK_SIDE) for i in batch]
+            ml = ml0
             lt = torch.tensor(lens, dtype=torch.int64)
             il = [torch.repeat_interleave(
                 torch.arange(len(batch), dtype=torch.int32) + image_idx_offset, lt)]
@@ -486,8 +504,10 @@ def measure_instances(instances: Union[object, Sequence[object]],
             counts_fast = lens
         else:
             counts_fast = None
+            early = None
     else:
         counts_fast = None
+        early = None
     for k, inst in enumerate(batch if counts_fast is None else []):
         boxes, scores, classes, masks = _gather_fields(inst, classes_of_interest)
         out_sz = (H, W)
@@ -512,52 +532,35 @@ def measure_instances(instances: Union[object, Sequence[object]],
     # word reports an overflow, in which case the call is repeated with the exact size.
     need_exact = _exact_words or eng._ws is None or gather
     words_each = tile_words_each(boxes, H, W) if need_exact else None
-    # ---- chunk the batch by image: H2D of chunk c+1 overlaps the kernels of chunk c, and
-    #      the D2H of chunk c's rows overlaps the kernels of chunk c+1 (three streams)
+    # ---- chunk the batch by image: the paste of chunk c starts as soon as its mask
+    #      probabilities have landed, while the later chunks are still in flight
     counts = counts_fast if counts_fast is not None else [int(b.shape[0]) for b in bl]
-    nchunks = max(1, min(int(pipeline_chunks), len(batch)))
-    per = (len(batch) + nchunks - 1) // nchunks
-    bounds = []                                   # (first image, last image + 1, lo row, hi row)
-    lo = 0
-    for c in range(nchunks):
-        i0, i1 = c * per, min(len(batch), (c + 1) * per)
-        if i0 >= i1:
-            break
-        hi = lo + sum(counts[i0:i1])
-        bounds.append((i0, i1, lo, hi))
-        lo = hi
-    nchunks = len(bounds)
-    starts = [0]
-    for k in counts:
-        starts.append(starts[-1] + k)
     main = torch.cuda.current_stream(dev)
     nb = dict(non_blocking=True)
     with torch.cuda.device(dev):
-        d_masks = torch.empty((n, MASK_SIDE, MASK_SIDE), dtype=torch.float32, device=dev)
-        rows_i = torch.empty((n, NUM_INT), dtype=torch.int64, device=dev)
-        rows_f = torch.empty((n, NUM_FLOAT), dtype=torch.float64, device=dev)
-        status = torch.zeros((nchunks, 4), dtype=torch.int64, device=dev)
+        if early is None:
+            early = _issue_mask_copies(eng, dev, ml, counts, pipeline_chunks)
+        d_masks, ev_in, bounds = early
+        nchunks = len(bounds)
+        rows_i = eng.device_buffer("rows_i", (n, NUM_INT), torch.int64)
+        rows_f = eng.device_buffer("rows_f", (n, NUM_FLOAT), torch.float64)
+        status = torch.zeros((max(nchunks, 1), 4), dtype=torch.int64, device=dev)
         if return_planes:
             planes = eng.alloc_planes(n, H, W)            # handed to the caller
         elif write_planes:
             planes = eng.scratch_planes(n, H, W)          # engine-owned, reused across calls
         else:
             planes = None
-        eng.h2d_stream.wait_stream(main)
         eng.d2h_stream.wait_stream(main)
-        ev_in = [torch.cuda.Event() for _ in bounds]
-        with torch.cuda.stream(eng.h2d_stream):
+        with torch.cuda.stream(eng.small_stream):
+            eng.small_stream.wait_stream(main)
             d_boxes = boxes.contiguous().to(dev, **nb)
             d_scores = torch.cat(sl).contiguous().to(dev, **nb)
             d_classes = torch.cat(cl).contiguous().to(dev, **nb)
             d_img = torch.cat(il).to(dev, **nb)
             d_inst = torch.cat(jl).to(dev, **nb)
             ev_small = torch.cuda.Event()
-            ev_small.record(eng.h2d_stream)
-            for c, (i0, i1, lo, hi) in enumerate(bounds):
-                for i in range(i0, i1):             # pinned sources stay pinned: async copies
-                    d_masks[starts[i]:starts[i + 1]].copy_(ml[i], non_blocking=True)
-                ev_in[c].record(eng.h2d_stream)
+            ev_small.record(eng.small_stream)
         if words_each is not None:
             words_c = [int(words_each[lo:hi].sum().item()) for (_, _, lo, hi) in bounds]
         else:
@@ -608,6 +611,38 @@ def measure_instances(instances: Union[object, Sequence[object]],
                                  f"uwcv_paste_measure (needs {int(st[c, 1])} tile words)")
     table = MeasurementTable(hi_.numpy(), hf_.numpy())
     return (table, planes) if return_planes else table
+
+
+def _issue_mask_copies(eng: "Engine", dev, ml, counts, pipeline_chunks: int):
+    """Enqueue the host->device copies of the mask probabilities on the engine's copy stream,
+    one event per chunk of images.  Returns (device masks, events, chunk bounds)."""
+    n = int(sum(counts))
+    nchunks = max(1, min(int(pipeline_chunks), len(ml)))
+    per = (len(ml) + nchunks - 1) // nchunks
+    bounds = []                                   # (first image, last image + 1, lo row, hi row)
+    lo = 0
+    for c in range(nchunks):
+        i0, i1 = c * per, min(len(ml), (c + 1) * per)
+        if i0 >= i1:
+            break
+        hi = lo + sum(counts[i0:i1])
+        bounds.append((i0, i1, lo, hi))
+        lo = hi
+    starts = [0]
+    for k in counts:
+        starts.append(starts[-1] + k)
+    main = torch.cuda.current_stream(dev)
+    with torch.cuda.device(dev):
+        d_masks = eng.device_buffer("masks", (n, MASK_SIDE, MASK_SIDE), torch.float32)
+        ev_in = [torch.cuda.Event() for _ in bounds]
+        eng.h2d_stream.wait_stream(main)
+        with torch.cuda.stream(eng.h2d_stream):
+            for c, (i0, i1, _lo, _hi) in enumerate(bounds):
+                for i in range(i0, i1):             # pinned sources stay pinned: async copies
+                    if counts[i]:
+                        d_masks[starts[i]:starts[i + 1]].copy_(ml[i], non_blocking=True)
+                ev_in[c].record(eng.h2d_stream)
+    return d_masks, ev_in, bounds
 
 
 def dist_is_multi() -> bool:
