@@ -12,9 +12,10 @@ planes, 1 bit / pixel) / moments -> border trace + descriptors; at N > 1 ranks a
 all-gather of the measurement table follows (image-sharded, weak scaling).
 
 Printed JSON keys (driver contract): metric/value/unit (instances measured per second,
-whole job), ms_per_step, mp_per_sec, e2e (same metric through uwcv.measure_instances
-with pinned HOST inputs: H2D of the step's inputs and D2H of the rows inside the timed
-region), roofline (paste kernel, algorithmic bytes / live CUDA-event time vs measured
+whole job), ms_per_step, mp_per_sec, e2e (same metric through the public call,
+uwcv.MeasurementStream.map = measure_instances with two calls in flight, with pinned HOST
+inputs: H2D of every step's inputs and D2H of its rows inside the timed region; the
+synchronous one-call-per-step time is reported beside it), roofline (paste kernel, algorithmic bytes / live CUDA-event time vs measured
 HBM peak), cpu_baseline (the reference's CPU path on a bounded sample, N = 1 only),
 gpu_launches, clocks.
 """
@@ -336,21 +337,37 @@ def run_ours(args):
 
     # ---- e2e: the public call with pinned host inputs -----------------------------------
     h2d = sum(int(b.pred_masks.numel()) * 4 + len(b) * (16 + 4 + 8 + 4 + 4) for b in batch)
-    d2h = n * (20 * 8 + 30 * 8) + 32
+    d2h = total_instances * (20 * 8 + 30 * 8) + 32     # gathered table at N > 1
     del planes
+    kw = dict(write_planes=True, gather=world > 1, gather_counts=counts)
     for _ in range(2):
-        uwcv.measure_instances(batch, (H, W), write_planes=True, gather=world > 1, device=dev)
+        uwcv.measure_instances(batch, (H, W), device=dev, **kw)
+    # (a) one synchronous call per step (latency form)
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        table = uwcv.measure_instances(batch, (H, W), write_planes=True, gather=world > 1,
-                                       device=dev)
+        table = uwcv.measure_instances(batch, (H, W), device=dev, **kw)
+    barrier()
+    sync_s = time.perf_counter() - t0
+    # (b) the throughput form of the same call: uwcv.MeasurementStream keeps two calls in
+    #     flight, so the H2D of step i + 1 and the D2H of step i - 1 run under the kernels of
+    #     step i.  Every step still copies its inputs from pinned host memory and reads its
+    #     rows back; all K tables are materialised on the host inside the timed region.
+    stream = uwcv.MeasurementStream(dev, depth=2)
+    for table in stream.map((batch for _ in range(3)), (H, W), **kw):
+        pass
+    barrier()
+    t0 = time.perf_counter()
+    got = 0
+    for table in stream.map((batch for _ in range(args.steps)), (H, W), **kw):
+        got += len(table)
     barrier()
     e2e_s = time.perf_counter() - t0
+    assert got == args.steps * total_instances, (got, total_instances)
     if world > 1:
-        t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+        t = torch.tensor([e2e_s, sync_s], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
+        e2e_s, sync_s = float(t[0].item()), float(t[1].item())
     e2e_val = args.steps * total_instances / e2e_s
 
     # ---- CPU baseline (rank 0, N = 1 only) ------------------------------------------------
@@ -378,7 +395,10 @@ def run_ours(args):
                        "collective": "all_gather of the row table" if world > 1 else "none"},
             "mp_per_sec": args.steps * world * n_img * H * W / 1e6 / (ms * 1e-3),
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": d2h, "ms_per_step": e2e_s / args.steps * 1e3},
+                    "d2h_bytes_per_step": d2h, "ms_per_step": e2e_s / args.steps * 1e3,
+                    "call": "uwcv.MeasurementStream(depth=2).map (pinned host Instances in, "
+                            "host MeasurementTable out, every step)",
+                    "sync_call_ms_per_step": sync_s / args.steps * 1e3},
             "gpu_launches": launches,
             "kernel_ms": {"layout": k_layout, "paste_measure": k_paste, "contour": k_contour},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",

@@ -406,3 +406,39 @@ def test_union_mode_equals_reference_literal_rows():
     ref = P.reference_literal_rows(batch[0], (H, W), [0, 1, 2, 3])
     assert np.allclose(ut.reference_rows(), ref, rtol=1e-6, atol=0)
     print(f"union mode: {total} reference rows matched")
+
+
+# ---------------------------------------------------------------- stream (e2e form) ----
+def test_measurement_stream_equals_synchronous_calls():
+    """uwcv.MeasurementStream (two calls in flight, per-slot buffers) returns, in order, the
+    tables of the synchronous call -- including when the cached workspace overflows and a
+    call is transparently repeated, and for device-resident inputs."""
+    H = W = 256
+    batches = [[synth.blob_instances(4 * s + k, 20 + 7 * s + k, H, W, seed=50 + s) for k in range(3)]
+               for s in range(5)]
+    batches.append([synth.blob_instances(99, 400, H, W, seed=77) for _ in range(2)])  # overflow
+    batches.append([])                                                                # empty
+    for b in batches[:2]:                                                             # pinned inputs
+        for inst in b:
+            for k, v in list(inst.get_fields().items()):
+                inst.set(k, v.pin_memory() if isinstance(v, torch.Tensor)
+                         else uwcv.Boxes(v.tensor.pin_memory()))
+    for inst in batches[2]:                                                           # device inputs
+        for k, v in list(inst.get_fields().items()):
+            inst.set(k, v.cuda() if isinstance(v, torch.Tensor) else uwcv.Boxes(v.tensor.cuda()))
+    want = [uwcv.measure_instances(b, (H, W)) for b in batches]
+    api.Engine._engines.clear()                      # fresh engine: small cached workspace
+    for depth in (1, 2, 3):
+        stream = uwcv.MeasurementStream(depth=depth)
+        got = list(stream.map(batches, (H, W)))
+        assert len(got) == len(want)
+        for g, w in zip(got, want):
+            assert np.array_equal(g.ints, w.ints)
+            assert np.array_equal(g.floats, w.floats, equal_nan=True)
+    # handles collected out of order
+    stream = uwcv.MeasurementStream(depth=2)
+    p0 = stream.submit(batches[0], (H, W))
+    p1 = stream.submit(batches[1], (H, W))
+    p2 = stream.submit(batches[3], (H, W))           # reuses slot 0: p0 is materialised first
+    for p, w in ((p2, want[3]), (p1, want[1]), (p0, want[0])):
+        assert np.array_equal(p.result().ints, w.ints)

@@ -1,13 +1,14 @@
 """uwcv -- B200-native post-inference measurement path of uw-com-vision.
 
 Public surface (mirrors the reference-side names, see api.py):
-    measure_instances, paste_masks_in_image, detector_postprocess,
+    measure_instances, MeasurementStream, paste_masks_in_image, detector_postprocess,
     fast_rcnn_inference_single_image, get_counts, MeasurementTable, Instances, Boxes
 """
 from .structures import Boxes, Instances                      # noqa: F401
 from .schema import (INT_COLUMNS, FLOAT_COLUMNS, CSV_COLUMNS, CLASS_NAMES,   # noqa: F401
                      CLASS_KEYWORDS)
-from .api import (Engine, MeasurementTable, measure_instances, paste_masks_in_image,  # noqa: F401
+from .api import (Engine, MeasurementTable, MeasurementStream, PendingTable,
+                  submit_measure_instances, measure_instances, paste_masks_in_image,  # noqa: F401
                   detector_postprocess, fast_rcnn_inference_single_image, get_counts,
                   scale_clip_boxes, tile_words)
 from .grouping import (group_by_class, write_classes_csv, moving_average, report_class,  # noqa: F401
@@ -16,7 +17,8 @@ from .dist import shard_indices, all_gather_table             # noqa: F401
 from .union import UnionTable, measure_union                  # noqa: F401
 
 __all__ = [
-    "Boxes", "Instances", "Engine", "MeasurementTable", "measure_instances",
+    "Boxes", "Instances", "Engine", "MeasurementTable", "MeasurementStream", "PendingTable",
+    "submit_measure_instances", "measure_instances",
     "paste_masks_in_image", "detector_postprocess", "fast_rcnn_inference_single_image",
     "get_counts", "group_by_class", "write_classes_csv", "moving_average", "report_class",
     "write_results_csv", "shard_indices", "all_gather_table", "UnionTable", "measure_union",

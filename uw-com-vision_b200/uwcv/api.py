@@ -190,9 +190,13 @@ class Engine:
         self.small_stream = torch.cuda.Stream(device)
         self.d2h_stream = torch.cuda.Stream(device)
         self._dev_bufs = {}
-        self._pin_i: Optional[torch.Tensor] = None
-        self._pin_f: Optional[torch.Tensor] = None
-        self._pin_s: Optional[torch.Tensor] = None
+        self._slots = {}
+
+    def slot(self, k: int = 0) -> "_Slot":
+        s = self._slots.get(k)
+        if s is None:
+            s = self._slots[k] = _Slot(self)
+        return s
 
     def device_buffer(self, name: str, shape, dtype) -> torch.Tensor:
         """Engine-owned device scratch, reused across (synchronous) calls."""
@@ -204,15 +208,6 @@ class Engine:
             self._dev_bufs[name] = None
             buf = self._dev_bufs[name] = torch.empty(max(need, 1), dtype=dtype, device=self.device)
         return buf[:need].view(*shape)
-
-    def pinned_rows(self, n: int, nchunks: int):
-        """Cached pinned host buffers for the device->host read of the row tables."""
-        if self._pin_i is None or self._pin_i.shape[0] < n:
-            self._pin_i = torch.empty((n, NUM_INT), dtype=torch.int64).pin_memory()
-            self._pin_f = torch.empty((n, NUM_FLOAT), dtype=torch.float64).pin_memory()
-        if self._pin_s is None or self._pin_s.shape[0] < nchunks:
-            self._pin_s = torch.empty((nchunks, 4), dtype=torch.int64).pin_memory()
-        return self._pin_i[:n], self._pin_f[:n], self._pin_s[:nchunks]
 
     def _workspace(self, n: int, words: int, slot: int = 0) -> torch.Tensor:
         """Workspace `slot` (0: default; 1: a second buffer of the same capacity for callers
@@ -443,12 +438,95 @@ def _gather_fields(inst, classes_of_interest):
     return boxes, scores, classes, masks
 
 
+class _Slot:
+    """Device + pinned host buffers of one in-flight call.  A synchronous call uses slot 0;
+    a ``MeasurementStream`` rotates over ``depth`` slots so that the host->device copies of
+    call i + 1 run under the kernels of call i."""
+
+    def __init__(self, eng: "Engine"):
+        self.eng = eng
+        self.dev = {}
+        self.pin = {}
+        self.pending: Optional["PendingTable"] = None
+
+    def device(self, name: str, shape, dtype) -> torch.Tensor:
+        need = 1
+        for v in shape:
+            need *= int(v)
+        buf = self.dev.get(name)
+        if buf is None or buf.dtype != dtype or buf.numel() < need:
+            # growing a buffer other streams may still use: drain the device first (rare)
+            torch.cuda.synchronize(self.eng.device)
+            self.dev[name] = None
+            buf = self.dev[name] = torch.empty(max(int(need * 1.1), 1), dtype=dtype,
+                                               device=self.eng.device)
+        return buf[:need].view(*shape)
+
+    def pinned(self, name: str, shape, dtype) -> torch.Tensor:
+        need = 1
+        for v in shape:
+            need *= int(v)
+        buf = self.pin.get(name)
+        if buf is None or buf.dtype != dtype or buf.numel() < need:
+            torch.cuda.synchronize(self.eng.device)
+            self.pin[name] = None
+            buf = self.pin[name] = torch.empty(max(int(need * 1.1), 1), dtype=dtype).pin_memory()
+        return buf[:need].view(*shape)
+
+
+class PendingTable:
+    """Handle of an enqueued ``measure_instances`` call: ``result()`` waits for the
+    device->host copy of the rows and returns what ``measure_instances`` returns."""
+
+    def __init__(self, slot: Optional[_Slot] = None, retry=None):
+        self._slot = slot
+        self._retry = retry
+        self._done = None
+        self._value = None
+        self.n = 0
+        self.planes = None
+        self.return_planes = False
+        self.hp_i = self.hp_f = self.hp_s = None
+
+    @staticmethod
+    def ready(value) -> "PendingTable":
+        p = PendingTable()
+        p._value = (value,)
+        return p
+
+    def result(self):
+        if self._value is not None:
+            return self._value[0]
+        self._done.synchronize()
+        st = self.hp_s
+        code = int(st[0])
+        if code != 0:
+            self._release()
+            if code == _lib.E_CAPACITY and self._retry is not None:
+                value = self._retry()
+                self._value = (value,)
+                return value
+            raise _lib.UwcvError(code, f"uwcv_paste_measure (needs {int(st[1])} tile words)")
+        table = MeasurementTable(self.hp_i.numpy().copy(), self.hp_f.numpy().copy())
+        value = (table, self.planes) if self.return_planes else table
+        self._value = (value,)
+        self._release()
+        return value
+
+    def _release(self):
+        if self._slot is not None and self._slot.pending is self:
+            self._slot.pending = None
+        self._slot = None
+        self.planes = None if not self.return_planes else self.planes
+
+
 def measure_instances(instances: Union[object, Sequence[object]],
                       output_size: Optional[Tuple[int, int]] = None,
                       classes_of_interest: Optional[Sequence[int]] = None, *,
                       mask_threshold: float = 0.5, pixels_per_metric: float = 0.85,
                       image_idx_offset: int = 0, return_planes: bool = False,
                       write_planes: bool = False, gather: bool = False,
+                      gather_counts: Optional[Sequence[int]] = None,
                       pipeline_chunks: int = 4, device=None, _exact_words: bool = False):
     """Per-instance measurement rows for one image or a batch of images.
 
@@ -463,21 +541,76 @@ def measure_instances(instances: Union[object, Sequence[object]],
     ``return_planes``); an empty selection returns an empty table (the reference prints
     and returns, nn_inference.py:383-385).  ``gather=True`` (under torch.distributed, one
     process per GPU, images sharded over ranks) all-gathers the device rows of every rank
-    before the host read, so each rank returns the whole job's table.
+    before the host read, so each rank returns the whole job's table; ``gather_counts``
+    (rows per rank, when the caller knows them) skips the count exchange.
     """
+    return submit_measure_instances(
+        instances, output_size, classes_of_interest, mask_threshold=mask_threshold,
+        pixels_per_metric=pixels_per_metric, image_idx_offset=image_idx_offset,
+        return_planes=return_planes, write_planes=write_planes, gather=gather,
+        gather_counts=gather_counts, pipeline_chunks=pipeline_chunks, device=device,
+        _exact_words=_exact_words).result()
+
+
+class MeasurementStream:
+    """Throughput form of ``measure_instances`` for a sequence of batches (the reference
+    loops over the images of a folder, nn_inference.py:485-498): up to ``depth`` calls are
+    in flight, so the host->device copy of batch i + 1 and the device->host read of batch
+    i - 1 run under the kernels of batch i.
+
+        stream = uwcv.MeasurementStream(device, depth=2)
+        for table in stream.map(batches, (H, W)): ...
+
+    ``submit`` returns a ``PendingTable``; tables come back in submission order."""
+
+    def __init__(self, device=None, depth: int = 2):
+        self.device = _require_cuda(device)
+        self.depth = max(1, int(depth))
+        self._next = 0
+
+    def submit(self, instances, output_size=None, classes_of_interest=None, **kw) -> PendingTable:
+        slot = self._next
+        self._next = (self._next + 1) % self.depth
+        return submit_measure_instances(instances, output_size, classes_of_interest,
+                                        device=self.device, _slot=slot, **kw)
+
+    def map(self, batches, output_size=None, classes_of_interest=None, **kw):
+        inflight: List[PendingTable] = []
+        for b in batches:
+            inflight.append(self.submit(b, output_size, classes_of_interest, **kw))
+            if len(inflight) >= self.depth:
+                yield inflight.pop(0).result()
+        while inflight:
+            yield inflight.pop(0).result()
+
+
+def submit_measure_instances(instances, output_size=None, classes_of_interest=None, *,
+                             mask_threshold: float = 0.5, pixels_per_metric: float = 0.85,
+                             image_idx_offset: int = 0, return_planes: bool = False,
+                             write_planes: bool = False, gather: bool = False,
+                             gather_counts: Optional[Sequence[int]] = None,
+                             pipeline_chunks: int = 4, device=None, _exact_words: bool = False,
+                             _slot: int = 0) -> PendingTable:
+    """Enqueue one ``measure_instances`` call (same arguments) and return its handle."""
     single = not isinstance(instances, (list, tuple))
     batch: List[object] = [instances] if single else list(instances)
     dev = _require_cuda(device)
     eng = Engine.get(dev)
+    empty = (MeasurementTable.empty(), None) if return_planes else MeasurementTable.empty()
     if not batch:
-        return MeasurementTable.empty()
+        return PendingTable.ready(MeasurementTable.empty())
     H, W = (int(output_size[0]), int(output_size[1])) if output_size is not None else \
         tuple(int(v) for v in batch[0].image_size)
+    slot = eng.slot(_slot)
+    if slot.pending is not None:            # the slot's previous call has not been collected
+        slot.pending.result()
 
     bl, sl, cl, ml, il, jl = [], [], [], [], [], []
     sizes = {tuple(int(v) for v in inst.image_size) for inst in batch}
     if output_size is None and len(sizes) > 1:
         raise ValueError("all images of one call must share the output size")
+    early = None
+    counts_fast = None
     if len(sizes) == 1 and classes_of_interest is None and len(batch) > 1 and \
             all(not _as_box_tensor(i.pred_boxes).is_cuda for i in batch):
         # fast host path: one scale / clip / non-empty over the concatenated boxes; the mask
@@ -485,9 +618,7 @@ def measure_instances(instances: Union[object, Sequence[object]],
         lens = [len(i) for i in batch]
         ml0 = [(i.pred_masks[:, 0] if i.pred_masks.dim() == 4 else i.pred_masks)
                .to(torch.float32).reshape(-1, MASK_SIDE, MASK_SIDE) for i in batch]
-        import os
-        early = None if os.environ.get("UWCV_NO_EARLY") else \
-            _issue_mask_copies(eng, dev, ml0, lens, pipeline_chunks)
+        early = _issue_mask_copies(eng, slot, dev, ml0, lens, pipeline_chunks)
         allb = torch.cat([_as_box_tensor(i.pred_boxes) for i in batch])
         b_all, keep_all = scale_clip_boxes(allb, batch[0].image_size, (H, W))
         if bool(keep_all.all()):
@@ -503,11 +634,7 @@ def measure_instances(instances: Union[object, Sequence[object]],
                    - torch.repeat_interleave(offs, lt)).to(torch.int32)]
             counts_fast = lens
         else:
-            counts_fast = None
             early = None
-    else:
-        counts_fast = None
-        early = None
     for k, inst in enumerate(batch if counts_fast is None else []):
         boxes, scores, classes, masks = _gather_fields(inst, classes_of_interest)
         out_sz = (H, W)
@@ -525,95 +652,110 @@ def measure_instances(instances: Union[object, Sequence[object]],
         jl.append(torch.arange(nk, dtype=torch.int32))
     boxes = torch.cat(bl)
     n = int(boxes.shape[0])
-    if n == 0:
-        return (MeasurementTable.empty(), None) if return_planes else MeasurementTable.empty()
+    gathered = gather and dist_is_multi()
+    if n == 0 and not gathered:
+        return PendingTable.ready(empty)
     # Workspace sizing: the exact tile-word count is only computed for the first call (or
     # after an overflow); afterwards the cached capacity is reused and the device status
     # word reports an overflow, in which case the call is repeated with the exact size.
-    need_exact = _exact_words or eng._ws is None or gather
-    words_each = tile_words_each(boxes, H, W) if need_exact else None
-    # ---- chunk the batch by image: the paste of chunk c starts as soon as its mask
-    #      probabilities have landed, while the later chunks are still in flight
+    need_exact = _exact_words or eng._ws is None
+    n_words = tile_words(boxes, H, W) if need_exact else eng._cap_words
     counts = counts_fast if counts_fast is not None else [int(b.shape[0]) for b in bl]
     main = torch.cuda.current_stream(dev)
     nb = dict(non_blocking=True)
+
+    def retry():
+        return measure_instances(
+            instances, output_size, classes_of_interest, mask_threshold=mask_threshold,
+            pixels_per_metric=pixels_per_metric, image_idx_offset=image_idx_offset,
+            return_planes=return_planes, write_planes=write_planes, gather=gather,
+            gather_counts=gather_counts, pipeline_chunks=pipeline_chunks, device=device,
+            _exact_words=True)
+
+    pend = PendingTable(slot, None if _exact_words else retry)
+    pend.return_planes = return_planes
     with torch.cuda.device(dev):
         if early is None:
-            early = _issue_mask_copies(eng, dev, ml, counts, pipeline_chunks)
+            early = _issue_mask_copies(eng, slot, dev, ml, counts, pipeline_chunks)
         d_masks, ev_in, bounds = early
-        nchunks = len(bounds)
-        rows_i = eng.device_buffer("rows_i", (n, NUM_INT), torch.int64)
-        rows_f = eng.device_buffer("rows_f", (n, NUM_FLOAT), torch.float64)
-        status = torch.zeros((max(nchunks, 1), 4), dtype=torch.int64, device=dev)
+        rows_i = slot.device("rows_i", (n, NUM_INT), torch.int64)
+        rows_f = slot.device("rows_f", (n, NUM_FLOAT), torch.float64)
+        status = slot.device("status", (4,), torch.int64)
         if return_planes:
             planes = eng.alloc_planes(n, H, W)            # handed to the caller
         elif write_planes:
             planes = eng.scratch_planes(n, H, W)          # engine-owned, reused across calls
         else:
             planes = None
-        eng.d2h_stream.wait_stream(main)
+        pend.planes = planes if return_planes else None
         with torch.cuda.stream(eng.small_stream):
             eng.small_stream.wait_stream(main)
-            d_boxes = boxes.contiguous().to(dev, **nb)
-            d_scores = torch.cat(sl).contiguous().to(dev, **nb)
-            d_classes = torch.cat(cl).contiguous().to(dev, **nb)
-            d_img = torch.cat(il).to(dev, **nb)
-            d_inst = torch.cat(jl).to(dev, **nb)
+            d_boxes = slot.device("boxes", (n, 4), torch.float32)
+            d_scores = slot.device("scores", (n,), torch.float32)
+            d_classes = slot.device("classes", (n,), torch.int64)
+            d_img = slot.device("img", (n,), torch.int32)
+            d_inst = slot.device("inst", (n,), torch.int32)
+            # staged through pinned memory so that the copies do not block the host
+            for dst, name, parts in ((d_boxes, "boxes", [boxes]), (d_scores, "scores", sl),
+                                     (d_classes, "classes", cl), (d_img, "img", il),
+                                     (d_inst, "inst", jl)):
+                if any(p_.is_cuda for p_ in parts):
+                    dst.copy_(parts[0] if len(parts) == 1 else torch.cat(parts), **nb)
+                    continue
+                hp = slot.pinned(name, dst.shape, dst.dtype)
+                torch.cat(parts, out=hp) if len(parts) > 1 else hp.copy_(parts[0])
+                dst.copy_(hp, **nb)
             ev_small = torch.cuda.Event()
             ev_small.record(eng.small_stream)
-        if words_each is not None:
-            words_c = [int(words_each[lo:hi].sum().item()) for (_, _, lo, hi) in bounds]
-        else:
-            words_c = [eng._cap_words] * len(bounds)
-        eng._workspace(n, sum(words_c) if words_each is not None else eng._cap_words)
-        gathered = gather and dist_is_multi()
-        hp_i, hp_f, hp_s = eng.pinned_rows(n, 1)
-        status = status[:1]
+        ws = eng._workspace(n, n_words)
         common = dict(image_idx=d_img, inst_idx=d_inst, classes=d_classes, scores=d_scores,
                       threshold=mask_threshold, pixels_per_metric=pixels_per_metric,
-                      planes=planes, n_tile_words=sum(words_c) if words_each is not None
-                      else eng._cap_words, rows_i=rows_i, rows_f=rows_f, status=status[0])
+                      planes=planes, n_tile_words=n_words, rows_i=rows_i, rows_f=rows_f,
+                      status=status)
         # layout for the whole call as soon as the boxes are on the device; paste chunk by chunk
         # as the mask probabilities arrive; one border-trace launch over all instances (its
         # duration is set by the longest serial chain, not by the instance count)
         main.wait_event(ev_small)
-        eng.run(d_masks, d_boxes, H, W, stages=1, **common)
-        for c, (i0, i1, lo, hi) in enumerate(bounds):
-            main.wait_event(ev_in[c])
-            eng.run(d_masks, d_boxes, H, W, stages=2, first=lo, count=hi - lo, **common)
-        eng.run(d_masks, d_boxes, H, W, stages=4, **common)
-        if not gathered:
-            ev = torch.cuda.Event()
-            ev.record(main)
-            with torch.cuda.stream(eng.d2h_stream):
-                eng.d2h_stream.wait_event(ev)
-                hp_i.copy_(rows_i, non_blocking=True)
-                hp_f.copy_(rows_f, non_blocking=True)
-                hp_s[0].copy_(status[0], non_blocking=True)
+        if n > 0:
+            eng.run(d_masks, d_boxes, H, W, stages=1, **common)
+            for c, (i0, i1, lo, hi) in enumerate(bounds):
+                main.wait_event(ev_in[c])
+                if hi > lo:
+                    eng.run(d_masks, d_boxes, H, W, stages=2, first=lo, count=hi - lo, **common)
+            eng.run(d_masks, d_boxes, H, W, stages=4, **common)
+        else:
+            status.zero_()
         if gathered:
             from .dist import all_gather_table
-            g_i, g_f = all_gather_table(rows_i, rows_f)
-            hi_, hf_, st = g_i.cpu(), g_f.cpu(), status.cpu()
+            out_i, out_f = all_gather_table(rows_i, rows_f, counts=gather_counts)
         else:
-            eng.d2h_stream.synchronize()
-            main.wait_stream(eng.d2h_stream)
-            hi_, hf_, st = hp_i.clone(), hp_f.clone(), hp_s.clone()
-        main.synchronize()                              # buffers of the side streams are done
-    for c in range(1):
-        if int(st[c, 0]) != 0:
-            if int(st[c, 0]) == _lib.E_CAPACITY and not _exact_words:
-                return measure_instances(
-                    instances, output_size, classes_of_interest, mask_threshold=mask_threshold,
-                    pixels_per_metric=pixels_per_metric, image_idx_offset=image_idx_offset,
-                    return_planes=return_planes, write_planes=write_planes, gather=gather,
-                    pipeline_chunks=pipeline_chunks, device=device, _exact_words=True)
-            raise _lib.UwcvError(int(st[c, 0]),
-                                 f"uwcv_paste_measure (needs {int(st[c, 1])} tile words)")
-    table = MeasurementTable(hi_.numpy(), hf_.numpy())
-    return (table, planes) if return_planes else table
+            out_i, out_f = rows_i, rows_f
+        r = int(out_i.shape[0])
+        hp_i = slot.pinned("rows_i", (r, NUM_INT), torch.int64)
+        hp_f = slot.pinned("rows_f", (r, NUM_FLOAT), torch.float64)
+        hp_s = slot.pinned("status", (4,), torch.int64)
+        ev = torch.cuda.Event()
+        ev.record(main)
+        with torch.cuda.stream(eng.d2h_stream):
+            eng.d2h_stream.wait_event(ev)
+            hp_i.copy_(out_i, **nb)
+            hp_f.copy_(out_f, **nb)
+            hp_s.copy_(status, **nb)
+            done = torch.cuda.Event()
+            done.record(eng.d2h_stream)
+        if gathered:                  # the gathered tensors belong to the main stream's pool
+            out_i.record_stream(eng.d2h_stream)
+            out_f.record_stream(eng.d2h_stream)
+        # rows / status / inputs are per slot and a slot is only reused after its call has
+        # been collected, so the main stream never waits for the device->host read
+    pend.n = r
+    pend.hp_i, pend.hp_f, pend.hp_s = hp_i, hp_f, hp_s
+    pend._done = done
+    slot.pending = pend
+    return pend
 
 
-def _issue_mask_copies(eng: "Engine", dev, ml, counts, pipeline_chunks: int):
+def _issue_mask_copies(eng: "Engine", slot: _Slot, dev, ml, counts, pipeline_chunks: int):
     """Enqueue the host->device copies of the mask probabilities on the engine's copy stream,
     one event per chunk of images.  Returns (device masks, events, chunk bounds)."""
     n = int(sum(counts))
@@ -633,9 +775,15 @@ def _issue_mask_copies(eng: "Engine", dev, ml, counts, pipeline_chunks: int):
         starts.append(starts[-1] + k)
     main = torch.cuda.current_stream(dev)
     with torch.cuda.device(dev):
-        d_masks = eng.device_buffer("masks", (n, MASK_SIDE, MASK_SIDE), torch.float32)
+        d_masks = slot.device("masks", (n, MASK_SIDE, MASK_SIDE), torch.float32)
         ev_in = [torch.cuda.Event() for _ in bounds]
-        eng.h2d_stream.wait_stream(main)
+        # the slot's previous call (the only other user of this buffer) was collected before
+        # this one was admitted, so the copies need not wait for the main stream
+        if any(m.is_cuda for m in ml):              # device-resident inputs: after their producer
+            eng.h2d_stream.wait_stream(main)
+            for m in ml:
+                if m.is_cuda:
+                    m.record_stream(eng.h2d_stream)
         with torch.cuda.stream(eng.h2d_stream):
             for c, (i0, i1, _lo, _hi) in enumerate(bounds):
                 for i in range(i0, i1):             # pinned sources stay pinned: async copies
