@@ -96,7 +96,7 @@ layout_local_kernel(const float* __restrict__ boxes, int64_t n, int H, int W,
 __global__ void __launch_bounds__(kLayoutThreads)
 layout_rebase_kernel(int64_t n, int nblk, TileDesc* __restrict__ desc,
                      const int64_t* __restrict__ block_sums, int64_t cap_words,
-                     int64_t* __restrict__ status) {
+                     int64_t* __restrict__ status, unsigned int* __restrict__ sched) {
   __shared__ int64_t s_words[kLayoutThreads];
   __shared__ int64_t s_rows[kLayoutThreads];
   const int t = threadIdx.x;
@@ -115,6 +115,7 @@ layout_rebase_kernel(int64_t n, int nblk, TileDesc* __restrict__ desc,
       status[1] = base_w;
       status[2] = base_r;
       status[0] = (base_w > cap_words) ? (int64_t)E_CAPACITY : 0;
+      sched[0] = sched[1] = sched[2] = sched[3] = 0u;
     }
     return;                                              // offsets of CTA 0 need no rebase
   }
@@ -178,6 +179,7 @@ paste_measure_kernel(const float* __restrict__ masks, const float* __restrict__ 
   __shared__ __align__(16) float s_mask[kMaskPitch * kMaskPitch];
   __shared__ unsigned long long s_acc[10];
   __shared__ int s_bbox[4];
+  __shared__ long long s_next[2];
 
   if (status[0] != 0) return;                       // layout overflowed the workspace
 
@@ -202,7 +204,12 @@ paste_measure_kernel(const float* __restrict__ masks, const float* __restrict__ 
   // other seven warps paste, pack and reduce.
   if (warp == kPasteWarps) {
     if (kPlanes && lane == 0 && fill_mode == 0) {
-      for (int64_t inst = first + blockIdx.x; inst < n; inst += gridDim.x) {
+      // planes are claimed one at a time from a device-wide counter: under a saturated write
+      // path the SMs do not drain at the same rate, and a static split leaves the fast ones
+      // idle at the end (tools/fill_bench2.cu: 6.3 TB/s static vs 7.6 TB/s dynamic)
+      int64_t inst = first + atomicAdd(&ws.sched[0], 1u);
+      while (inst < n) {
+        const int64_t next = first + atomicAdd(&ws.sched[0], 1u);   // in flight under the fill
         const TileDesc d = ws.desc[inst];
         char* base = reinterpret_cast<char*>(planes + inst * plane_words);
         const int band_lo = d.th > 0 ? d.y0 : H;            // empty tile: whole plane is zero
@@ -222,13 +229,21 @@ paste_measure_kernel(const float* __restrict__ masks, const float* __restrict__ 
             }
           }
         bulk_commit();
+        inst = next;
       }
       bulk_wait_read_all();                            // the zero source must outlive the copies
     }
-    return;
-  }
+  } else {
 
-  for (int64_t inst = first + blockIdx.x; inst < n; inst += gridDim.x) {
+  if (tid == 0) s_next[0] = first + atomicAdd(&ws.sched[1], 1u);
+  compute_barrier();
+  for (int it = 0;; ++it) {
+    const int64_t inst = s_next[it & 1];
+    if (inst >= n) break;
+    // the claim of the next instance travels under this one's work: the counter's reply is
+    // only consumed (stored to shared memory) before the last barrier of the iteration
+    long long claim = 0;
+    if (tid == 0) claim = first + atomicAdd(&ws.sched[1], 1u);
     const TileDesc d = ws.desc[inst];
     const float bx0 = boxes[4 * inst + 0], by0 = boxes[4 * inst + 1];
     const float bx1 = boxes[4 * inst + 2], by1 = boxes[4 * inst + 3];
@@ -366,7 +381,15 @@ paste_measure_kernel(const float* __restrict__ masks, const float* __restrict__ 
       }
       rows_i[inst * kNumInt + tid] = v;
     }
+    if (tid == 0) s_next[(it + 1) & 1] = claim;
     compute_barrier();                                 // s_mask / s_acc are rewritten next round
+  }
+  }
+  // the last CTA out re-arms the counters for the next launch on this workspace
+  __syncthreads();
+  if (tid == 0) {
+    const unsigned int done = atomicAdd(&ws.sched[2], 1u);
+    if (done == gridDim.x - 1) { ws.sched[0] = 0u; ws.sched[1] = 0u; ws.sched[2] = 0u; }
   }
 }
 
@@ -394,7 +417,7 @@ cudaError_t launch_layout(const float* boxes, int64_t n, int H, int W, const Wor
   const int nblk = (int)layout_blocks(n);
   layout_local_kernel<<<nblk, kLayoutThreads, 0, stream>>>(boxes, n, H, W, ws.desc, ws.block_sums);
   layout_rebase_kernel<<<nblk, kLayoutThreads, 0, stream>>>(n, nblk, ws.desc, ws.block_sums,
-                                                            ws.cap_words, status);
+                                                            ws.cap_words, status, ws.sched);
   zero_marks_kernel<<<num_sms * 4, 256, 0, stream>>>(ws.V, ws.G, status);
   return cudaPeekAtLastError();
 }

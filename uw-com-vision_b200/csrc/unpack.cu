@@ -41,9 +41,11 @@ cudaError_t launch_unpack(const uint32_t* planes, int64_t n, int H, int W, uint8
   if (n == 0) return cudaSuccess;
   const int wpr = plane_row_words(W);
   const int64_t total = n * H * ((W + 31) >> 5);
+  // one word per thread in a one-shot grid: the hardware hands CTAs to whichever SM drains
+  // first (a static grid-stride split stops at 6.3 TB/s of stores, tools/fill_bench2.cu)
+  (void)num_sms;
   int64_t grid = (total + 255) / 256;
-  const int64_t cap = (int64_t)num_sms * 32;
-  if (grid > cap) grid = cap;
+  if (grid > 0x7fffffffLL) grid = 0x7fffffffLL;
   unpack_planes_kernel<<<(unsigned)grid, 256, 0, stream>>>(planes, n, H, W, wpr, out);
   return cudaPeekAtLastError();
 }

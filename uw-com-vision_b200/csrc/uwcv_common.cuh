@@ -50,6 +50,7 @@ constexpr int kLayoutThreads = 1024;   // instances per layout CTA
 struct Workspace {
   TileDesc* desc;      // [N]
   int64_t* block_sums; // [2 * ceil(N / 1024)]  per-CTA (tile words, tile rows) of the layout
+  unsigned int* sched; // [4]  work counters of the paste kernel (fill, tile, CTAs done); zero between launches
   uint32_t* M;         // [cap_words]  mask bits
   uint32_t* V;         // [cap_words]  border-visited marks
   uint32_t* G;         // [cap_words]  "right neighbour was background" marks (negative marks)
@@ -63,7 +64,7 @@ __host__ __device__ inline size_t layout_blocks(int64_t n) {
   return (size_t)((n + kLayoutThreads - 1) / kLayoutThreads);
 }
 __host__ __device__ inline size_t header_bytes(int64_t n) {
-  return align_up((size_t)n * sizeof(TileDesc), 256) + align_up(layout_blocks(n) * 16 + 16, 256);
+  return align_up((size_t)n * sizeof(TileDesc), 256) + align_up(layout_blocks(n) * 16 + 16, 256) + 256;
 }
 __host__ __device__ inline size_t workspace_bytes(int64_t n, int64_t tile_words) {
   return header_bytes(n) + (size_t)tile_words * 28 + 256;
@@ -75,6 +76,7 @@ __host__ __device__ inline Workspace carve(void* ws, size_t ws_bytes, int64_t n)
   w.desc = (TileDesc*)p;
   w.block_sums = (int64_t*)(p + align_up((size_t)n * sizeof(TileDesc), 256));
   size_t d = header_bytes(n);
+  w.sched = (unsigned int*)(p + d - 256);
   int64_t cap = ws_bytes > d + 256 ? (int64_t)((ws_bytes - d - 256) / 28) : 0;
   cap &= ~(int64_t)3;                         // keep every plane 16-byte aligned
   w.cap_words = cap;

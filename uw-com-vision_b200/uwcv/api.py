@@ -191,6 +191,33 @@ class Engine:
         self.d2h_stream = torch.cuda.Stream(device)
         self._dev_bufs = {}
         self._slots = {}
+        self._host_pool = []
+
+    def host_rows(self, r: int):
+        """Pinned host memory for one call's rows, recycled once the table that was handed out
+        with it is gone: returns (torch int64 [r,20], torch float64 [r,30], and the numpy views
+        of the same memory that the MeasurementTable will own).  A buffer is free when nothing
+        but the pool refers to its root array (every numpy view keeps a reference to it)."""
+        import sys
+        need = max(r * (NUM_INT + NUM_FLOAT), 1)
+        entry = None
+        for e in self._host_pool:
+            if e[0].numel() >= need and sys.getrefcount(e[1]) == 2:
+                entry = e
+                break
+        if entry is None:
+            self._host_pool = [e for e in self._host_pool
+                               if sys.getrefcount(e[1]) > 2 or e[0].numel() >= need]
+            buf = torch.empty(int(need * 1.1) + 64, dtype=torch.int64).pin_memory()
+            entry = [buf, buf.numpy()]
+            self._host_pool.append(entry)
+        buf, arr = entry
+        a, b = r * NUM_INT, r * (NUM_INT + NUM_FLOAT)
+        t_i = buf[:a].view(r, NUM_INT)
+        t_f = buf[a:b].view(torch.float64).view(r, NUM_FLOAT)
+        n_i = arr[:a].reshape(r, NUM_INT)
+        n_f = arr[a:b].view(np.float64).reshape(r, NUM_FLOAT)
+        return t_i, t_f, n_i, n_f
 
     def slot(self, k: int = 0) -> "_Slot":
         s = self._slots.get(k)
@@ -486,7 +513,7 @@ class PendingTable:
         self.n = 0
         self.planes = None
         self.return_planes = False
-        self.hp_i = self.hp_f = self.hp_s = None
+        self.hp_i = self.hp_f = self.hp_s = self.np_i = self.np_f = None
 
     @staticmethod
     def ready(value) -> "PendingTable":
@@ -507,7 +534,7 @@ class PendingTable:
                 self._value = (value,)
                 return value
             raise _lib.UwcvError(code, f"uwcv_paste_measure (needs {int(st[1])} tile words)")
-        table = MeasurementTable(self.hp_i.numpy().copy(), self.hp_f.numpy().copy())
+        table = MeasurementTable(self.np_i, self.np_f)
         value = (table, self.planes) if self.return_planes else table
         self._value = (value,)
         self._release()
@@ -517,6 +544,7 @@ class PendingTable:
         if self._slot is not None and self._slot.pending is self:
             self._slot.pending = None
         self._slot = None
+        self.hp_i = self.hp_f = self.hp_s = self.np_i = self.np_f = None
         self.planes = None if not self.return_planes else self.planes
 
 
@@ -688,8 +716,12 @@ def submit_measure_instances(instances, output_size=None, classes_of_interest=No
         else:
             planes = None
         pend.planes = planes if return_planes else None
+        small_parts = (("boxes", [boxes]), ("scores", sl), ("classes", cl), ("img", il), ("inst", jl))
+        if any(p_.is_cuda for _, parts in small_parts for p_ in parts):
+            eng.small_stream.wait_stream(main)        # device-resident inputs: after their producer
+        # (host inputs: the slot's buffers are free -- its previous call has been collected --
+        #  so these copies do not queue behind the kernels of the call before)
         with torch.cuda.stream(eng.small_stream):
-            eng.small_stream.wait_stream(main)
             d_boxes = slot.device("boxes", (n, 4), torch.float32)
             d_scores = slot.device("scores", (n,), torch.float32)
             d_classes = slot.device("classes", (n,), torch.int64)
@@ -731,8 +763,9 @@ def submit_measure_instances(instances, output_size=None, classes_of_interest=No
         else:
             out_i, out_f = rows_i, rows_f
         r = int(out_i.shape[0])
-        hp_i = slot.pinned("rows_i", (r, NUM_INT), torch.int64)
-        hp_f = slot.pinned("rows_f", (r, NUM_FLOAT), torch.float64)
+        # the rows land in pinned memory that the returned table owns (no host copy); the
+        # engine recycles the buffer when the table is gone
+        hp_i, hp_f, pend.np_i, pend.np_f = eng.host_rows(r)
         hp_s = slot.pinned("status", (4,), torch.int64)
         ev = torch.cuda.Event()
         ev.record(main)
