@@ -209,6 +209,7 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=dev)
 
     n_img, n_inst = args.images, args.instances
@@ -286,9 +287,11 @@ def run_ours(args):
         if len(fields) < 3:
             # the timed region is shorter than a few nvidia-smi periods: keep the same load
             # running (untimed) for about a second and sample the clocks under it
+            # (rank 0 only: the kernels without the collective, which the other ranks do not join)
             c0 = time.time()
             while time.time() - c0 < 1.0:
-                step()
+                step(stages=3)
+                step(stages=4)
                 torch.cuda.synchronize(dev)
             time.sleep(0.12)
             fields = sampler.window(wall0, time.time())
