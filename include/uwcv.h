@@ -120,6 +120,28 @@ int uwcv_paste_measure_range(const float* masks, const float* boxes, const int32
                              int64_t first, int64_t count);
 
 /*
+ * uwcv_paste_measure_heads -- as uwcv_paste_measure_range, fed straight from the mask head
+ * (the single-forward path): `masks` is [N, mask_channels, 28, 28] float32
+ * and instance i uses channel classes[i] + channel_offset (mask_channels == 1: channel 0, the
+ * class-agnostic head).  With is_logits != 0 the values are the head's raw logits and the
+ * sigmoid is applied while the tile is staged, as torch's CUDA sigmoid computes it
+ * (1 / (1 + expf(-x)), IEEE add and divide): no N x 1 x 28 x 28 probability tensor is
+ * materialised.  A channel outside [0, mask_channels) yields an empty mask.
+ *
+ * Stands in for detectron2 modeling/roi_heads/mask_head.py::mask_rcnn_inference
+ * (pred_mask_logits[arange(N), pred_classes][:, None].sigmoid()) followed by
+ * detector_postprocess, i.e. what predictor(im) does after the mask head at
+ * nn_inference.py:372.  classes must be non-NULL when mask_channels > 1.
+ */
+int uwcv_paste_measure_heads(const float* masks, int mask_channels, int channel_offset,
+                             int is_logits, const float* boxes, const int32_t* image_idx,
+                             const int32_t* inst_idx, const int64_t* classes, const float* scores,
+                             int64_t N, int H, int W, float thr, double pixels_per_metric,
+                             uint32_t* bitplanes, int64_t* rows_i, double* rows_f, void* workspace,
+                             size_t ws_bytes, int64_t* status, void* stream, int stages,
+                             int64_t first, int64_t count);
+
+/*
  * uwcv_unpack_planes -- expand bit-planes into the Detectron2-literal N x H x W bool
  * tensor (one byte per pixel), for callers that read pred_masks as such
  * (nn_inference.py:326, :376).

@@ -9,7 +9,8 @@ restate the published upstream algorithms the reference reaches through
 * ``Boxes`` / ``Instances``       -- detectron2/structures/{boxes,instances}.py
 * ``detector_postprocess``        -- detectron2/modeling/postprocessing.py
 * ``paste_masks_in_image``        -- detectron2/layers/mask_ops.py
-* ``fast_rcnn_inference_single_image`` -- detectron2/modeling/roi_heads/fast_rcnn.py
+* ``fast_rcnn_inference_single_image`` / ``fast_rcnn_inference`` -- detectron2/modeling/roi_heads/fast_rcnn.py
+* ``mask_rcnn_inference``         -- detectron2/modeling/roi_heads/mask_head.py
 * ``batched_nms_vanilla``         -- torchvision/ops/boxes.py:_batched_nms_vanilla
 
 The arithmetic itself is delegated to the libraries the reference runs on
@@ -339,6 +340,32 @@ def fast_rcnn_inference_single_image(boxes: torch.Tensor, scores: torch.Tensor,
     result.scores = scores
     result.pred_classes = filter_inds[:, 1]
     return result, filter_inds[:, 0]
+
+
+def fast_rcnn_inference(boxes, scores, image_shapes, score_thresh: float, nms_thresh: float,
+                        topk_per_image: int):
+    """UPSTREAM fast_rcnn.py::fast_rcnn_inference: the per-image function over a batch."""
+    out = [fast_rcnn_inference_single_image(b, s, shape, score_thresh, nms_thresh, topk_per_image)
+           for b, s, shape in zip(boxes, scores, image_shapes)]
+    return [x[0] for x in out], [x[1] for x in out]
+
+
+def mask_rcnn_inference(pred_mask_logits: torch.Tensor, pred_instances: List["Instances"]) -> None:
+    """UPSTREAM mask_head.py::mask_rcnn_inference: select the predicted class's channel of the
+    N x K x Hm x Wm mask logits (channel 0 for a class-agnostic head), sigmoid, and attach the
+    N x 1 x Hm x Wm probabilities to each image's Instances as ``pred_masks``."""
+    cls_agnostic_mask = pred_mask_logits.size(1) == 1
+    if cls_agnostic_mask:
+        mask_probs_pred = pred_mask_logits.sigmoid()
+    else:
+        num_masks = pred_mask_logits.shape[0]
+        class_pred = torch.cat([i.pred_classes for i in pred_instances])
+        indices = torch.arange(num_masks, device=class_pred.device)
+        mask_probs_pred = pred_mask_logits[indices, class_pred][:, None].sigmoid()
+    num_boxes_per_image = [len(i) for i in pred_instances]
+    mask_probs_pred = mask_probs_pred.split(num_boxes_per_image, dim=0)
+    for prob, instances in zip(mask_probs_pred, pred_instances):
+        instances.pred_masks = prob
 
 
 # --------------------------------------------------------------------------

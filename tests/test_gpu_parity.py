@@ -442,3 +442,113 @@ def test_measurement_stream_equals_synchronous_calls():
     p2 = stream.submit(batches[3], (H, W))           # reuses slot 0: p0 is materialised first
     for p, w in ((p2, want[3]), (p1, want[1]), (p0, want[0])):
         assert np.array_equal(p.result().ints, w.ints)
+
+
+# ---------------------------------------------------------------- single forward (f4) ---
+def _logit_instances(n, K, H, W, seed, offset):
+    """Instances carrying raw mask-head logits [n, K + offset, 28, 28] (blob-shaped, so that the
+    thresholded masks are realistic) next to the probabilities mask_rcnn_inference derives."""
+    base = synth.blob_instances(0, n, H, W, seed=seed)
+    g = torch.Generator().manual_seed(seed)
+    p = base.pred_masks[:, 0].clamp(1e-6, 1 - 1e-6)
+    own = torch.log(p) - torch.log1p(-p)                         # logit of the blob
+    logits = torch.randn((n, K + offset, 28, 28), generator=g) * 3.0
+    cls = base.pred_classes % K
+    logits[torch.arange(n), cls + offset] = own
+    # saturated / special values must survive the fused sigmoid exactly as torch's
+    logits[0, cls[0] + offset, 0, :6] = torch.tensor([0.0, 88.0, -88.0, 104.0, -104.0, 1e-8])
+    inst = uwcv.Instances((H, W), pred_boxes=base.pred_boxes, scores=base.scores, pred_classes=cls)
+    inst.set("pred_mask_logits", logits)
+    return inst
+
+
+def test_fused_sigmoid_class_select_equals_mask_rcnn_inference():
+    """uwcv_paste_measure_heads (channel select + sigmoid inside the paste kernel) == Detectron2's
+    mask_rcnn_inference followed by the plain path, bit for bit, with torch's CUDA sigmoid (the
+    device the reference's model runs on); against the CPU sigmoid the masks may differ where a
+    1-ulp difference of a probability crosses the threshold -- counted and bounded."""
+    H = W = 320
+    for K, offset in ((4, 0), (4, 1), (1, 0)):
+        batch = [_logit_instances(40 + 5 * k, K, H, W, seed=300 + k, offset=offset) for k in range(3)]
+        fused = uwcv.measure_instances(batch, (H, W), mask_channel_offset=offset, return_planes=True)
+        # unfused on the GPU: torch ops do what mask_rcnn_inference does
+        plain = []
+        for b in batch:
+            lg = b.pred_mask_logits.cuda()
+            idx = torch.arange(len(b), device="cuda")
+            ch = (b.pred_classes.cuda() + offset) if lg.shape[1] > 1 else torch.zeros_like(idx)
+            probs = lg[idx, ch][:, None].sigmoid().cpu()
+            plain.append(uwcv.Instances((H, W), pred_boxes=b.pred_boxes, scores=b.scores,
+                                        pred_classes=b.pred_classes, pred_masks=probs))
+        want = uwcv.measure_instances(plain, (H, W), return_planes=True)
+        assert np.array_equal(fused[0].ints, want[0].ints)
+        assert np.array_equal(fused[0].floats, want[0].floats, equal_nan=True)
+        assert torch.equal(fused[1], want[1])
+        # oracle (CPU): mask_rcnn_inference restatement + the CPU pipeline
+        if offset == 0:
+            ob = [P.to_oracle_instances(uwcv.Instances((H, W), pred_boxes=b.pred_boxes, scores=b.scores,
+                                                       pred_classes=b.pred_classes,
+                                                       pred_masks=torch.zeros(len(b), 1, 28, 28)))
+                  for b in batch]
+            d2.mask_rcnn_inference(torch.cat([b.pred_mask_logits for b in batch]), ob)
+            cpu_batch = [uwcv.Instances((H, W), pred_boxes=b.pred_boxes, scores=b.scores,
+                                        pred_classes=b.pred_classes, pred_masks=o.pred_masks)
+                         for b, o in zip(batch, ob)]
+            ri, rf = P.oracle_table(cpu_batch, (H, W))
+            diff = int((fused[0].ints[:, IC["area_px"]] != ri[:, IC["area_px"]]).sum())
+            print(f"K={K}: instances whose pixel area differs from the CPU-sigmoid oracle: {diff} / {len(ri)}")
+            assert diff <= max(1, len(ri) // 100)
+            if diff == 0:
+                compare_tables(fused[0], ri, rf)
+
+
+def test_bad_class_channel_gives_empty_mask():
+    inst = _logit_instances(10, 4, 128, 128, seed=5, offset=0)
+    inst.pred_classes[3] = 17                                    # outside the head's channels
+    t = uwcv.measure_instances(inst, (128, 128))
+    assert t["valid"][3] == 0 and t["area_px"][3] == 0
+    assert (t["valid"][[0, 1, 2]] == 1).all()
+
+
+def test_single_forward_torchvision_maskrcnn():
+    """SingleForward on a random-init torchvision Mask R-CNN: the batched NMS equals the
+    Detectron2 restatement on the same head outputs, and the measured table equals the one
+    obtained by materialising mask_rcnn_inference's probabilities first."""
+    import torchvision
+    torch.manual_seed(0)
+    model = torchvision.models.detection.maskrcnn_resnet50_fpn(
+        weights=None, weights_backbone=None, num_classes=5, min_size=256, max_size=256,
+        box_score_thresh=0.0, rpn_post_nms_top_n_test=200).cuda().eval()
+    images = [torch.rand(3, 256, 256) for _ in range(2)]
+    sf = uwcv.SingleForward(model, score_thresh=0.05, nms_thresh=0.5, detections_per_image=50)
+    inst = sf.predict(images)
+    assert len(inst) == 2 and all(i.has("pred_mask_logits") for i in inst)
+    assert sum(len(i) for i in inst) > 0
+    table = sf.measure(images)
+    assert 0 < len(table) <= sum(len(i) for i in inst)      # detector_postprocess drops empty boxes
+    plain = []
+    for i in inst:
+        lg = i.pred_mask_logits
+        probs = lg[torch.arange(len(i), device=lg.device), i.pred_classes + 1][:, None].sigmoid()
+        plain.append(uwcv.Instances(i.image_size, pred_boxes=i.pred_boxes, scores=i.scores,
+                                    pred_classes=i.pred_classes, pred_masks=probs))
+    want = uwcv.measure_instances(plain, (256, 256))
+    assert np.array_equal(table.ints, want.ints)
+    assert np.array_equal(table.floats, want.floats, equal_nan=True)
+    # the batched NMS against the oracle's fast_rcnn_inference on random head outputs
+    g = torch.Generator().manual_seed(1)
+    boxes_l, scores_l, shapes = [], [], []
+    for b in range(3):
+        R, K = 150 + 20 * b, 4
+        ctr = torch.rand((R, 1, 2), generator=g) * 200 + 20
+        wh = torch.rand((R, K, 2), generator=g) * 60 + 4
+        bx = torch.cat((ctr - wh / 2, ctr + wh / 2), dim=2).reshape(R, K * 4)
+        sc = torch.softmax(torch.randn((R, K + 1), generator=g) * 2, dim=1)
+        boxes_l.append(bx); scores_l.append(sc); shapes.append((240, 250))
+    got, got_rows = uwcv.fast_rcnn_inference(boxes_l, scores_l, shapes, 0.3, 0.5, 40)
+    ref, ref_rows = d2.fast_rcnn_inference(boxes_l, scores_l, shapes, 0.3, 0.5, 40)
+    for a, ar, r, rr in zip(got, got_rows, ref, ref_rows):
+        assert torch.equal(a.pred_boxes.tensor.cpu(), r.pred_boxes.tensor)
+        assert torch.equal(a.scores.cpu(), r.scores)
+        assert torch.equal(a.pred_classes.cpu(), r.pred_classes)
+        assert torch.equal(ar.cpu(), rr)

@@ -295,3 +295,21 @@ def test_golden_c1_consistency(golden_dir):
     cols = [j for j in range(ri.shape[1]) if j != skip]
     assert np.array_equal(ri2[:, cols], ri[sel][:, cols])
     assert np.array_equal(rf2, g["rows_f"][sel], equal_nan=True)
+
+
+def test_mask_rcnn_inference_restatement():
+    """detectron2 mask_head.py::mask_rcnn_inference: predicted-class channel, sigmoid, split per
+    image (class-agnostic head: channel 0)."""
+    from oracle import d2
+    g = torch.Generator().manual_seed(3)
+    logits = torch.randn((7, 4, 28, 28), generator=g) * 4
+    cls = torch.tensor([0, 3, 1, 2, 2, 0, 1])
+    insts = [d2.Instances((50, 60), pred_classes=cls[:3]), d2.Instances((50, 60), pred_classes=cls[3:])]
+    d2.mask_rcnn_inference(logits, insts)
+    assert insts[0].pred_masks.shape == (3, 1, 28, 28) and insts[1].pred_masks.shape == (4, 1, 28, 28)
+    for k in range(7):
+        got = (insts[0] if k < 3 else insts[1]).pred_masks[k if k < 3 else k - 3, 0]
+        assert torch.equal(got, torch.sigmoid(logits[k, cls[k]]))
+    ag = [d2.Instances((50, 60), pred_classes=cls)]
+    d2.mask_rcnn_inference(logits[:, :1], ag)
+    assert torch.equal(ag[0].pred_masks, torch.sigmoid(logits[:, :1]))

@@ -167,6 +167,12 @@ __device__ __forceinline__ void axis_coord(int p, float lo, float hi, int& base,
   base = (int)fc + kPad;           // in [0, kMaskSide + kPad] = [0, 30]; taps base, base+1 <= 31
 }
 
+// torch's CUDA sigmoid (ATen UnaryOpsKernel: 1 / (1 + std::exp(-a)) in float): accurate expf,
+// IEEE add and divide
+__device__ __forceinline__ float sigmoid_as_torch(float a) {
+  return __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-a)));
+}
+
 template <bool kPlanes>
 __global__ void __launch_bounds__(kPasteThreads)
 paste_measure_kernel(const float* __restrict__ masks, const float* __restrict__ boxes,
@@ -174,7 +180,7 @@ paste_measure_kernel(const float* __restrict__ masks, const float* __restrict__ 
                      const int64_t* __restrict__ classes, int64_t n, int H, int W, float thr,
                      uint32_t* __restrict__ planes, int64_t* __restrict__ rows_i,
                      Workspace ws, const int64_t* __restrict__ status, int zero_bytes,
-                     int rot_mul, int fill_mode, int debug_skip, int64_t first) {
+                     int rot_mul, int fill_mode, int debug_skip, int64_t first, MaskSource src) {
   extern __shared__ __align__(128) unsigned char s_zero[];     // zero_bytes (planes only)
   __shared__ __align__(16) float s_mask[kMaskPitch * kMaskPitch];
   __shared__ unsigned long long s_acc[10];
@@ -270,10 +276,17 @@ paste_measure_kernel(const float* __restrict__ masks, const float* __restrict__ 
     }
 
     // ---- stage the 28x28 probabilities into the zero-framed copy --------------------
-    const float* msrc = masks + inst * (kMaskSide * kMaskSide);
+    // probabilities as given, or (single-forward path) the predicted class's channel of the
+    // mask head's logits with the sigmoid of mask_rcnn_inference applied on the way in
+    int64_t chan = 0;
+    if (src.channels > 1) chan = (classes ? classes[inst] : 0) + src.channel_offset;
+    const bool chan_ok = chan >= 0 && chan < src.channels;       // bad class id: empty mask
+    const float* msrc = masks + inst * src.stride + (chan_ok ? chan : 0) * (kMaskSide * kMaskSide);
     for (int k = tid; k < kMaskSide * kMaskSide; k += kComputeThreads) {
       int r = k / kMaskSide, c = k - r * kMaskSide;
-      s_mask[(r + kPad) * kMaskPitch + c + kPad] = __ldg(msrc + k);
+      float v = chan_ok ? __ldg(msrc + k) : 0.f;
+      if (src.logits) v = chan_ok ? sigmoid_as_torch(v) : 0.f;
+      s_mask[(r + kPad) * kMaskPitch + c + kPad] = v;
     }
     if (tid < 10) s_acc[tid] = 0ull;
     if (tid == 0) { s_bbox[0] = INT_MAX; s_bbox[1] = INT_MAX; s_bbox[2] = -1; s_bbox[3] = -1; }
@@ -427,7 +440,7 @@ cudaError_t launch_paste_measure(const float* masks, const float* boxes, const i
                                  const int32_t* inst_idx, const int64_t* classes, int64_t first,
                                  int64_t count, int H, int W, float thr, uint32_t* planes,
                                  int64_t* rows_i, const Workspace& ws, const int64_t* status,
-                                 int num_sms, cudaStream_t stream) {
+                                 int num_sms, cudaStream_t stream, const MaskSource& src) {
   if (count == 0) return cudaSuccess;
   const int64_t n = first + count;
   int per_sm = 0;
@@ -462,11 +475,11 @@ cudaError_t launch_paste_measure(const float* masks, const float* boxes, const i
   if (planes)
     paste_measure_kernel<true><<<(unsigned)grid, kPasteThreads, dyn, stream>>>(
         masks, boxes, image_idx, inst_idx, classes, n, H, W, thr, planes, rows_i, ws, status,
-        zero_bytes, rot_mul, fill_mode, debug_skip, first);
+        zero_bytes, rot_mul, fill_mode, debug_skip, first, src);
   else
     paste_measure_kernel<false><<<(unsigned)grid, kPasteThreads, dyn, stream>>>(
         masks, boxes, image_idx, inst_idx, classes, n, H, W, thr, planes, rows_i, ws, status,
-        zero_bytes, rot_mul, fill_mode, debug_skip, first);
+        zero_bytes, rot_mul, fill_mode, debug_skip, first, src);
   return cudaPeekAtLastError();
 }
 

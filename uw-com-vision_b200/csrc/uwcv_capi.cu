@@ -7,7 +7,8 @@ cudaError_t launch_layout(const float*, int64_t, int, int, const Workspace&, int
                           cudaStream_t);
 cudaError_t launch_paste_measure(const float*, const float*, const int32_t*, const int32_t*,
                                  const int64_t*, int64_t, int64_t, int, int, float, uint32_t*,
-                                 int64_t*, const Workspace&, const int64_t*, int, cudaStream_t);
+                                 int64_t*, const Workspace&, const int64_t*, int, cudaStream_t,
+                                 const MaskSource&);
 cudaError_t launch_contour_measure(int64_t, int64_t, const float*, double, int64_t*, double*,
                                    const Workspace&, const int64_t*, int, cudaStream_t);
 cudaError_t launch_unpack(const uint32_t*, int64_t, int, int, uint8_t*, int, cudaStream_t);
@@ -78,13 +79,16 @@ int uwcv_paste_measure_stages(const float* masks, const float* boxes, const int3
                                   ws_bytes, status, stream, stages, 0, N);
 }
 
-int uwcv_paste_measure_range(const float* masks, const float* boxes, const int32_t* image_idx,
+int uwcv_paste_measure_heads(const float* masks, int mask_channels, int channel_offset,
+                             int is_logits, const float* boxes, const int32_t* image_idx,
                              const int32_t* inst_idx, const int64_t* classes, const float* scores,
                              int64_t N, int H, int W, float thr, double pixels_per_metric,
                              uint32_t* bitplanes, int64_t* rows_i, double* rows_f, void* workspace,
                              size_t ws_bytes, int64_t* status, void* stream, int stages,
                              int64_t first, int64_t count) {
   if (N < 0 || H <= 0 || W <= 0) return UWCV_E_SHAPE;
+  if (mask_channels < 1 || mask_channels > 65536) return UWCV_E_SHAPE;
+  if (mask_channels > 1 && N > 0 && !classes) return UWCV_E_NULL;
   if (H > 32768 || W > 32768) return UWCV_E_TOO_LARGE;
   if (!(thr > 0.f)) return UWCV_E_THRESH;
   if (!(pixels_per_metric > 0.0)) return UWCV_E_SHAPE;
@@ -101,16 +105,32 @@ int uwcv_paste_measure_range(const float* masks, const float* boxes, const int32
     return UWCV_E_ALIGN;
   if (ws_bytes < uwcv::workspace_bytes(N, 4)) return UWCV_E_WORKSPACE;
   const uwcv::Workspace ws = uwcv::carve(workspace, ws_bytes, N);
+  uwcv::MaskSource src;
+  src.stride = (int64_t)mask_channels * UWCV_MASK_SIDE * UWCV_MASK_SIDE;
+  src.channels = mask_channels;
+  src.channel_offset = channel_offset;
+  src.logits = is_logits ? 1 : 0;
   if ((stages & 1) && uwcv::launch_layout(boxes, N, H, W, ws, status, num_sms(), st) != cudaSuccess)
     return UWCV_E_LAUNCH;
   if ((stages & 2) &&
       uwcv::launch_paste_measure(masks, boxes, image_idx, inst_idx, classes, first, count, H, W,
-                                 thr, bitplanes, rows_i, ws, status, num_sms(), st) != cudaSuccess)
+                                 thr, bitplanes, rows_i, ws, status, num_sms(), st, src) != cudaSuccess)
     return UWCV_E_LAUNCH;
   if ((stages & 4) && uwcv::launch_contour_measure(first, count, scores, pixels_per_metric, rows_i,
                                                    rows_f, ws, status, num_sms(), st) != cudaSuccess)
     return UWCV_E_LAUNCH;
   return UWCV_OK;
+}
+
+int uwcv_paste_measure_range(const float* masks, const float* boxes, const int32_t* image_idx,
+                             const int32_t* inst_idx, const int64_t* classes, const float* scores,
+                             int64_t N, int H, int W, float thr, double pixels_per_metric,
+                             uint32_t* bitplanes, int64_t* rows_i, double* rows_f, void* workspace,
+                             size_t ws_bytes, int64_t* status, void* stream, int stages,
+                             int64_t first, int64_t count) {
+  return uwcv_paste_measure_heads(masks, 1, 0, 0, boxes, image_idx, inst_idx, classes, scores, N, H,
+                                  W, thr, pixels_per_metric, bitplanes, rows_i, rows_f, workspace,
+                                  ws_bytes, status, stream, stages, first, count);
 }
 
 int uwcv_unpack_planes(const uint32_t* bitplanes, int64_t N, int H, int W, uint8_t* out,

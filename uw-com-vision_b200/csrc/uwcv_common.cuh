@@ -44,6 +44,14 @@ struct __align__(16) TileDesc {
   int64_t row_off;    // offset of the tile's first row in the per-row trace scratch
 };
 
+// Where the 28 x 28 mask of instance i comes from: base + i * stride (+ channel * 784)
+struct MaskSource {
+  int64_t stride;        // floats between consecutive instances (784 for plain probabilities)
+  int channels;          // 1: the only channel; > 1: channel classes[i] + channel_offset
+  int channel_offset;
+  int logits;            // 1: apply the sigmoid of mask_rcnn_inference while staging
+};
+
 // Workspace carve-up, computed identically on host and device.
 constexpr int kLayoutThreads = 1024;   // instances per layout CTA
 

@@ -42,6 +42,8 @@ def lib() -> C.CDLL:
     L.uwcv_paste_measure_stages.argtypes = L.uwcv_paste_measure.argtypes + [i32]
     L.uwcv_paste_measure_range.restype = C.c_int
     L.uwcv_paste_measure_range.argtypes = L.uwcv_paste_measure_stages.argtypes + [i64, i64]
+    L.uwcv_paste_measure_heads.restype = C.c_int
+    L.uwcv_paste_measure_heads.argtypes = [vp, i32, i32, i32] + L.uwcv_paste_measure_range.argtypes[1:]
     L.uwcv_unpack_planes.restype = C.c_int
     L.uwcv_unpack_planes.argtypes = [vp, i64, i32, i32, vp, vp]
     L.uwcv_union_workspace_bytes.restype = sz
@@ -59,7 +61,8 @@ def lib() -> C.CDLL:
 
 
 EXPORTS = ("uwcv_version", "uwcv_strerror", "uwcv_plane_row_words", "uwcv_workspace_bytes",
-           "uwcv_paste_measure", "uwcv_paste_measure_stages", "uwcv_paste_measure_range", "uwcv_unpack_planes",
+           "uwcv_paste_measure", "uwcv_paste_measure_stages", "uwcv_paste_measure_range", "uwcv_paste_measure_heads",
+           "uwcv_unpack_planes",
            "uwcv_union_workspace_bytes", "uwcv_union_measure", "uwcv_nms_workspace_bytes",
            "uwcv_nms_filter")
 

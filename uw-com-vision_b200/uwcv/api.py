@@ -260,10 +260,13 @@ class Engine:
             planes: Optional[torch.Tensor] = None, n_tile_words: Optional[int] = None,
             rows_i: Optional[torch.Tensor] = None, rows_f: Optional[torch.Tensor] = None,
             stages: int = 7, status: Optional[torch.Tensor] = None, ws_slot: int = 0,
-            first: int = 0, count: Optional[int] = None):
+            first: int = 0, count: Optional[int] = None, mask_channels: int = 1,
+            channel_offset: int = 0, logits: bool = False):
         """All tensors on ``self.device``, contiguous: masks [N,28,28] f32, boxes [N,4] f32
         (output space), image_idx/inst_idx int32, classes int64, scores f32,
-        planes None or uint32/int32 [N, H, plane_row_words(W)].
+        planes None or uint32/int32 [N, H, plane_row_words(W)].  Single-forward form: masks
+        [N, mask_channels, 28, 28] (instance i uses channel classes[i] + channel_offset),
+        ``logits=True`` applies the mask head's sigmoid while staging (uwcv_paste_measure_heads).
         Returns (rows_i [N,20] int64, rows_f [N,30] float64, status [4] int64)."""
         n = int(boxes.shape[0])
         dev = self.device
@@ -276,8 +279,8 @@ class Engine:
         ws = self._workspace(n, n_tile_words, ws_slot)
         status = self.status if status is None else status
         with torch.cuda.device(dev):
-            rc = self.L.uwcv_paste_measure_range(
-                _ptr(masks), _ptr(boxes), _ptr(image_idx), _ptr(inst_idx), _ptr(classes),
+            rc = self.L.uwcv_paste_measure_heads(
+                _ptr(masks), int(mask_channels), int(channel_offset), int(bool(logits)), _ptr(boxes), _ptr(image_idx), _ptr(inst_idx), _ptr(classes),
                 _ptr(scores), n, int(H), int(W), float(threshold), float(pixels_per_metric),
                 _ptr(planes), _ptr(rows_i), _ptr(rows_f), _ptr(ws), ws.numel(),
                 _ptr(status), _stream_ptr(dev), int(stages), int(first),
@@ -450,13 +453,27 @@ def fast_rcnn_inference_single_image(boxes: torch.Tensor, scores: torch.Tensor,
 # measurement entry (GetMask_Contours / GetCounts replacement)
 # ----------------------------------------------------------------------------------
 
+def _mask_field(inst):
+    """(tensor [N, C, 28, 28], is_logits): ``pred_masks`` (N x 1 x 28 x 28 probabilities, the
+    output of mask_rcnn_inference) or, on the single-forward path, ``pred_mask_logits``
+    (N x K x 28 x 28 raw mask-head output; channel select + sigmoid happen in the kernel)."""
+    has = inst.has if hasattr(inst, "has") else (lambda k: k in inst._fields)
+    if has("pred_mask_logits") and not has("pred_masks"):
+        m = inst.pred_mask_logits
+        if m.dim() != 4:
+            raise ValueError(f"pred_mask_logits must be N x K x 28 x 28, got {tuple(m.shape)}")
+        return m, True
+    m = inst.pred_masks
+    if m.dim() == 3:
+        m = m[:, None]
+    return m, False
+
+
 def _gather_fields(inst, classes_of_interest):
     boxes = _as_box_tensor(inst.pred_boxes)
     scores = inst.scores
     classes = inst.pred_classes
-    masks = inst.pred_masks
-    if masks.dim() == 4:
-        masks = masks[:, 0]
+    masks, _ = _mask_field(inst)
     if classes_of_interest is not None:
         sel = torch.zeros(len(classes), dtype=torch.bool, device=classes.device)
         for c in classes_of_interest:
@@ -555,6 +572,7 @@ def measure_instances(instances: Union[object, Sequence[object]],
                       image_idx_offset: int = 0, return_planes: bool = False,
                       write_planes: bool = False, gather: bool = False,
                       gather_counts: Optional[Sequence[int]] = None,
+                      mask_channel_offset: int = 0,
                       pipeline_chunks: int = 4, device=None, _exact_words: bool = False):
     """Per-instance measurement rows for one image or a batch of images.
 
@@ -571,13 +589,18 @@ def measure_instances(instances: Union[object, Sequence[object]],
     process per GPU, images sharded over ranks) all-gathers the device rows of every rank
     before the host read, so each rank returns the whole job's table; ``gather_counts``
     (rows per rank, when the caller knows them) skips the count exchange.
+
+    Single-forward form: instead of ``pred_masks`` the instances may carry
+    ``pred_mask_logits`` (N x K x 28 x 28, the mask head's raw output); the kernel reads channel
+    ``pred_classes[i] + mask_channel_offset`` and applies the sigmoid itself, which is what
+    detectron2's ``mask_rcnn_inference`` does before ``detector_postprocess``.
     """
     return submit_measure_instances(
         instances, output_size, classes_of_interest, mask_threshold=mask_threshold,
         pixels_per_metric=pixels_per_metric, image_idx_offset=image_idx_offset,
         return_planes=return_planes, write_planes=write_planes, gather=gather,
-        gather_counts=gather_counts, pipeline_chunks=pipeline_chunks, device=device,
-        _exact_words=_exact_words).result()
+        gather_counts=gather_counts, mask_channel_offset=mask_channel_offset,
+        pipeline_chunks=pipeline_chunks, device=device, _exact_words=_exact_words).result()
 
 
 class MeasurementStream:
@@ -617,6 +640,7 @@ def submit_measure_instances(instances, output_size=None, classes_of_interest=No
                              image_idx_offset: int = 0, return_planes: bool = False,
                              write_planes: bool = False, gather: bool = False,
                              gather_counts: Optional[Sequence[int]] = None,
+                             mask_channel_offset: int = 0,
                              pipeline_chunks: int = 4, device=None, _exact_words: bool = False,
                              _slot: int = 0) -> PendingTable:
     """Enqueue one ``measure_instances`` call (same arguments) and return its handle."""
@@ -634,6 +658,15 @@ def submit_measure_instances(instances, output_size=None, classes_of_interest=No
         slot.pending.result()
 
     bl, sl, cl, ml, il, jl = [], [], [], [], [], []
+    mfields = [_mask_field(inst) for inst in batch]
+    logits = mfields[0][1]
+    channels = int(mfields[0][0].shape[1]) if mfields[0][0].dim() == 4 else 1
+    for m, lg in mfields:
+        if lg != logits or (len(m) and int(m.shape[1]) != channels):
+            raise ValueError("all images of one call must carry the same kind of mask field")
+        if len(m) and tuple(m.shape[-2:]) != (MASK_SIDE, MASK_SIDE):
+            raise ValueError(f"uwcv is built for {MASK_SIDE}x{MASK_SIDE} mask heads, got {tuple(m.shape)}")
+    mrow = channels * MASK_SIDE * MASK_SIDE
     sizes = {tuple(int(v) for v in inst.image_size) for inst in batch}
     if output_size is None and len(sizes) > 1:
         raise ValueError("all images of one call must share the output size")
@@ -644,8 +677,7 @@ def submit_measure_instances(instances, output_size=None, classes_of_interest=No
         # fast host path: one scale / clip / non-empty over the concatenated boxes; the mask
         # probabilities start moving to the device first (optimistically: no box is dropped)
         lens = [len(i) for i in batch]
-        ml0 = [(i.pred_masks[:, 0] if i.pred_masks.dim() == 4 else i.pred_masks)
-               .to(torch.float32).reshape(-1, MASK_SIDE, MASK_SIDE) for i in batch]
+        ml0 = [m.to(torch.float32).reshape(-1, mrow) for m, _ in mfields]
         early = _issue_mask_copies(eng, slot, dev, ml0, lens, pipeline_chunks)
         allb = torch.cat([_as_box_tensor(i.pred_boxes) for i in batch])
         b_all, keep_all = scale_clip_boxes(allb, batch[0].image_size, (H, W))
@@ -675,7 +707,7 @@ def submit_measure_instances(instances, output_size=None, classes_of_interest=No
         bl.append(b)
         sl.append(scores.to(torch.float32))
         cl.append(classes.to(torch.int64))
-        ml.append(masks.to(torch.float32).reshape(-1, MASK_SIDE, MASK_SIDE))
+        ml.append(masks.to(torch.float32).reshape(-1, mrow))
         il.append(torch.full((nk,), image_idx_offset + k, dtype=torch.int32))
         jl.append(torch.arange(nk, dtype=torch.int32))
     boxes = torch.cat(bl)
@@ -697,8 +729,8 @@ def submit_measure_instances(instances, output_size=None, classes_of_interest=No
             instances, output_size, classes_of_interest, mask_threshold=mask_threshold,
             pixels_per_metric=pixels_per_metric, image_idx_offset=image_idx_offset,
             return_planes=return_planes, write_planes=write_planes, gather=gather,
-            gather_counts=gather_counts, pipeline_chunks=pipeline_chunks, device=device,
-            _exact_words=True)
+            gather_counts=gather_counts, mask_channel_offset=mask_channel_offset,
+            pipeline_chunks=pipeline_chunks, device=device, _exact_words=True)
 
     pend = PendingTable(slot, None if _exact_words else retry)
     pend.return_planes = return_planes
@@ -743,7 +775,8 @@ def submit_measure_instances(instances, output_size=None, classes_of_interest=No
         common = dict(image_idx=d_img, inst_idx=d_inst, classes=d_classes, scores=d_scores,
                       threshold=mask_threshold, pixels_per_metric=pixels_per_metric,
                       planes=planes, n_tile_words=n_words, rows_i=rows_i, rows_f=rows_f,
-                      status=status)
+                      status=status, mask_channels=channels,
+                      channel_offset=mask_channel_offset if channels > 1 else 0, logits=logits)
         # layout for the whole call as soon as the boxes are on the device; paste chunk by chunk
         # as the mask probabilities arrive; one border-trace launch over all instances (its
         # duration is set by the longest serial chain, not by the instance count)
@@ -807,8 +840,21 @@ def _issue_mask_copies(eng: "Engine", slot: _Slot, dev, ml, counts, pipeline_chu
     for k in counts:
         starts.append(starts[-1] + k)
     main = torch.cuda.current_stream(dev)
+    mrow = int(ml[0].shape[1]) if len(ml) else MASK_SIDE * MASK_SIDE
+    # device-resident masks that already sit back to back in one allocation (the mask head's
+    # output split per image) are used where they are
+    live = [m for m in ml if m.shape[0] > 0]
+    if live and all(m.is_cuda and m.device == dev and m.is_contiguous() and
+                    m.dtype == torch.float32 for m in live) and \
+            all(a.data_ptr() + a.numel() * 4 == b.data_ptr() and
+                a.untyped_storage().data_ptr() == b.untyped_storage().data_ptr()
+                for a, b in zip(live[:-1], live[1:])) and live[0].data_ptr() % 16 == 0:
+        whole = torch.as_strided(live[0], (n, mrow), (mrow, 1))
+        ev = torch.cuda.Event()
+        ev.record(main)
+        return whole, [ev for _ in bounds], bounds
     with torch.cuda.device(dev):
-        d_masks = slot.device("masks", (n, MASK_SIDE, MASK_SIDE), torch.float32)
+        d_masks = slot.device("masks", (n, mrow), torch.float32)
         ev_in = [torch.cuda.Event() for _ in bounds]
         # the slot's previous call (the only other user of this buffer) was collected before
         # this one was admitted, so the copies need not wait for the main stream
