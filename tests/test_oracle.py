@@ -309,7 +309,9 @@ def test_mask_rcnn_inference_restatement():
     assert insts[0].pred_masks.shape == (3, 1, 28, 28) and insts[1].pred_masks.shape == (4, 1, 28, 28)
     for k in range(7):
         got = (insts[0] if k < 3 else insts[1]).pred_masks[k if k < 3 else k - 3, 0]
-        assert torch.equal(got, torch.sigmoid(logits[k, cls[k]]))
+        # torch's CPU sigmoid is not bit-stable across tensor shapes (vectorised body vs scalar
+        # tail differ by an ulp), which is why the f4 parity bar is torch's CUDA sigmoid
+        assert torch.allclose(got, torch.sigmoid(logits[k, cls[k]]), rtol=3e-7, atol=0)
     ag = [d2.Instances((50, 60), pred_classes=cls)]
     d2.mask_rcnn_inference(logits[:, :1], ag)
     assert torch.equal(ag[0].pred_masks, torch.sigmoid(logits[:, :1]))
