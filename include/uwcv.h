@@ -193,6 +193,40 @@ int uwcv_union_measure(const void* paste_workspace, size_t paste_ws_bytes, int64
                        int64_t rec_cap, int64_t ext_rows_cap, double pixels_per_metric,
                        int64_t* rows_i, double* rows_f, int64_t* counters, void* stream);
 
+/*
+ * Mask clean-up + RLE export -- stands in for postprocess_masks
+ * (nn_inference.py:259-302) and rle_encoding (:247-257) of the reference's export loop (:315-336).
+ *
+ * Call order on one stream: uwcv_paste_measure_stages(stages = 3) -> [uwcv_mask_column_totals,
+ * host decides `limit`] -> uwcv_clean_masks -> exclusive scan of run_counts (caller) ->
+ * uwcv_rle_write.  The instances of one image must be consecutive and carry inst_idx = 0, 1, ...
+ * in list (score) order; image_slot[i] in [0, B) is the image's position in this call.  The
+ * workspace's mask plane is REPLACED by the cleaned masks; its other planes are scratch (do not
+ * run stage 4 on it afterwards).
+ *
+ * uwcv_mask_column_totals: column_totals [B, W] int32 (zeroed by the caller) += number of mask
+ *   pixels of every instance in each image column -- what the reference's
+ *   np.sum(ori_mask, axis=(0, 1)) yields (:277); the caller derives limit[b] from it.
+ * uwcv_clean_masks: per instance with inst_idx < limit[image_slot] (limit == NULL: all):
+ *   fill holes (scipy binary_fill_holes), dilate + erode with the 3 x 3 cross (skimage defaults,
+ *   reflected border), cut the pixels covered by an earlier cleaned mask of the image, empty the
+ *   mask if it has more than one 8-connected piece.  Outputs, [N] each: flags (bit 0 = emptied as
+ *   multi-piece, bit 1 = beyond limit: not part of the output), area (pixels of the result),
+ *   run_counts (column-major runs of the result, before merging across columns).
+ * uwcv_rle_write: runs [2 * run_offsets[N]] int64 = (start, length) pairs, start 1-based in
+ *   column-major order (x * H + y + 1), instance i at run_offsets[i] .. run_offsets[i + 1].  A run
+ *   that ends on the last image row and the next that starts on row 0 of the following column are
+ *   one run for the reference (consecutive flat indices): the caller merges pairs with
+ *   start[k + 1] == start[k] + length[k].
+ */
+int uwcv_mask_column_totals(const void* paste_workspace, size_t ws_bytes, int64_t N, int W,
+                            const int32_t* image_slot, int32_t* column_totals, void* stream);
+int uwcv_clean_masks(void* paste_workspace, size_t ws_bytes, int64_t N, int H, int W,
+                     const int32_t* image_slot, const int32_t* inst_idx, const int32_t* limit,
+                     int32_t* flags, int64_t* area, int64_t* run_counts, void* stream);
+int uwcv_rle_write(const void* paste_workspace, size_t ws_bytes, int64_t N, int H, int W,
+                   const int64_t* run_offsets, int64_t* runs, void* stream);
+
 /* Bytes of workspace for uwcv_nms_filter; image_off is a HOST array [B + 1];
  * num_classes <= 0 means 128. */
 size_t uwcv_nms_workspace_bytes(const int64_t* image_off, int B, int num_classes);

@@ -552,3 +552,87 @@ def test_single_forward_torchvision_maskrcnn():
         assert torch.equal(a.scores.cpu(), r.scores)
         assert torch.equal(a.pred_classes.cpu(), r.pred_classes)
         assert torch.equal(ar.cpu(), rr)
+
+
+# ---------------------------------------------------------------- clean-up + RLE (f2) ---
+def _oracle_export(batch, names, H, W):
+    from oracle import cleanup as OC
+    masks_l, scores_l = [], []
+    for b in batch:
+        res = d2.detector_postprocess(P.to_oracle_instances(b), H, W, 0.5)
+        masks_l.append(res.pred_masks.numpy())
+        scores_l.append(res.scores.numpy())
+    return OC.export_rows(names, masks_l, scores_l, (H, W))
+
+
+def _sorted_by_score(inst):
+    order = torch.argsort(inst.scores, descending=True)
+    out = uwcv.Instances(inst.image_size)
+    for k, v in inst.get_fields().items():
+        out.set(k, uwcv.Boxes(v.tensor[order]) if hasattr(v, "tensor") else v[order])
+    return out
+
+
+def test_clean_masks_and_rle_equal_the_reference_export():
+    """export_rle == postprocess_masks + rle_encoding of the reference (oracle/cleanup.py) on the
+    masks the Detectron2 restatement pastes: identical ImageId / EncodedPixels rows."""
+    H, W = 192, 224                                        # W a multiple of 32, H not
+    batch, names = [], []
+    for k in range(4):                                     # dense: overlaps, cuts, several pieces
+        batch.append(_sorted_by_score(synth.blob_instances(k, 60, H, W, seed=700 + k)))
+        names.append(f"img{k}.tif")
+    # hand-made image: border-touching boxes, near-border growth, a full-height all-ones mask
+    # (runs continue across columns), identical boxes (the second is cut away entirely)
+    boxes = torch.tensor([[10., 0., 42., float(H)], [0., 0., 30.5, 20.], [1., 150., 40., 191.],
+                          [100., 60., 160., 120.], [100., 60., 160., 120.], [180., 100., float(W), 140.],
+                          [120., 1., 150., 30.]])
+    m = torch.ones((7, 1, 28, 28))
+    g = torch.Generator().manual_seed(9)
+    m[3:5] = synth.blob_probs(2, g)[:, None]
+    m[6, 0, 10:18, 10:18] = 0.0                            # a hole: filled
+    hand = uwcv.Instances((H, W), pred_boxes=uwcv.Boxes(boxes),
+                          scores=torch.linspace(0.95, 0.6, 7), pred_classes=torch.zeros(7, dtype=torch.int64),
+                          pred_masks=m)
+    batch.append(hand); names.append("hand.tif")
+    zero = _sorted_by_score(synth.blob_instances(9, 12, H, W, seed=710))
+    zero.scores[-1] = 0.0                                  # ``ori_score.all() < 0.5``: image skipped
+    batch.append(zero); names.append("zero.tif")
+    thin = uwcv.Instances((H, W), pred_boxes=uwcv.Boxes(torch.tensor([[50., 20. + 9 * i, 52., 28. + 9 * i] for i in range(5)])),
+                          scores=torch.linspace(0.9, 0.5, 5), pred_classes=torch.zeros(5, dtype=torch.int64),
+                          pred_masks=torch.ones((5, 1, 28, 28)))
+    batch.append(thin); names.append("thin.tif")           # 2 occupied columns < 5 instances: truncated
+    batch.append(uwcv.Instances((H, W), pred_boxes=uwcv.Boxes(torch.zeros((0, 4))), scores=torch.zeros(0),
+                                pred_classes=torch.zeros(0, dtype=torch.int64),
+                                pred_masks=torch.zeros((0, 1, 28, 28))))
+    names.append("none.tif")
+    ids, enc = _oracle_export(batch, names, H, W)
+    got = uwcv.export_rle(batch, (H, W), names)
+    assert got.image_id == ids
+    bad = [k for k, (a, b) in enumerate(zip(got.encoded_pixels, enc)) if a != b]
+    assert not bad, f"{len(bad)} of {len(enc)} rows differ, first {bad[:5]} ({got.image_id[bad[0]]})"
+    assert "zero" not in ids and ids.count("thin") == 2 and "none" not in ids
+    n_empty = sum(1 for e in enc if e == "")
+    n_multi = int(got.multi_piece.sum())
+    print(f"{len(enc)} rows, {n_empty} emptied ({n_multi} as multi-piece)")
+    assert n_multi > 0 and n_empty > n_multi               # both mechanisms are exercised
+    # areas reported by the kernel == pixels of the decoded strings
+    from oracle import cleanup as OC
+    for k in (0, len(enc) // 2, len(enc) - 1):
+        assert int(OC.rle_decode(enc[k], (W, H)).sum()) == int(got.area[k])
+
+
+def test_rle_full_size_round_trip():
+    """Config-2-sized image: every exported run lies inside its instance's pixel box, the decoded
+    masks of an image are pairwise disjoint (the point of the overlap cut), areas match."""
+    from oracle import cleanup as OC
+    H = W = 2048
+    inst = _sorted_by_score(synth.blob_instances(0, 1000, H, W, seed=1234))
+    got = uwcv.export_rle(inst, (H, W), ["a.tif"])
+    assert len(got) == 1000
+    cover = np.zeros(H * W, dtype=np.uint8)
+    for k in range(len(got)):
+        s = np.array(got.encoded_pixels[k].split(), dtype=np.int64).reshape(-1, 2)
+        assert int(s[:, 1].sum()) == int(got.area[k])
+        for a, l in s:
+            cover[a - 1:a - 1 + l] += 1
+    assert cover.max() <= 1

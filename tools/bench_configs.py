@@ -77,4 +77,10 @@ out["config4_4096_dense"] = {"candidates": len(cb), "instances": k, "nms_ms": ms
 t0 = time.perf_counter(); ut = uwcv.measure_union(batch[0], (2048, 2048), classes_of_interest=[3]); t1 = time.perf_counter()
 t0 = time.perf_counter(); ut = uwcv.measure_union(batch[:8], (2048, 2048), classes_of_interest=[3]); t1 = time.perf_counter()
 out["union_mode_8_images_class3"] = {"rows": len(ut), "wall_ms": (t1 - t0) * 1e3}
+# ---- f2: mask clean-up + RLE export on 8 config-2 images ------------------------------------------
+uwcv.export_rle(batch[:2], (2048, 2048))
+torch.cuda.synchronize()
+t0 = time.perf_counter(); ex = uwcv.export_rle(batch[:8], (2048, 2048)); t1 = time.perf_counter()
+out["rle_export_8_images"] = {"rows": len(ex), "wall_ms": (t1 - t0) * 1e3,
+                              "emptied_multi_piece": int(ex.multi_piece.sum())}
 print(json.dumps(out, indent=1))

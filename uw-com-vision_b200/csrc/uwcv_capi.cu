@@ -19,6 +19,12 @@ cudaError_t launch_union(int64_t, const Workspace&, const int32_t*, const TileDe
                          double*, int64_t*, int, cudaStream_t);
 cudaError_t launch_nms(const float*, const float*, const int64_t*, const int64_t*, int, int, float,
                        double, int, int64_t*, int32_t*, void*, cudaStream_t);
+cudaError_t launch_column_totals(int64_t, int, const Workspace&, const int32_t*, int32_t*,
+                                 cudaStream_t);
+cudaError_t launch_clean(int64_t, int, int, const Workspace&, const int32_t*, const int32_t*,
+                         const int32_t*, int32_t*, int64_t*, int64_t*, cudaStream_t);
+cudaError_t launch_rle_write(int64_t, int, int, const Workspace&, const int64_t*, int64_t*,
+                             cudaStream_t);
 }  // namespace uwcv
 
 namespace {
@@ -141,6 +147,48 @@ int uwcv_unpack_planes(const uint32_t* bitplanes, int64_t N, int H, int W, uint8
   if (misaligned(bitplanes)) return UWCV_E_ALIGN;
   return uwcv::launch_unpack(bitplanes, N, H, W, out, num_sms(),
                              reinterpret_cast<cudaStream_t>(stream)) == cudaSuccess
+             ? UWCV_OK : UWCV_E_LAUNCH;
+}
+
+int uwcv_mask_column_totals(const void* paste_workspace, size_t ws_bytes, int64_t N, int W,
+                            const int32_t* image_slot, int32_t* column_totals, void* stream) {
+  if (N < 0 || W <= 0) return UWCV_E_SHAPE;
+  if (N == 0) return UWCV_OK;
+  if (!paste_workspace || !image_slot || !column_totals) return UWCV_E_NULL;
+  if (misaligned(paste_workspace)) return UWCV_E_ALIGN;
+  if (ws_bytes < uwcv::workspace_bytes(N, 4)) return UWCV_E_WORKSPACE;
+  const uwcv::Workspace ws = uwcv::carve(const_cast<void*>(paste_workspace), ws_bytes, N);
+  return uwcv::launch_column_totals(N, W, ws, image_slot, column_totals,
+                                    reinterpret_cast<cudaStream_t>(stream)) == cudaSuccess
+             ? UWCV_OK : UWCV_E_LAUNCH;
+}
+
+int uwcv_clean_masks(void* paste_workspace, size_t ws_bytes, int64_t N, int H, int W,
+                     const int32_t* image_slot, const int32_t* inst_idx, const int32_t* limit,
+                     int32_t* flags, int64_t* area, int64_t* run_counts, void* stream) {
+  if (N < 0 || H <= 0 || W <= 0) return UWCV_E_SHAPE;
+  if (H > 32768 || W > 32768) return UWCV_E_TOO_LARGE;
+  if (N == 0) return UWCV_OK;
+  if (!paste_workspace || !image_slot || !inst_idx || !flags || !area || !run_counts)
+    return UWCV_E_NULL;
+  if (misaligned(paste_workspace)) return UWCV_E_ALIGN;
+  if (ws_bytes < uwcv::workspace_bytes(N, 4)) return UWCV_E_WORKSPACE;
+  const uwcv::Workspace ws = uwcv::carve(paste_workspace, ws_bytes, N);
+  return uwcv::launch_clean(N, H, W, ws, image_slot, inst_idx, limit, flags, area, run_counts,
+                            reinterpret_cast<cudaStream_t>(stream)) == cudaSuccess
+             ? UWCV_OK : UWCV_E_LAUNCH;
+}
+
+int uwcv_rle_write(const void* paste_workspace, size_t ws_bytes, int64_t N, int H, int W,
+                   const int64_t* run_offsets, int64_t* runs, void* stream) {
+  if (N < 0 || H <= 0 || W <= 0) return UWCV_E_SHAPE;
+  if (N == 0) return UWCV_OK;
+  if (!paste_workspace || !run_offsets || !runs) return UWCV_E_NULL;
+  if (misaligned(paste_workspace)) return UWCV_E_ALIGN;
+  if (ws_bytes < uwcv::workspace_bytes(N, 4)) return UWCV_E_WORKSPACE;
+  const uwcv::Workspace ws = uwcv::carve(const_cast<void*>(paste_workspace), ws_bytes, N);
+  return uwcv::launch_rle_write(N, H, W, ws, run_offsets, runs,
+                                reinterpret_cast<cudaStream_t>(stream)) == cudaSuccess
              ? UWCV_OK : UWCV_E_LAUNCH;
 }
 

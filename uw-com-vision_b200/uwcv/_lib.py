@@ -44,6 +44,12 @@ def lib() -> C.CDLL:
     L.uwcv_paste_measure_range.argtypes = L.uwcv_paste_measure_stages.argtypes + [i64, i64]
     L.uwcv_paste_measure_heads.restype = C.c_int
     L.uwcv_paste_measure_heads.argtypes = [vp, i32, i32, i32] + L.uwcv_paste_measure_range.argtypes[1:]
+    L.uwcv_mask_column_totals.restype = C.c_int
+    L.uwcv_mask_column_totals.argtypes = [vp, sz, i64, i32, vp, vp, vp]
+    L.uwcv_clean_masks.restype = C.c_int
+    L.uwcv_clean_masks.argtypes = [vp, sz, i64, i32, i32, vp, vp, vp, vp, vp, vp, vp]
+    L.uwcv_rle_write.restype = C.c_int
+    L.uwcv_rle_write.argtypes = [vp, sz, i64, i32, i32, vp, vp, vp]
     L.uwcv_unpack_planes.restype = C.c_int
     L.uwcv_unpack_planes.argtypes = [vp, i64, i32, i32, vp, vp]
     L.uwcv_union_workspace_bytes.restype = sz
@@ -62,7 +68,7 @@ def lib() -> C.CDLL:
 
 EXPORTS = ("uwcv_version", "uwcv_strerror", "uwcv_plane_row_words", "uwcv_workspace_bytes",
            "uwcv_paste_measure", "uwcv_paste_measure_stages", "uwcv_paste_measure_range", "uwcv_paste_measure_heads",
-           "uwcv_unpack_planes",
+           "uwcv_unpack_planes", "uwcv_mask_column_totals", "uwcv_clean_masks", "uwcv_rle_write",
            "uwcv_union_workspace_bytes", "uwcv_union_measure", "uwcv_nms_workspace_bytes",
            "uwcv_nms_filter")
 

@@ -9,7 +9,7 @@ PKG_DIR = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_DIR = os.path.join(PKG_DIR, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libuwcv.so")
-SOURCES = ["uwcv_capi.cu", "paste_measure.cu", "contour.cu", "union.cu", "nms.cu", "unpack.cu"]
+SOURCES = ["uwcv_capi.cu", "paste_measure.cu", "contour.cu", "union.cu", "nms.cu", "unpack.cu", "cleanup.cu"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
