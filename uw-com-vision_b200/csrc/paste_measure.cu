@@ -141,6 +141,11 @@ __device__ __forceinline__ void bulk_store_zero(void* gdst, uint32_t smem_src, u
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
                :: "l"(gdst), "r"(smem_src), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void bulk_store_zero_hint(void* gdst, uint32_t smem_src, uint32_t bytes,
+                                                     uint64_t policy) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;"
+               :: "l"(gdst), "r"(smem_src), "r"(bytes), "l"(policy) : "memory");
+}
 __device__ __forceinline__ void bulk_commit() {
   asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
@@ -174,7 +179,7 @@ __device__ __forceinline__ float sigmoid_as_torch(float a) {
 }
 
 template <bool kPlanes>
-__global__ void __launch_bounds__(kPasteThreads)
+__global__ void __launch_bounds__(kPasteThreads, 3)
 paste_measure_kernel(const float* __restrict__ masks, const float* __restrict__ boxes,
                      const int32_t* __restrict__ image_idx, const int32_t* __restrict__ inst_idx,
                      const int64_t* __restrict__ classes, int64_t n, int H, int W, float thr,
@@ -209,7 +214,12 @@ paste_measure_kernel(const float* __restrict__ masks, const float* __restrict__ 
   // ordering is needed and the fill runs at the speed of the TMA / HBM write path while the
   // other seven warps paste, pack and reduce.
   if (warp == kPasteWarps) {
-    if (kPlanes && lane == 0 && fill_mode == 0) {
+    if (kPlanes && lane == 0 && (fill_mode == 0 || fill_mode == 2)) {
+      // fill_mode 2: the zero rows are marked evict-first in L2, so that the stream of plane
+      // bytes does not push the tile workspace (read by the border trace) out of the cache
+      uint64_t policy = 0;
+      if (fill_mode == 2)
+        asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
       // planes are claimed one at a time from a device-wide counter: under a saturated write
       // path the SMs do not drain at the same rate, and a static split leaves the fast ones
       // idle at the end (tools/fill_bench2.cu: 6.3 TB/s static vs 7.6 TB/s dynamic)
@@ -225,7 +235,9 @@ paste_measure_kernel(const float* __restrict__ masks, const float* __restrict__ 
         for (int sgi = 0; sgi < 2; ++sgi)
           for (int64_t o = seg_lo[sgi]; o < seg_hi[sgi]; o += zero_bytes) {
             const int64_t rem = seg_hi[sgi] - o;
-            bulk_store_zero(base + o, zero_smem, (uint32_t)(rem < zero_bytes ? rem : zero_bytes));
+            const uint32_t nbytes = (uint32_t)(rem < zero_bytes ? rem : zero_bytes);
+            if (fill_mode == 2) bulk_store_zero_hint(base + o, zero_smem, nbytes, policy);
+            else bulk_store_zero(base + o, zero_smem, nbytes);
             if (rot_mul > 0) {                       // bounded number of bulk stores in flight
               bulk_commit();
               if (rot_mul == 1) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");

@@ -189,6 +189,11 @@ class Engine:
         self.h2d_stream = torch.cuda.Stream(device)
         self.small_stream = torch.cuda.Stream(device)
         self.d2h_stream = torch.cuda.Stream(device)
+        # the border trace of call i runs on its own stream so that its (latency-bound, mostly
+        # idle) tail overlaps the (HBM-bound) paste of call i + 1: two workspaces, used in turn
+        self.trace_stream = torch.cuda.Stream(device)
+        self._trace_done = [None, None]
+        self._parity = 0
         self._dev_bufs = {}
         self._slots = {}
         self._host_pool = []
@@ -240,6 +245,8 @@ class Engine:
         """Workspace `slot` (0: default; 1: a second buffer of the same capacity for callers
         that keep two calls in flight)."""
         if self._ws is None or n > self._cap_n or words > self._cap_words:
+            if self._ws is not None:
+                torch.cuda.synchronize(self.device)     # another stream may still trace on it
             cap_n = max(n, self._cap_n)
             cap_w = max(int(words * 1.25) + 1024, self._cap_words)
             nbytes = self.L.uwcv_workspace_bytes(cap_n, cap_w)
@@ -278,6 +285,10 @@ class Engine:
             n_tile_words = tile_words(boxes, H, W)
         ws = self._workspace(n, n_tile_words, ws_slot)
         status = self.status if status is None else status
+        if (stages & 1) and self._trace_done[ws_slot] is not None:
+            # the layout is about to hand this workspace out again: after the trace that reads it
+            torch.cuda.current_stream(dev).wait_event(self._trace_done[ws_slot])
+            self._trace_done[ws_slot] = None
         with torch.cuda.device(dev):
             rc = self.L.uwcv_paste_measure_heads(
                 _ptr(masks), int(mask_channels), int(channel_offset), int(bool(logits)), _ptr(boxes), _ptr(image_idx), _ptr(inst_idx), _ptr(classes),
@@ -289,6 +300,36 @@ class Engine:
         if n > 0:        # layout = 3 kernels, paste = 1, contour = 1
             self.launches += 3 * (stages & 1) + ((stages >> 1) & 1) + ((stages >> 2) & 1)
         return rows_i, rows_f, status
+
+    def run_overlapped(self, masks, boxes, H, W, *, paste_ranges=None, after=None, **kw):
+        """Layout + paste on the current stream, border trace on ``trace_stream``, alternating
+        between the two workspaces.  ``paste_ranges``: [(first, count, event or None), ...] --
+        the paste of a range waits for its event (chunks of a host->device copy in flight).
+        ``after``: callable run on the trace stream behind the trace (collectives, D2H hand-off).
+        Returns the event that marks the rows complete."""
+        dev = self.device
+        main = torch.cuda.current_stream(dev)
+        p = self._parity
+        self._parity ^= 1
+        n = int(boxes.shape[0])
+        kw = dict(kw, ws_slot=p)
+        self.run(masks, boxes, H, W, stages=1, **kw)
+        for first, count, ev in (paste_ranges or [(0, n, None)]):
+            if ev is not None:
+                main.wait_event(ev)
+            if count > 0:
+                self.run(masks, boxes, H, W, stages=2, first=first, count=count, **kw)
+        pasted = torch.cuda.Event()
+        pasted.record(main)
+        with torch.cuda.stream(self.trace_stream):
+            self.trace_stream.wait_event(pasted)
+            self.run(masks, boxes, H, W, stages=4, **kw)
+            if after is not None:
+                after()
+            done = torch.cuda.Event()
+            done.record(self.trace_stream)
+        self._trace_done[p] = done
+        return done
 
     def check_status(self) -> None:
         """Synchronising read of the device status word; raises on workspace overflow."""
@@ -781,35 +822,40 @@ def submit_measure_instances(instances, output_size=None, classes_of_interest=No
         # as the mask probabilities arrive; one border-trace launch over all instances (its
         # duration is set by the longest serial chain, not by the instance count)
         main.wait_event(ev_small)
+        r = n
+        out = {}
+
+        def gather_rows():
+            from .dist import all_gather_table
+            out["i"], out["f"] = all_gather_table(rows_i, rows_f, counts=gather_counts)
+
         if n > 0:
-            eng.run(d_masks, d_boxes, H, W, stages=1, **common)
-            for c, (i0, i1, lo, hi) in enumerate(bounds):
-                main.wait_event(ev_in[c])
-                if hi > lo:
-                    eng.run(d_masks, d_boxes, H, W, stages=2, first=lo, count=hi - lo, **common)
-            eng.run(d_masks, d_boxes, H, W, stages=4, **common)
+            rows_done = eng.run_overlapped(
+                d_masks, d_boxes, H, W,
+                paste_ranges=[(lo, hi - lo, ev_in[c]) for c, (i0, i1, lo, hi) in enumerate(bounds)],
+                after=gather_rows if gathered else None, **common)
         else:
             status.zero_()
-        if gathered:
-            from .dist import all_gather_table
-            out_i, out_f = all_gather_table(rows_i, rows_f, counts=gather_counts)
-        else:
-            out_i, out_f = rows_i, rows_f
+            with torch.cuda.stream(eng.trace_stream):
+                eng.trace_stream.wait_stream(main)
+                if gathered:
+                    gather_rows()
+                rows_done = torch.cuda.Event()
+                rows_done.record(eng.trace_stream)
+        out_i, out_f = (out["i"], out["f"]) if gathered else (rows_i, rows_f)
         r = int(out_i.shape[0])
         # the rows land in pinned memory that the returned table owns (no host copy); the
         # engine recycles the buffer when the table is gone
         hp_i, hp_f, pend.np_i, pend.np_f = eng.host_rows(r)
         hp_s = slot.pinned("status", (4,), torch.int64)
-        ev = torch.cuda.Event()
-        ev.record(main)
         with torch.cuda.stream(eng.d2h_stream):
-            eng.d2h_stream.wait_event(ev)
+            eng.d2h_stream.wait_event(rows_done)
             hp_i.copy_(out_i, **nb)
             hp_f.copy_(out_f, **nb)
             hp_s.copy_(status, **nb)
             done = torch.cuda.Event()
             done.record(eng.d2h_stream)
-        if gathered:                  # the gathered tensors belong to the main stream's pool
+        if gathered:                  # the gathered tensors belong to the trace stream's pool
             out_i.record_stream(eng.d2h_stream)
             out_f.record_stream(eng.d2h_stream)
         # rows / status / inputs are per slot and a slot is only reused after its call has
