@@ -210,6 +210,9 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # keep stdout to the one JSON line
+        # the all-gather of step i is issued behind the trace of step i while the paste of step
+        # i + 1 already holds the SMs: its kernel must be placed first when CTAs retire
+        os.environ.setdefault("TORCH_NCCL_HIGH_PRIORITY", "1")
         dist.init_process_group("nccl", device_id=dev)
 
     n_img, n_inst = args.images, args.instances
