@@ -636,3 +636,21 @@ def test_rle_full_size_round_trip():
         for a, l in s:
             cover[a - 1:a - 1 + l] += 1
     assert cover.max() <= 1
+
+
+def test_tile_major_shards_gather_into_the_whole_image_table():
+    """configs[3] partition of one micrograph: measuring the tile-major shards (as 4 ranks would)
+    and sorting the concatenated rows gives the table of the unsharded call."""
+    H = W = 1024
+    inst = synth.blob_instances(0, 600, H, W, seed=42)
+    whole = uwcv.measure_instances(inst, (H, W))
+    parts = []
+    boxes = api.scale_clip_boxes(inst.pred_boxes.tensor, inst.image_size, (H, W))[0]
+    for r in range(4):
+        idx = uwcv.shard_instances_by_tile(boxes, (H, W), r, 4)
+        parts.append(uwcv.measure_instances(uwcv.take_instances(inst, idx), (H, W)))
+    assert sum(len(p) for p in parts) == len(whole) and min(len(p) for p in parts) > 0
+    cat = uwcv.MeasurementTable.concat(parts)
+    gi, gf = uwcv.sort_rows(torch.from_numpy(cat.ints), torch.from_numpy(cat.floats))
+    assert np.array_equal(gi.numpy(), whole.ints)
+    assert np.array_equal(gf.numpy(), whole.floats, equal_nan=True)

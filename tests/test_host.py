@@ -191,3 +191,29 @@ def test_all_gather_table_gloo_world2():
         assert np.array_equal(gi[:, :2], expect)
         assert np.array_equal(gf[:, 0], expect[:, 0] + 0.25)
     assert udist.shard_indices(5, 0, 2) == [0, 2, 4] and udist.shard_indices(5, 1, 2) == [1, 3]
+
+
+def test_tile_major_sharding_partitions_the_instances():
+    """configs[3]-style partition of one micrograph: every instance lands on exactly one rank,
+    whichever grid is used, and neighbours in space land together."""
+    g = torch.Generator().manual_seed(4)
+    H = W = 4096
+    c = torch.rand((5000, 2), generator=g) * torch.tensor([W, H])
+    wh = torch.rand((5000, 2), generator=g) * 40 + 8
+    boxes = torch.cat((c - wh / 2, c + wh / 2), dim=1)
+    boxes[0] = torch.tensor([-30.0, -30.0, 10.0, 10.0])             # centre outside the image: clamped
+    boxes[1] = torch.tensor([W - 5.0, H - 5.0, W + 50.0, H + 50.0])
+    for world, grid in ((1, None), (2, None), (4, None), (8, None), (8, (4, 4)), (3, None)):
+        shards = [udist.shard_instances_by_tile(boxes, (H, W), r, world, grid) for r in range(world)]
+        allidx = torch.cat(shards)
+        assert allidx.numel() == 5000 and torch.equal(torch.sort(allidx)[0], torch.arange(5000))
+        for s_ in shards:
+            assert torch.equal(s_, torch.sort(s_)[0])
+    s4 = [udist.shard_instances_by_tile(boxes, (H, W), r, 4) for r in range(4)]      # 2 x 2 grid
+    own = torch.empty(5000, dtype=torch.long)
+    for r, s_ in enumerate(s4):
+        own[s_] = r
+    cx, cy = (boxes[:, 0] + boxes[:, 2]) / 2, (boxes[:, 1] + boxes[:, 3]) / 2
+    inside = (cx > 0) & (cx < W) & (cy > 0) & (cy < H)
+    want = (cy >= H / 2).long() * 2 + (cx >= W / 2).long()
+    assert torch.equal(own[inside], want[inside])

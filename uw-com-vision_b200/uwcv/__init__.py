@@ -13,7 +13,8 @@ from .api import (Engine, MeasurementTable, MeasurementStream, PendingTable,
                   scale_clip_boxes, tile_words)
 from .grouping import (group_by_class, write_classes_csv, moving_average, report_class,  # noqa: F401
                        write_results_csv)
-from .dist import shard_indices, all_gather_table             # noqa: F401
+from .dist import (shard_indices, shard_instances_by_tile, take_instances,   # noqa: F401
+                   all_gather_table, sort_rows)
 from .union import UnionTable, measure_union                  # noqa: F401
 from .heads import SingleForward, fast_rcnn_inference         # noqa: F401
 from .cleanup import RleExport, export_rle, write_rle_csv     # noqa: F401
@@ -23,5 +24,5 @@ __all__ = [
     "submit_measure_instances", "measure_instances",
     "paste_masks_in_image", "detector_postprocess", "fast_rcnn_inference_single_image",
     "get_counts", "group_by_class", "write_classes_csv", "moving_average", "report_class",
-    "write_results_csv", "shard_indices", "all_gather_table", "UnionTable", "measure_union", "SingleForward", "fast_rcnn_inference", "RleExport", "export_rle", "write_rle_csv",
+    "write_results_csv", "shard_indices", "shard_instances_by_tile", "take_instances", "all_gather_table", "sort_rows", "UnionTable", "measure_union", "SingleForward", "fast_rcnn_inference", "RleExport", "export_rle", "write_rle_csv",
 ]

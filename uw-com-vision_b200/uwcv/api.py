@@ -494,6 +494,10 @@ def fast_rcnn_inference_single_image(boxes: torch.Tensor, scores: torch.Tensor,
 # measurement entry (GetMask_Contours / GetCounts replacement)
 # ----------------------------------------------------------------------------------
 
+def _has(inst, name: str) -> bool:
+    return inst.has(name) if hasattr(inst, "has") else name in inst._fields
+
+
 def _mask_field(inst):
     """(tensor [N, C, 28, 28], is_logits): ``pred_masks`` (N x 1 x 28 x 28 probabilities, the
     output of mask_rcnn_inference) or, on the single-forward path, ``pred_mask_logits``
@@ -635,6 +639,10 @@ def measure_instances(instances: Union[object, Sequence[object]],
     ``pred_mask_logits`` (N x K x 28 x 28, the mask head's raw output); the kernel reads channel
     ``pred_classes[i] + mask_channel_offset`` and applies the sigmoid itself, which is what
     detectron2's ``mask_rcnn_inference`` does before ``detector_postprocess``.
+
+    An optional int field ``orig_idx`` (as ``uwcv.take_instances`` attaches) is reported as the
+    ``inst_idx`` column instead of the position inside the call, so that the shards of one
+    image (``shard_instances_by_tile``) gather into the table of the whole image.
     """
     return submit_measure_instances(
         instances, output_size, classes_of_interest, mask_threshold=mask_threshold,
@@ -731,8 +739,11 @@ def submit_measure_instances(instances, output_size=None, classes_of_interest=No
             il = [torch.repeat_interleave(
                 torch.arange(len(batch), dtype=torch.int32) + image_idx_offset, lt)]
             offs = torch.cumsum(lt, 0) - lt
-            jl = [(torch.arange(int(lt.sum()), dtype=torch.int64)
-                   - torch.repeat_interleave(offs, lt)).to(torch.int32)]
+            if all(_has(i, "orig_idx") for i in batch):          # shards keep their global numbering
+                jl = [torch.cat([i.orig_idx.to(torch.int32).cpu() for i in batch])]
+            else:
+                jl = [(torch.arange(int(lt.sum()), dtype=torch.int64)
+                       - torch.repeat_interleave(offs, lt)).to(torch.int32)]
             counts_fast = lens
         else:
             early = None
@@ -750,7 +761,16 @@ def submit_measure_instances(instances, output_size=None, classes_of_interest=No
         cl.append(classes.to(torch.int64))
         ml.append(masks.to(torch.float32).reshape(-1, mrow))
         il.append(torch.full((nk,), image_idx_offset + k, dtype=torch.int32))
-        jl.append(torch.arange(nk, dtype=torch.int32))
+        if _has(inst, "orig_idx"):
+            oi = inst.orig_idx.to(torch.int32).cpu()
+            if classes_of_interest is not None:
+                sel = torch.zeros(len(oi), dtype=torch.bool)
+                for c in classes_of_interest:
+                    sel |= inst.pred_classes.cpu() == int(c)
+                oi = oi[sel]
+            jl.append(oi[keep.cpu()] if nk != keep.numel() else oi)
+        else:
+            jl.append(torch.arange(nk, dtype=torch.int32))
     boxes = torch.cat(bl)
     n = int(boxes.shape[0])
     gathered = gather and dist_is_multi()

@@ -19,6 +19,49 @@ def shard_indices(n_items: int, rank: int, world: int) -> List[int]:
     return list(range(rank, n_items, world))
 
 
+def shard_instances_by_tile(boxes: torch.Tensor, image_size: Tuple[int, int], rank: int, world: int,
+                            grid: Tuple[int, int] = None) -> torch.Tensor:
+    """Tile-major partition of ONE huge micrograph (BASELINE configs[3]): the
+    image is cut into a ``grid`` of gy x gx tiles (default: the most square factorisation of
+    ``world``), tile t belongs to rank ``t % world`` and an instance belongs to the tile holding
+    its box centre.  No halo is needed: an instance's mask is confined to its own box, so the rank
+    that owns the centre measures the whole instance.  Returns the indices (int64, ascending) of
+    the instances of ``rank``; the shards of all ranks are a partition of ``range(N)``.
+    ``boxes``: N x 4 XYXY in ``image_size`` = (H, W) coordinates."""
+    H, W = int(image_size[0]), int(image_size[1])
+    if grid is None:
+        gy = int(world ** 0.5)
+        while world % gy:
+            gy -= 1
+        grid = (gy, world // gy)
+    gy, gx = int(grid[0]), int(grid[1])
+    b = boxes.detach().to(torch.float64)
+    cx = ((b[:, 0] + b[:, 2]) * 0.5).clamp(0, W - 1e-9)
+    cy = ((b[:, 1] + b[:, 3]) * 0.5).clamp(0, H - 1e-9)
+    tx = torch.floor(cx * gx / W).long().clamp(0, gx - 1)
+    ty = torch.floor(cy * gy / H).long().clamp(0, gy - 1)
+    owner = (ty * gx + tx) % world
+    return torch.nonzero(owner == rank, as_tuple=False).flatten()
+
+
+def take_instances(inst, idx: torch.Tensor):
+    """The sub-``Instances`` at ``idx`` with a field ``orig_idx`` holding the original positions
+    (reported by ``measure_instances`` as the ``inst_idx`` column)."""
+    from .structures import Boxes, Instances
+    out = Instances(tuple(inst.image_size))
+    fields = inst.get_fields() if hasattr(inst, "get_fields") else inst._fields
+    for k, v in fields.items():
+        if k == "orig_idx":
+            continue
+        if hasattr(v, "tensor"):
+            out.set(k, Boxes(v.tensor[idx.to(v.tensor.device)]))
+        else:
+            out.set(k, v[idx.to(v.device)])
+    base = fields["orig_idx"] if "orig_idx" in fields else torch.arange(len(inst))
+    out.set("orig_idx", base[idx.to(base.device)].to(torch.int32))
+    return out
+
+
 def all_gather_table(rows_i: torch.Tensor, rows_f: torch.Tensor, group=None, counts=None
                      ) -> Tuple[torch.Tensor, torch.Tensor]:
     """rows_i [r, Ci] int64, rows_f [r, Cf] float64 on this rank's device -> the
