@@ -431,7 +431,10 @@ def run_ours(args):
                          "kernel": "paste_measure_kernel<true>",
                          "bytes_per_instance": bpi, "instances_per_launch": n,
                          "frac_of_nominal_8000": achieved / 8000.0,
-                         "memset_same_buffer_gbs": memset_gbs},
+                         # a plain zero fill of the same plane buffer (torch's one-shot
+                         # elementwise kernel): the ceiling of a write-only stream on this GPU
+                         "memset_same_buffer_gbs": memset_gbs,
+                         "frac_of_zero_fill": achieved / memset_gbs},
             "clocks": clocks,
         }
         if cpu is not None:
