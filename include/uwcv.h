@@ -142,6 +142,37 @@ int uwcv_paste_measure_heads(const float* masks, int mask_channels, int channel_
                              int64_t first, int64_t count);
 
 /*
+ * uwcv_paste_measure_gather -- as uwcv_paste_measure_heads, with the all-gather of the
+ * measurement table fused into the border-trace kernel (the one collective of
+ * the path).  Every rank passes the tables of ALL ranks -- device pointers that are valid on
+ * this GPU: peer-mapped / symmetric memory over NVLink, this rank's own table included -- and
+ * its row offset; the trace kernel stores its finished rows (coalesced 16-byte stores, one
+ * contiguous block per warp) into rows [row_base, row_base + N) of every table.  The tables are
+ * complete on every rank once all ranks have passed a barrier issued on `stream` after this
+ * call (the caller's: e.g. a symmetric-memory signal barrier); no NCCL kernel is involved.
+ * gather == NULL or gather->world == 0: no gather.  Stage 4 must cover the whole call.
+ *
+ * Stands in for the dist all-gather the image-sharded job ends with (there is none in the
+ * single-process reference; nn_inference.py:485-498 loops over all images in one process).
+ */
+#define UWCV_MAX_PEERS 16
+typedef struct uwcv_gather {
+  int32_t world;                       /* number of ranks, <= UWCV_MAX_PEERS */
+  int32_t reserved;
+  int64_t row_base;                    /* first row of this rank in the gathered tables */
+  int64_t* rows_i[UWCV_MAX_PEERS];     /* [total_rows, UWCV_NUM_INT] of rank p   */
+  double* rows_f[UWCV_MAX_PEERS];      /* [total_rows, UWCV_NUM_FLOAT] of rank p */
+} uwcv_gather;
+
+int uwcv_paste_measure_gather(const float* masks, int mask_channels, int channel_offset,
+                              int is_logits, const float* boxes, const int32_t* image_idx,
+                              const int32_t* inst_idx, const int64_t* classes, const float* scores,
+                              int64_t N, int H, int W, float thr, double pixels_per_metric,
+                              uint32_t* bitplanes, int64_t* rows_i, double* rows_f, void* workspace,
+                              size_t ws_bytes, int64_t* status, void* stream, int stages,
+                              int64_t first, int64_t count, const uwcv_gather* gather);
+
+/*
  * uwcv_unpack_planes -- expand bit-planes into the Detectron2-literal N x H x W bool
  * tensor (one byte per pixel), for callers that read pred_masks as such
  * (nn_inference.py:326, :376).

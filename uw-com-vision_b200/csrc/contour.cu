@@ -29,13 +29,14 @@
 namespace uwcv {
 
 constexpr int kContourThreads = 64;
+static_assert((kNumInt * 8) % 16 == 0 && (kNumFloat * 8) % 16 == 0, "rows are copied as 16-byte words");
 static_assert(F_CHORDS - F_CAREA == 15, "describe_contour writes 16 contiguous float columns");
 
 __global__ void __launch_bounds__(kContourThreads)
 contour_measure_kernel(int64_t first, int64_t n, int lanes, const float* __restrict__ scores,
                        double pixels_per_metric, int64_t* __restrict__ rows_i,
                        double* __restrict__ rows_f, Workspace ws,
-                       const int64_t* __restrict__ status) {
+                       const int64_t* __restrict__ status, GatherDst g) {
   if (status[0] != 0) return;                            // uniform over the grid
   // `lanes` instances per warp: the kernel is bound by the latency of each lane's serial
   // chain, not by issue slots, so small batches are spread over more warps
@@ -187,11 +188,34 @@ contour_measure_kernel(int64_t first, int64_t n, int lanes, const float* __restr
   // ---- hull, min-area rectangle and descriptor block of the best contour ----------------
   describe_contour(have, best, best + d.th, best_y, best_ymax, d.wx0 * 32, d.y0, best_a2,
                    best_perim, pixels_per_metric, rf + F_CAREA);
+
+  // ---- fused all-gather: publish this warp's rows into every rank's table ------------------
+  // The `lanes` instances of a warp are consecutive, so its rows are one contiguous block of
+  // each table (160 B and 240 B per row): the warp copies them with coalesced 16-byte stores
+  // into the same rows (shifted by this rank's offset) of every peer, over NVLink for the
+  // remote ones.  The tables become consistent at the caller's barrier after this kernel.
+  if (g.world > 0) {
+    __syncwarp();
+    const int64_t w0 = first + warp * lanes;
+    if (w0 < n) {
+      const int cnt = (int)((n - w0) < (int64_t)lanes ? (n - w0) : (int64_t)lanes);
+      const uint4* si = reinterpret_cast<const uint4*>(rows_i + w0 * kNumInt);
+      const uint4* sf = reinterpret_cast<const uint4*>(rows_f + w0 * kNumFloat);
+      const int ni = cnt * (kNumInt * 8 / 16), nf = cnt * (kNumFloat * 8 / 16);
+      for (int p = 0; p < g.world; ++p) {
+        uint4* di = reinterpret_cast<uint4*>(g.rows_i[p] + (g.row_base + w0) * kNumInt);
+        uint4* df = reinterpret_cast<uint4*>(g.rows_f[p] + (g.row_base + w0) * kNumFloat);
+        for (int k = lane; k < ni; k += 32) di[k] = si[k];
+        for (int k = lane; k < nf; k += 32) df[k] = sf[k];
+      }
+    }
+  }
 }
 
 cudaError_t launch_contour_measure(int64_t first, int64_t count, const float* scores, double ppm,
                                    int64_t* rows_i, double* rows_f, const Workspace& ws,
-                                   const int64_t* status, int num_sms, cudaStream_t stream) {
+                                   const int64_t* status, int num_sms, cudaStream_t stream,
+                                   const GatherDst& gather) {
   if (count == 0) return cudaSuccess;
   const int64_t n = count;                               // sizing below is per launched range
   int per_sm = 0;
@@ -205,7 +229,8 @@ cudaError_t launch_contour_measure(int64_t first, int64_t count, const float* sc
   const int64_t warps = (n + lanes - 1) / lanes;
   const unsigned grid = (unsigned)((warps * 32 + kContourThreads - 1) / kContourThreads);
   contour_measure_kernel<<<grid, kContourThreads, 0, stream>>>(first, first + count, lanes, scores,
-                                                               ppm, rows_i, rows_f, ws, status);
+                                                               ppm, rows_i, rows_f, ws, status,
+                                                               gather);
   return cudaPeekAtLastError();
 }
 

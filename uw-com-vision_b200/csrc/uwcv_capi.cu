@@ -10,7 +10,8 @@ cudaError_t launch_paste_measure(const float*, const float*, const int32_t*, con
                                  int64_t*, const Workspace&, const int64_t*, int, cudaStream_t,
                                  const MaskSource&);
 cudaError_t launch_contour_measure(int64_t, int64_t, const float*, double, int64_t*, double*,
-                                   const Workspace&, const int64_t*, int, cudaStream_t);
+                                   const Workspace&, const int64_t*, int, cudaStream_t,
+                                   const GatherDst&);
 cudaError_t launch_unpack(const uint32_t*, int64_t, int, int, uint8_t*, int, cudaStream_t);
 size_t nms_workspace_bytes_host(const int64_t*, int, int);
 size_t union_workspace_bytes_host(int64_t, int64_t);
@@ -85,14 +86,29 @@ int uwcv_paste_measure_stages(const float* masks, const float* boxes, const int3
                                   ws_bytes, status, stream, stages, 0, N);
 }
 
-int uwcv_paste_measure_heads(const float* masks, int mask_channels, int channel_offset,
+int uwcv_paste_measure_gather(const float* masks, int mask_channels, int channel_offset,
                              int is_logits, const float* boxes, const int32_t* image_idx,
                              const int32_t* inst_idx, const int64_t* classes, const float* scores,
                              int64_t N, int H, int W, float thr, double pixels_per_metric,
                              uint32_t* bitplanes, int64_t* rows_i, double* rows_f, void* workspace,
                              size_t ws_bytes, int64_t* status, void* stream, int stages,
-                             int64_t first, int64_t count) {
+                             int64_t first, int64_t count, const uwcv_gather* gather) {
   if (N < 0 || H <= 0 || W <= 0) return UWCV_E_SHAPE;
+  uwcv::GatherDst gd;
+  gd.world = 0;
+  gd.row_base = 0;
+  if (gather && gather->world > 0) {
+    if (gather->world > UWCV_MAX_PEERS || gather->row_base < 0) return UWCV_E_SHAPE;
+    if ((stages & 4) && (first != 0 || count != N)) return UWCV_E_SHAPE;   // whole-call traces only
+    gd.world = gather->world;
+    gd.row_base = gather->row_base;
+    for (int p = 0; p < gather->world; ++p) {
+      if (!gather->rows_i[p] || !gather->rows_f[p]) return UWCV_E_NULL;
+      if (misaligned(gather->rows_i[p]) || misaligned(gather->rows_f[p])) return UWCV_E_ALIGN;
+      gd.rows_i[p] = gather->rows_i[p];
+      gd.rows_f[p] = gather->rows_f[p];
+    }
+  }
   if (mask_channels < 1 || mask_channels > 65536) return UWCV_E_SHAPE;
   if (mask_channels > 1 && N > 0 && !classes) return UWCV_E_NULL;
   if (H > 32768 || W > 32768) return UWCV_E_TOO_LARGE;
@@ -123,9 +139,22 @@ int uwcv_paste_measure_heads(const float* masks, int mask_channels, int channel_
                                  thr, bitplanes, rows_i, ws, status, num_sms(), st, src) != cudaSuccess)
     return UWCV_E_LAUNCH;
   if ((stages & 4) && uwcv::launch_contour_measure(first, count, scores, pixels_per_metric, rows_i,
-                                                   rows_f, ws, status, num_sms(), st) != cudaSuccess)
+                                                   rows_f, ws, status, num_sms(), st, gd) != cudaSuccess)
     return UWCV_E_LAUNCH;
   return UWCV_OK;
+}
+
+int uwcv_paste_measure_heads(const float* masks, int mask_channels, int channel_offset,
+                             int is_logits, const float* boxes, const int32_t* image_idx,
+                             const int32_t* inst_idx, const int64_t* classes, const float* scores,
+                             int64_t N, int H, int W, float thr, double pixels_per_metric,
+                             uint32_t* bitplanes, int64_t* rows_i, double* rows_f, void* workspace,
+                             size_t ws_bytes, int64_t* status, void* stream, int stages,
+                             int64_t first, int64_t count) {
+  return uwcv_paste_measure_gather(masks, mask_channels, channel_offset, is_logits, boxes, image_idx,
+                                   inst_idx, classes, scores, N, H, W, thr, pixels_per_metric,
+                                   bitplanes, rows_i, rows_f, workspace, ws_bytes, status, stream,
+                                   stages, first, count, nullptr);
 }
 
 int uwcv_paste_measure_range(const float* masks, const float* boxes, const int32_t* image_idx,

@@ -52,6 +52,16 @@ struct MaskSource {
   int logits;            // 1: apply the sigmoid of mask_rcnn_inference while staging
 };
 
+// Fused all-gather of the measurement rows: every rank's trace kernel stores its finished rows
+// into the tables of ALL ranks (peer memory over NVLink), at its own row offset.
+constexpr int kMaxPeers = 16;
+struct GatherDst {
+  int world;                       // 0: no gather
+  int64_t row_base;                // first row of this rank in the gathered tables
+  int64_t* rows_i[kMaxPeers];      // [total_rows, kNumInt]   per peer (this rank included)
+  double* rows_f[kMaxPeers];       // [total_rows, kNumFloat] per peer
+};
+
 // Workspace carve-up, computed identically on host and device.
 constexpr int kLayoutThreads = 1024;   // instances per layout CTA
 

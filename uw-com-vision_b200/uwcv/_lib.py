@@ -9,6 +9,14 @@ from .build import LIB_PATH
 
 _lib = None
 
+MAX_PEERS = 16
+
+
+class Gather(C.Structure):
+    """uwcv_gather of include/uwcv.h."""
+    _fields_ = [("world", C.c_int32), ("reserved", C.c_int32), ("row_base", C.c_int64),
+                ("rows_i", C.c_void_p * MAX_PEERS), ("rows_f", C.c_void_p * MAX_PEERS)]
+
 E_CAPACITY = -7
 
 
@@ -44,6 +52,8 @@ def lib() -> C.CDLL:
     L.uwcv_paste_measure_range.argtypes = L.uwcv_paste_measure_stages.argtypes + [i64, i64]
     L.uwcv_paste_measure_heads.restype = C.c_int
     L.uwcv_paste_measure_heads.argtypes = [vp, i32, i32, i32] + L.uwcv_paste_measure_range.argtypes[1:]
+    L.uwcv_paste_measure_gather.restype = C.c_int
+    L.uwcv_paste_measure_gather.argtypes = L.uwcv_paste_measure_heads.argtypes + [C.POINTER(Gather)]
     L.uwcv_mask_column_totals.restype = C.c_int
     L.uwcv_mask_column_totals.argtypes = [vp, sz, i64, i32, vp, vp, vp]
     L.uwcv_clean_masks.restype = C.c_int
@@ -67,7 +77,7 @@ def lib() -> C.CDLL:
 
 
 EXPORTS = ("uwcv_version", "uwcv_strerror", "uwcv_plane_row_words", "uwcv_workspace_bytes",
-           "uwcv_paste_measure", "uwcv_paste_measure_stages", "uwcv_paste_measure_range", "uwcv_paste_measure_heads",
+           "uwcv_paste_measure", "uwcv_paste_measure_stages", "uwcv_paste_measure_range", "uwcv_paste_measure_heads", "uwcv_paste_measure_gather",
            "uwcv_unpack_planes", "uwcv_mask_column_totals", "uwcv_clean_masks", "uwcv_rle_write",
            "uwcv_union_workspace_bytes", "uwcv_union_measure", "uwcv_nms_workspace_bytes",
            "uwcv_nms_filter")

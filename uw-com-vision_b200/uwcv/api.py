@@ -197,6 +197,7 @@ class Engine:
         self._dev_bufs = {}
         self._slots = {}
         self._host_pool = []
+        self._fused = None
 
     def host_rows(self, r: int):
         """Pinned host memory for one call's rows, recycled once the table that was handed out
@@ -223,6 +224,34 @@ class Engine:
         n_i = arr[:a].reshape(r, NUM_INT)
         n_f = arr[a:b].view(np.float64).reshape(r, NUM_FLOAT)
         return t_i, t_f, n_i, n_f
+
+    def fused_gather(self):
+        """The symmetric-memory gather context of this device (created on first use, a
+        collective), or None when torch.distributed is not a multi-rank NCCL job or symmetric
+        memory cannot be set up (the caller then uses the NCCL all_gather_table)."""
+        if self._fused is None:
+            self._fused = False
+            import os
+            import torch.distributed as dist
+            if not os.environ.get("UWCV_NO_FUSED_GATHER") and dist.is_available() and \
+                    dist.is_initialized() and dist.get_world_size() > 1 and \
+                    dist.get_backend() == "nccl":
+                ok = 1
+                try:
+                    from .dist import FusedGather
+                    fg = FusedGather(self.device)
+                    fg.ensure(1024)
+                except Exception as e:                      # noqa: BLE001
+                    import warnings
+                    warnings.warn(f"uwcv: fused gather unavailable ({type(e).__name__}: {e}); "
+                                  "using the NCCL all-gather")
+                    ok = 0
+                # all ranks take the same path
+                t = torch.tensor([ok], dtype=torch.int32, device=self.device)
+                dist.all_reduce(t, op=dist.ReduceOp.MIN)
+                if int(t.item()) == 1:
+                    self._fused = fg
+        return self._fused or None
 
     def slot(self, k: int = 0) -> "_Slot":
         s = self._slots.get(k)
@@ -268,7 +297,7 @@ class Engine:
             rows_i: Optional[torch.Tensor] = None, rows_f: Optional[torch.Tensor] = None,
             stages: int = 7, status: Optional[torch.Tensor] = None, ws_slot: int = 0,
             first: int = 0, count: Optional[int] = None, mask_channels: int = 1,
-            channel_offset: int = 0, logits: bool = False):
+            channel_offset: int = 0, logits: bool = False, gather=None):
         """All tensors on ``self.device``, contiguous: masks [N,28,28] f32, boxes [N,4] f32
         (output space), image_idx/inst_idx int32, classes int64, scores f32,
         planes None or uint32/int32 [N, H, plane_row_words(W)].  Single-forward form: masks
@@ -290,12 +319,13 @@ class Engine:
             torch.cuda.current_stream(dev).wait_event(self._trace_done[ws_slot])
             self._trace_done[ws_slot] = None
         with torch.cuda.device(dev):
-            rc = self.L.uwcv_paste_measure_heads(
+            rc = self.L.uwcv_paste_measure_gather(
                 _ptr(masks), int(mask_channels), int(channel_offset), int(bool(logits)), _ptr(boxes), _ptr(image_idx), _ptr(inst_idx), _ptr(classes),
                 _ptr(scores), n, int(H), int(W), float(threshold), float(pixels_per_metric),
                 _ptr(planes), _ptr(rows_i), _ptr(rows_f), _ptr(ws), ws.numel(),
                 _ptr(status), _stream_ptr(dev), int(stages), int(first),
-                int(n - first if count is None else count))
+                int(n - first if count is None else count),
+                C.byref(gather) if (gather is not None and (stages & 4)) else None)
         _lib.check(rc, "uwcv_paste_measure")
         if n > 0:        # layout = 3 kernels, paste = 1, contour = 1
             self.launches += 3 * (stages & 1) + ((stages >> 1) & 1) + ((stages >> 2) & 1)
@@ -779,7 +809,8 @@ def submit_measure_instances(instances, output_size=None, classes_of_interest=No
     # Workspace sizing: the exact tile-word count is only computed for the first call (or
     # after an overflow); afterwards the cached capacity is reused and the device status
     # word reports an overflow, in which case the call is repeated with the exact size.
-    need_exact = _exact_words or eng._ws is None
+    # (a gathered call must not be repeated on one rank only: always size exactly)
+    need_exact = _exact_words or eng._ws is None or gathered
     n_words = tile_words(boxes, H, W) if need_exact else eng._cap_words
     counts = counts_fast if counts_fast is not None else [int(b.shape[0]) for b in bl]
     main = torch.cuda.current_stream(dev)
@@ -849,19 +880,41 @@ def submit_measure_instances(instances, output_size=None, classes_of_interest=No
             from .dist import all_gather_table
             out["i"], out["f"] = all_gather_table(rows_i, rows_f, counts=gather_counts)
 
+        fg = eng.fused_gather() if gathered else None
+        gstruct = gset = None
+        if fg is not None:
+            # fused all-gather: the trace kernel stores the rows into every rank's table
+            # (symmetric memory over NVLink), a signal barrier completes them -- no collective
+            # kernel has to find SMs next to the following call's paste
+            cts = gather_counts
+            if cts is None:
+                import torch.distributed as dist
+                c_l = torch.tensor([n], dtype=torch.int64, device=dev)
+                c_all = torch.empty(fg.world, dtype=torch.int64, device=dev)
+                dist.all_gather_into_tensor(c_all, c_l)
+                cts = c_all.cpu().tolist()
+            gstruct, gset, g_total = fg.begin(cts)
         if n > 0:
             rows_done = eng.run_overlapped(
                 d_masks, d_boxes, H, W,
                 paste_ranges=[(lo, hi - lo, ev_in[c]) for c, (i0, i1, lo, hi) in enumerate(bounds)],
+                gather=gstruct, after=(lambda: fg.barrier(gset)) if fg is not None else None,
                 **common)
         else:
             status.zero_()
-            rows_done = torch.cuda.Event()
-            rows_done.record(main)
-        if gathered:
-            # the collective stays on the main stream, behind the trace: an NCCL kernel issued
-            # from the trace stream would have to wait for SMs held by the next call's paste
-            # (measured: 8.2 vs 7.4 ms/step at 2 GPUs), so gathered calls run back to back
+            with torch.cuda.stream(eng.trace_stream):
+                eng.trace_stream.wait_stream(main)
+                if fg is not None:
+                    fg.barrier(gset)
+                rows_done = torch.cuda.Event()
+                rows_done.record(eng.trace_stream)
+        if fg is not None:
+            out["i"], out["f"] = fg.tables(gset, g_total)
+        elif gathered:
+            # NCCL fallback: the collective stays on the main stream, behind the trace: an NCCL
+            # kernel issued from the trace stream would have to wait for SMs held by the next
+            # call's paste (measured: 8.2 vs 7.5 ms/step at 2 GPUs), so gathered calls run back
+            # to back
             main.wait_event(rows_done)
             gather_rows()
             rows_done = torch.cuda.Event()
@@ -879,7 +932,9 @@ def submit_measure_instances(instances, output_size=None, classes_of_interest=No
             hp_s.copy_(status, **nb)
             done = torch.cuda.Event()
             done.record(eng.d2h_stream)
-        if gathered:                  # the gathered tensors belong to the main stream's pool
+        if fg is not None:
+            fg.read_done[gset] = done
+        elif gathered:                # the gathered tensors belong to the main stream's pool
             out_i.record_stream(eng.d2h_stream)
             out_f.record_stream(eng.d2h_stream)
         # rows / status / inputs are per slot and a slot is only reused after its call has

@@ -100,3 +100,90 @@ def sort_rows(rows_i: torch.Tensor, rows_f: torch.Tensor) -> Tuple[torch.Tensor,
     key = rows_i[:, 0] * (1 << 32) + rows_i[:, 1]
     order = torch.argsort(key, stable=True)
     return rows_i[order], rows_f[order]
+
+
+class FusedGather:
+    """All-gather of the measurement rows WITHOUT a collective kernel: the tables of all ranks
+    live in symmetric memory (``torch.distributed._symmetric_memory``: every rank maps every
+    peer's buffer over NVLink), the border-trace kernel of each rank stores its finished rows
+    into all of them (``uwcv_paste_measure_gather``), and a signal barrier on the same stream
+    makes them complete.  Two table sets are used in turn so that the device->host read of call
+    i never races the peers' stores of call i + 2.
+
+    Construction is a collective (rendezvous); it raises when symmetric memory is not available
+    for the group, and the caller then stays on ``all_gather_table`` (NCCL)."""
+
+    def __init__(self, device: torch.device, group=None):
+        import torch.distributed._symmetric_memory as symm
+        self._symm = symm
+        self.device = device
+        self.group = group if group is not None else dist.group.WORLD
+        self.world = dist.get_world_size(self.group)
+        self.rank = dist.get_rank(self.group)
+        from ._lib import MAX_PEERS
+        if self.world > MAX_PEERS:
+            raise RuntimeError(f"FusedGather supports up to {MAX_PEERS} ranks")
+        self.cap = 0
+        self.sets = []                 # [(buffer, handle)] x 2
+        self.read_done = [None, None]  # event: the last device->host read of the set finished
+        self.parity = 0
+
+    def _offsets(self, cap: int):
+        from .schema import NUM_INT
+        off_f = (cap * NUM_INT * 8 + 255) // 256 * 256
+        return off_f
+
+    def ensure(self, total_rows: int) -> None:
+        """(Collective when it grows.)  Capacity for ``total_rows`` rows in both table sets."""
+        from .schema import NUM_FLOAT
+        if total_rows <= self.cap:
+            return
+        torch.cuda.synchronize(self.device)
+        cap = max(int(total_rows * 1.1) + 64, 1024)
+        nbytes = self._offsets(cap) + cap * NUM_FLOAT * 8 + 256
+        self.sets = []
+        for _ in range(2):
+            buf = self._symm.empty(nbytes, dtype=torch.uint8, device=self.device)
+            hdl = self._symm.rendezvous(buf, self.group)
+            self.sets.append((buf, hdl))
+        self.cap = cap
+        self.read_done = [None, None]
+
+    def begin(self, counts):
+        """-> (ctypes uwcv_gather for this rank, set index, total rows)."""
+        import ctypes as C
+        from ._lib import Gather
+        from .schema import NUM_FLOAT, NUM_INT  # noqa: F401
+        counts = [int(c) for c in counts]
+        total = sum(counts)
+        self.ensure(total)
+        k = self.parity
+        self.parity ^= 1
+        buf, hdl = self.sets[k]
+        g = Gather()
+        g.world = self.world
+        g.row_base = sum(counts[:self.rank])
+        off_f = self._offsets(self.cap)
+        ptrs = list(hdl.buffer_ptrs)
+        for p in range(self.world):
+            g.rows_i[p] = int(ptrs[p])
+            g.rows_f[p] = int(ptrs[p]) + off_f
+        return g, k, total
+
+    def barrier(self, k: int) -> None:
+        """On the current stream, behind the trace kernel: all ranks' rows of set k have landed
+        everywhere when it completes.  The rank first makes sure its own read of the OTHER set
+        is over: passing this barrier is what lets the peers write that set again."""
+        cur = torch.cuda.current_stream(self.device)
+        other = self.read_done[k ^ 1]
+        if other is not None:
+            cur.wait_event(other)
+        self.sets[k][1].barrier(channel=0)
+
+    def tables(self, k: int, total: int):
+        from .schema import NUM_FLOAT, NUM_INT
+        buf = self.sets[k][0]
+        off_f = self._offsets(self.cap)
+        ti = buf[: self.cap * NUM_INT * 8].view(torch.int64).view(self.cap, NUM_INT)[:total]
+        tf = buf[off_f: off_f + self.cap * NUM_FLOAT * 8].view(torch.float64).view(self.cap, NUM_FLOAT)[:total]
+        return ti, tf
