@@ -386,9 +386,14 @@ def run_ours(args):
 
     # ---- e2e: the public call with pinned host inputs -----------------------------------
     h2d = sum(int(b.pred_masks.numel()) * 4 + len(b) * (16 + 4 + 8 + 4 + 4) for b in batch)
-    d2h = total_instances * (20 * 8 + 30 * 8) + 32     # gathered table at N > 1
+    d2h = total_instances * (20 * 8 + 30 * 8) + 32     # rank 0 at N > 1: the gathered table
     del planes
-    kw = dict(write_planes=True, gather=world > 1, gather_counts=counts)
+    # at N > 1 the whole job's table goes to the host of rank 0 (the other ranks read their own
+    # rows): every rank's device holds the gathered table either way
+    kw = dict(write_planes=True, gather=world > 1, gather_counts=counts,
+              gather_dst=0 if world > 1 else None)
+    if os.environ.get("UWCV_BENCH_E2E_NOGATHER"):            # probe: independent ranks
+        kw = dict(write_planes=True)
     for _ in range(2):
         uwcv.measure_instances(batch, (H, W), device=dev, **kw)
     # (a) one synchronous call per step (latency form)
@@ -412,7 +417,11 @@ def run_ours(args):
         got += len(table)
     barrier()
     e2e_s = time.perf_counter() - t0
-    assert got == args.steps * total_instances, (got, total_instances)
+    if not os.environ.get("UWCV_BENCH_E2E_NOGATHER"):
+        assert got == args.steps * (total_instances if rank == 0 else n), (got, total_instances, n)
+    if os.environ.get("UWCV_BENCH_VERBOSE"):
+        print(f"rank {rank}: e2e {e2e_s / args.steps * 1e3:.2f} ms/step, sync {sync_s / args.steps * 1e3:.2f}",
+              file=sys.stderr, flush=True)
     if world > 1:
         t = torch.tensor([e2e_s, sync_s], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
