@@ -182,6 +182,7 @@ class Engine:
         self.device = device
         self.L = _lib.lib()
         self._ws: Optional[torch.Tensor] = None
+        self._ws2: Optional[torch.Tensor] = None
         self._cap_words = 0
         self._cap_n = 0
         self.status = torch.zeros(4, dtype=torch.int64, device=device)
@@ -194,7 +195,6 @@ class Engine:
         self.trace_stream = torch.cuda.Stream(device, priority=-1)   # its CTAs go first when SMs free up
         self._trace_done = [None, None]
         self._parity = 0
-        self._dev_bufs = {}
         self._slots = {}
         self._host_pool = []
         self._fused = None
@@ -259,17 +259,6 @@ class Engine:
             s = self._slots[k] = _Slot(self)
         return s
 
-    def device_buffer(self, name: str, shape, dtype) -> torch.Tensor:
-        """Engine-owned device scratch, reused across (synchronous) calls."""
-        need = 1
-        for v in shape:
-            need *= int(v)
-        buf = self._dev_bufs.get(name)
-        if buf is None or buf.dtype != dtype or buf.numel() < need:
-            self._dev_bufs[name] = None
-            buf = self._dev_bufs[name] = torch.empty(max(need, 1), dtype=dtype, device=self.device)
-        return buf[:need].view(*shape)
-
     def _workspace(self, n: int, words: int, slot: int = 0) -> torch.Tensor:
         """Workspace `slot` (0: default; 1: a second buffer of the same capacity for callers
         that keep two calls in flight)."""
@@ -285,7 +274,7 @@ class Engine:
             self._cap_n, self._cap_words = cap_n, cap_w
         if slot == 0:
             return self._ws
-        if getattr(self, "_ws2", None) is None or self._ws2.numel() != self._ws.numel():
+        if self._ws2 is None or self._ws2.numel() != self._ws.numel():
             self._ws2 = torch.empty(self._ws.numel(), dtype=torch.uint8, device=self.device)
         return self._ws2
 
