@@ -822,7 +822,7 @@ def submit_measure_instances(instances, output_size=None, classes_of_interest=No
     with torch.cuda.device(dev):
         if early is None:
             early = _issue_mask_copies(eng, slot, dev, ml, counts, pipeline_chunks)
-        d_masks, ev_in, bounds = early
+        d_masks, ev_in, bounds, resume_mask_copies = early
         rows_i = slot.device("rows_i", (n, NUM_INT), torch.int64)
         rows_f = slot.device("rows_f", (n, NUM_FLOAT), torch.float64)
         status = slot.device("status", (4,), torch.int64)
@@ -856,6 +856,7 @@ def submit_measure_instances(instances, output_size=None, classes_of_interest=No
                 dst.copy_(hp, **nb)
             ev_small = torch.cuda.Event()
             ev_small.record(eng.small_stream)
+        resume_mask_copies()                      # the other chunks queue behind the small copies
         ws = eng._workspace(n, n_words)
         common = dict(image_idx=d_img, inst_idx=d_inst, classes=d_classes, scores=d_scores,
                       threshold=mask_threshold, pixels_per_metric=pixels_per_metric,
@@ -944,8 +945,12 @@ def submit_measure_instances(instances, output_size=None, classes_of_interest=No
 
 
 def _issue_mask_copies(eng: "Engine", slot: _Slot, dev, ml, counts, pipeline_chunks: int):
-    """Enqueue the host->device copies of the mask probabilities on the engine's copy stream,
-    one event per chunk of images.  Returns (device masks, events, chunk bounds)."""
+    """Enqueue the host->device copy of the FIRST chunks of mask probabilities on the engine's
+    copy stream and return (device masks, one event per chunk, chunk bounds, resume); calling
+    ``resume()`` enqueues the remaining chunks.  The caller issues its small copies (boxes,
+    scores, ...) in between: the copy engine serves copies in issue order, so boxes queued behind
+    200 MB of masks would hold the layout -- and with it every paste -- back until the last mask
+    has landed."""
     n = int(sum(counts))
     nchunks = max(1, min(int(pipeline_chunks), len(ml)))
     per = (len(ml) + nchunks - 1) // nchunks
@@ -974,7 +979,7 @@ def _issue_mask_copies(eng: "Engine", slot: _Slot, dev, ml, counts, pipeline_chu
         whole = torch.as_strided(live[0], (n, mrow), (mrow, 1))
         ev = torch.cuda.Event()
         ev.record(main)
-        return whole, [ev for _ in bounds], bounds
+        return whole, [ev for _ in bounds], bounds, (lambda: None)
     with torch.cuda.device(dev):
         d_masks = slot.device("masks", (n, mrow), torch.float32)
         ev_in = [torch.cuda.Event() for _ in bounds]
@@ -985,13 +990,21 @@ def _issue_mask_copies(eng: "Engine", slot: _Slot, dev, ml, counts, pipeline_chu
             for m in ml:
                 if m.is_cuda:
                     m.record_stream(eng.h2d_stream)
-        with torch.cuda.stream(eng.h2d_stream):
-            for c, (i0, i1, _lo, _hi) in enumerate(bounds):
-                for i in range(i0, i1):             # pinned sources stay pinned: async copies
-                    if counts[i]:
-                        d_masks[starts[i]:starts[i + 1]].copy_(ml[i], non_blocking=True)
-                ev_in[c].record(eng.h2d_stream)
-    return d_masks, ev_in, bounds
+
+        def issue(c0: int, c1: int) -> None:
+            with torch.cuda.device(dev), torch.cuda.stream(eng.h2d_stream):
+                for c in range(c0, c1):
+                    i0, i1, _lo, _hi = bounds[c]
+                    for i in range(i0, i1):         # pinned sources stay pinned: async copies
+                        if counts[i]:
+                            d_masks[starts[i]:starts[i + 1]].copy_(ml[i], non_blocking=True)
+                    ev_in[c].record(eng.h2d_stream)
+
+        # half of the chunks go out at once: about as much copy time as the host needs to
+        # prepare the small tensors
+        n_early = max(1, len(bounds) // 2)
+        issue(0, n_early)
+    return d_masks, ev_in, bounds, (lambda: issue(n_early, len(bounds)))
 
 
 def dist_is_multi() -> bool:
