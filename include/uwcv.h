@@ -181,6 +181,15 @@ int uwcv_unpack_planes(const uint32_t* bitplanes, int64_t N, int H, int W, uint8
                        void* stream);
 
 /*
+ * uwcv_ingest -- copy `bytes` (rounded up to 16: both buffers must be padded accordingly) from
+ * pinned, device-mapped HOST memory (cudaHostAlloc / torch pin_memory under unified addressing)
+ * to device memory with a kernel instead of the copy engine.  For the small per-call arrays
+ * (boxes, scores, classes, indices): a cudaMemcpyAsync of 1 MB issued behind the 200 MB of mask
+ * probabilities of a batch is served after them and delays the first kernel by milliseconds.
+ */
+int uwcv_ingest(const void* src_host_mapped, void* dst, size_t bytes, void* stream);
+
+/*
  * Union / connected-component mode -- the reference-literal GetMask_Contours
  * (nn_inference.py:394-459): the masks of the selected class are OR-ed into one image and
  * EVERY external contour of that union is measured (touching instances merge).

@@ -217,3 +217,32 @@ def test_tile_major_sharding_partitions_the_instances():
     inside = (cx > 0) & (cx < W) & (cy > 0) & (cy < H)
     want = (cy >= H / 2).long() * 2 + (cx >= W / 2).long()
     assert torch.equal(own[inside], want[inside])
+
+
+def test_scale_clip_equals_detectron2_column_ops_and_words_bound():
+    """The whole-tensor form of Boxes.scale / clip / nonempty is bit-identical to Detectron2's
+    column-wise ops (oracle restatement), non-finite boxes raise as Boxes.clip does, and the cheap
+    workspace bound never undercuts the exact tile-word count."""
+    from oracle import d2
+    from uwcv import api
+    g = torch.Generator().manual_seed(0)
+    for in_size, out_size in (((800, 1333), (1024, 1024)), ((512, 512), (2048, 2048)),
+                              ((1000, 700), (333, 777)), ((640, 640), (640, 640)),
+                              ((100, 200), (300, 600))):
+        bx = (torch.rand((4000, 4), generator=g) - 0.2) * 1500
+        ref = d2.Boxes(bx.clone())
+        ref.scale(out_size[1] / in_size[1], out_size[0] / in_size[0])
+        ref.clip(out_size)
+        mine, keep = api.scale_clip_boxes(bx, in_size, out_size)
+        assert torch.equal(mine, ref.tensor) and torch.equal(keep, ref.nonempty())
+    for bad in (float("nan"), float("inf"), -float("inf")):
+        bx = torch.rand((10, 4))
+        bx[3, 1] = bad
+        with pytest.raises(AssertionError):
+            api.scale_clip_boxes(bx, (10, 10), (10, 10))
+    for trial in range(100):
+        c = torch.rand((60, 2), generator=g) * 300 - 50
+        wh = torch.exp(torch.rand((60, 2), generator=g) * 9 - 3)
+        bx, _ = api.scale_clip_boxes(torch.cat((c, c + wh), 1), (256, 256), (256, 256))
+        assert api.tile_words_bound(bx) >= api.tile_words(bx, 256, 256)
+    assert api.tile_words_bound(torch.zeros((0, 4))) == 0

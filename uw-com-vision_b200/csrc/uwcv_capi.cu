@@ -13,6 +13,7 @@ cudaError_t launch_contour_measure(int64_t, int64_t, const float*, double, int64
                                    const Workspace&, const int64_t*, int, cudaStream_t,
                                    const GatherDst&);
 cudaError_t launch_unpack(const uint32_t*, int64_t, int, int, uint8_t*, int, cudaStream_t);
+cudaError_t launch_ingest(const void*, void*, size_t, cudaStream_t);
 size_t nms_workspace_bytes_host(const int64_t*, int, int);
 size_t union_workspace_bytes_host(int64_t, int64_t);
 cudaError_t launch_union(int64_t, const Workspace&, const int32_t*, const TileDesc*, const int32_t*,
@@ -218,6 +219,15 @@ int uwcv_rle_write(const void* paste_workspace, size_t ws_bytes, int64_t N, int 
   const uwcv::Workspace ws = uwcv::carve(const_cast<void*>(paste_workspace), ws_bytes, N);
   return uwcv::launch_rle_write(N, H, W, ws, run_offsets, runs,
                                 reinterpret_cast<cudaStream_t>(stream)) == cudaSuccess
+             ? UWCV_OK : UWCV_E_LAUNCH;
+}
+
+int uwcv_ingest(const void* src_host_mapped, void* dst, size_t bytes, void* stream) {
+  if (bytes == 0) return UWCV_OK;
+  if (!src_host_mapped || !dst) return UWCV_E_NULL;
+  if (misaligned(src_host_mapped) || misaligned(dst)) return UWCV_E_ALIGN;
+  return uwcv::launch_ingest(src_host_mapped, dst, bytes, reinterpret_cast<cudaStream_t>(stream)) ==
+                 cudaSuccess
              ? UWCV_OK : UWCV_E_LAUNCH;
 }
 
