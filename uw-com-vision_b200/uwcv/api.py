@@ -184,7 +184,9 @@ class Engine:
     """Per-device cache of workspace / output buffers around the C ABI.
 
     ``run`` enqueues layout + paste/measure + contour kernels on the current stream and
-    returns device tensors; nothing synchronises until the caller reads them."""
+    returns device tensors; nothing synchronises until the caller reads them.  One engine per
+    device, driven from one host thread at a time (the C ABI underneath is re-entrant; the
+    buffer caches here are not locked)."""
 
     _engines = {}
 
