@@ -43,10 +43,6 @@ class RleExport:
         return len(self.encoded_pixels)
 
 
-def _format_runs(starts: np.ndarray, lengths: np.ndarray) -> str:
-    return ' '.join(f"{int(s)} {int(l)}" for s, l in zip(starts, lengths))
-
-
 def export_rle(instances, output_size: Optional[Tuple[int, int]] = None,
                names: Optional[Sequence[str]] = None, *, mask_threshold: float = 0.5,
                min_crys_size: int = 2, mask_channel_offset: int = 0, device=None) -> RleExport:
@@ -148,20 +144,20 @@ def export_rle(instances, output_size: Optional[Tuple[int, int]] = None,
         m_inst = inst_of_run[head]
     else:
         m_start = m_len = m_inst = np.zeros(0, np.int64)
-    bounds = np.searchsorted(m_inst, np.arange(n + 1))
+    bounds = np.searchsorted(m_inst, np.arange(n + 1)).tolist()
+    # text of every number once (start, length interleaved), joined per instance below
+    inter = np.empty(2 * len(m_start), dtype=np.int64)
+    inter[0::2] = m_start
+    inter[1::2] = m_len
+    words = list(map(str, inter.tolist()))
     slot = torch.cat(slot_l).numpy()
     idx = torch.cat(inst_l).numpy()
     out = RleExport([], [], None, None, None, None)
-    keep_rows = []
-    for i in range(n):
-        b = int(slot[i])
-        if idx[i] >= h_limit[b]:
-            continue
-        keep_rows.append(i)
-        out.image_id.append(names[b].replace('.tif', ''))
-        out.encoded_pixels.append(_format_runs(m_start[bounds[i]:bounds[i + 1]],
-                                               m_len[bounds[i]:bounds[i + 1]]))
-    kr = np.asarray(keep_rows, dtype=np.int64)
+    kr = np.flatnonzero(idx < h_limit[slot])              # instances that are part of the output
+    ids = [nm.replace('.tif', '') for nm in names]
+    for i, b in zip(kr.tolist(), slot[kr].tolist()):
+        out.image_id.append(ids[b])
+        out.encoded_pixels.append(' '.join(words[2 * bounds[i]: 2 * bounds[i + 1]]))
     out.image_idx = slot[kr].astype(np.int64)
     out.inst_idx = idx[kr].astype(np.int64)
     out.area = h_area[kr]
