@@ -271,9 +271,8 @@ def test_fast_rcnn_inference_drop_in():
     assert torch.equal(out.pred_boxes.tensor.cpu(), ref.pred_boxes.tensor)
     assert torch.equal(out.scores.cpu(), ref.scores)
     assert torch.equal(out.pred_classes.cpu(), ref.pred_classes)
-    # kept proposal rows index the finite-filtered list in the oracle, the original list here
-    valid = torch.isfinite(boxes).all(1) & torch.isfinite(scores).all(1)
-    assert torch.equal(rows.cpu(), torch.arange(R)[valid][ref_rows])
+    # kept proposal rows index the finite-filtered list, as Detectron2's filter_inds[:, 0] do
+    assert torch.equal(rows.cpu(), ref_rows)
 
 
 # ---------------------------------------------------------------- full size --------

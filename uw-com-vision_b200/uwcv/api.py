@@ -496,14 +496,14 @@ def fast_rcnn_inference_single_image(boxes: torch.Tensor, scores: torch.Tensor,
                                      image_shape: Tuple[int, int], score_thresh: float,
                                      nms_thresh: float, topk_per_image: int, device=None):
     """detectron2 fast_rcnn_inference_single_image: boxes R x (K*4) (or R x 4), scores
-    R x (K+1) with the background column last.  Returns (Instances, kept proposal rows)."""
+    R x (K+1) with the background column last.  Returns (Instances, kept proposal rows) -- the
+    rows index the input after non-finite rows have been dropped, as Detectron2's do."""
     dev = _require_cuda(device if device is not None else (boxes.device if boxes.is_cuda else None))
     boxes = boxes.to(dev, torch.float32)
     scores = scores.to(dev, torch.float32)
     valid = torch.isfinite(boxes).all(dim=1) & torch.isfinite(scores).all(dim=1)
-    rows = torch.arange(boxes.shape[0], device=dev)
     if not bool(valid.all()):
-        boxes, scores, rows = boxes[valid], scores[valid], rows[valid]
+        boxes, scores = boxes[valid], scores[valid]
     scores = scores[:, :-1]
     R, K = scores.shape
     nreg = boxes.shape[1] // 4
@@ -526,7 +526,8 @@ def fast_rcnn_inference_single_image(boxes: torch.Tensor, scores: torch.Tensor,
     res.pred_boxes = Boxes(cand_boxes[keep])
     res.scores = cand_scores[keep]
     res.pred_classes = cand_cls[keep]
-    return res, rows[keep // K]
+    # Detectron2 returns filter_inds[:, 0]: row positions AFTER its finite-value filter
+    return res, keep // K
 
 
 # ----------------------------------------------------------------------------------

@@ -33,19 +33,19 @@ def fast_rcnn_inference(boxes: Sequence[torch.Tensor], scores: Sequence[torch.Te
     """detectron2.modeling.roi_heads.fast_rcnn.fast_rcnn_inference for a list of images, in
     ONE batched kernel sequence.  ``boxes[b]`` is R_b x (K*4) (or R_b x 4), ``scores[b]`` is
     R_b x (K+1) with the background column LAST.  Returns (list of Instances with pred_boxes /
-    scores / pred_classes, list of kept proposal-row indices), as Detectron2 does."""
+    scores / pred_classes, list of kept proposal-row indices -- positions after Detectron2's
+    finite-value filter, i.e. ``filter_inds[:, 0]``), as Detectron2 does."""
     dev = _require_cuda(device if device is not None else
                         (boxes[0].device if len(boxes) and boxes[0].is_cuda else None))
     eng = Engine.get(dev)
-    cb, cs, cc, rows, off = [], [], [], [], [0]
+    cb, cs, cc, off = [], [], [], [0]
     K = 0
     for bx, sc, (h, w) in zip(boxes, scores, image_shapes):
         bx = bx.to(dev, torch.float32)
         sc = sc.to(dev, torch.float32)
         valid = torch.isfinite(bx).all(dim=1) & torch.isfinite(sc).all(dim=1)
-        r = torch.arange(bx.shape[0], device=dev)
         if not bool(valid.all()):
-            bx, sc, r = bx[valid], sc[valid], r[valid]
+            bx, sc = bx[valid], sc[valid]
         sc = sc[:, :-1]
         R, K = sc.shape
         nreg = bx.shape[1] // 4
@@ -58,7 +58,6 @@ def fast_rcnn_inference(boxes: Sequence[torch.Tensor], scores: Sequence[torch.Te
         cb.append(b4.reshape(R * K, 4))
         cs.append(sc.reshape(R * K))
         cc.append(torch.arange(K, device=dev, dtype=torch.int64).repeat(R))
-        rows.append(r)
         off.append(off[-1] + R * K)
     if not cb:
         return [], []
@@ -76,7 +75,7 @@ def fast_rcnn_inference(boxes: Sequence[torch.Tensor], scores: Sequence[torch.Te
         res.scores = cand_scores[k]
         res.pred_classes = cand_cls[k]
         results.append(res)
-        kept_rows.append(rows[b][(k - off[b]) // K])
+        kept_rows.append((k - off[b]) // K)        # positions after the finite-value filter (D2)
     return results, kept_rows
 
 
