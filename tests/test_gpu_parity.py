@@ -688,3 +688,22 @@ def test_clean_masks_on_arbitrary_binary_shapes():
     table = uwcv.measure_instances(batch, (H, W))
     ri, rf = P.oracle_table(batch, (H, W))
     compare_tables(table, ri, rf)
+
+
+def test_single_forward_stream_equals_per_batch_calls():
+    """SingleForward.measure_stream (network of batch i + 1 enqueued while batch i is measured)
+    yields the tables of measure() batch by batch."""
+    import torchvision
+    torch.manual_seed(1)
+    model = torchvision.models.detection.maskrcnn_resnet50_fpn(
+        weights=None, weights_backbone=None, num_classes=5, min_size=192, max_size=192,
+        box_score_thresh=0.0, rpn_post_nms_top_n_test=100).cuda().eval()
+    sf = uwcv.SingleForward(model, score_thresh=0.05, nms_thresh=0.5, detections_per_image=40)
+    g = torch.Generator().manual_seed(3)
+    batches = [[torch.rand((3, 192, 192), generator=g) for _ in range(2)] for _ in range(4)]
+    want = [sf.measure(b) for b in batches]
+    got = list(sf.measure_stream(batches))
+    assert len(got) == len(want) and sum(len(t) for t in want) > 0
+    for a, b in zip(got, want):
+        assert np.array_equal(a.ints, b.ints)
+        assert np.array_equal(a.floats, b.floats, equal_nan=True)
