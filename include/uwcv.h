@@ -267,6 +267,22 @@ int uwcv_clean_masks(void* paste_workspace, size_t ws_bytes, int64_t N, int H, i
 int uwcv_rle_write(const void* paste_workspace, size_t ws_bytes, int64_t N, int H, int W,
                    const int64_t* run_offsets, int64_t* runs, void* stream);
 
+/*
+ * Literal postprocess_masks(ori_mask, ...) entry (nn_inference.py:259, called at :325-327 with
+ * Detectron2's pasted pred_masks): N x H x W bool / uint8 masks in, cleaned masks out.
+ *   uwcv_mask_pixel_boxes: boxes [N, 4] float32 = [xmin, ymin, xmax + 1, ymax + 1] of the set
+ *     pixels of every mask (zeros for an empty one): feed them to uwcv_paste_measure_stages
+ *     (stages = 1, the layout) so that every mask gets a tile with a margin;
+ *   uwcv_pack_mask_tiles: fills the tile mask plane of that workspace from the bytes (instead of
+ *     stage 2); then uwcv_mask_column_totals / uwcv_clean_masks / uwcv_rle_write as above;
+ *   uwcv_tiles_to_masks: out [N, H, W] uint8, zeroed by the caller, receives the cleaned masks.
+ */
+int uwcv_mask_pixel_boxes(const uint8_t* masks, int64_t N, int H, int W, float* boxes, void* stream);
+int uwcv_pack_mask_tiles(const uint8_t* masks, int64_t N, int H, int W, void* paste_workspace,
+                         size_t ws_bytes, void* stream);
+int uwcv_tiles_to_masks(const void* paste_workspace, size_t ws_bytes, int64_t N, int H, int W,
+                        uint8_t* out, void* stream);
+
 /* Bytes of workspace for uwcv_nms_filter; image_off is a HOST array [B + 1];
  * num_classes <= 0 means 128. */
 size_t uwcv_nms_workspace_bytes(const int64_t* image_off, int B, int num_classes);

@@ -707,3 +707,37 @@ def test_single_forward_stream_equals_per_batch_calls():
     for a, b in zip(got, want):
         assert np.array_equal(a.ints, b.ints)
         assert np.array_equal(a.floats, b.floats, equal_nan=True)
+
+
+def test_postprocess_masks_literal_drop_in():
+    """uwcv.postprocess_masks(ori_mask, ori_score, image) -- N x H x W bool masks in, list of
+    cleaned uint8 masks out -- equals the reference's function (oracle/cleanup.py) mask for mask,
+    including its None / [] / truncation behaviour."""
+    from oracle import cleanup as OC
+    rng = np.random.default_rng(11)
+    for H, W in ((96, 128), (77, 131)):                       # W a multiple of 16 (vector path) and not
+        n = 30
+        masks = np.zeros((n, H, W), dtype=bool)
+        for i in range(n):
+            y0, x0 = rng.integers(0, H - 12), rng.integers(0, W - 12)
+            h, w = rng.integers(6, 40), rng.integers(6, 40)
+            blob = rng.random((min(h, H - y0), min(w, W - x0))) < 0.8
+            masks[i, y0:y0 + blob.shape[0], x0:x0 + blob.shape[1]] = blob
+        masks[3] = False                                      # an empty mask stays in the list
+        masks[5, :, 10:14] = True                             # full height: touches both borders
+        scores = np.linspace(0.95, 0.55, n)
+        want = OC.postprocess_masks(masks.copy(), scores, (H, W))
+        got = uwcv.postprocess_masks(masks, scores, np.zeros((H, W, 3), np.uint8))
+        assert len(got) == len(want) == n
+        for k, (a, b) in enumerate(zip(got, want)):
+            assert a.dtype == np.uint8 and np.array_equal(a, b), (H, W, k)
+        assert sum(1 for b in want if b.sum() == 0) > 3        # overlaps / pieces were exercised
+        # torch input, zero score -> None; no masks -> None; all-empty masks -> []
+        assert uwcv.postprocess_masks(torch.from_numpy(masks), np.append(scores[:-1], 0.0), (H, W)) is None
+        assert uwcv.postprocess_masks(masks[:0], scores[:0], (H, W)) is None
+        assert uwcv.postprocess_masks(np.zeros((3, H, W), bool), scores[:3], (H, W)) == []
+        # fewer occupied columns than instances: the list is truncated (:277-284)
+        thin = np.zeros((5, H, W), bool)
+        thin[:, 20:40, 30:32] = True
+        g2, w2 = uwcv.postprocess_masks(thin, scores[:5], (H, W)), OC.postprocess_masks(thin.copy(), scores[:5], (H, W))
+        assert len(g2) == len(w2) == 2 and all(np.array_equal(a, b) for a, b in zip(g2, w2))

@@ -23,6 +23,7 @@
 // not the image border (tile_geometry), so "outside the tile" is background connected to the
 // image border: the tile ring is a complete seed set for the hole fill, and dilation never
 // leaves the tile.
+#include <climits>
 #include "uwcv_common.cuh"
 
 namespace uwcv {
@@ -369,6 +370,122 @@ cudaError_t launch_rle_write(int64_t n, int H, int W, const Workspace& ws, const
                              int64_t* runs, cudaStream_t stream) {
   if (n == 0) return cudaSuccess;
   rle_write_kernel<<<warps_grid(n), kCleanThreads, 0, stream>>>(n, H, W, ws, run_off, runs);
+  return cudaPeekAtLastError();
+}
+
+}  // namespace uwcv
+
+// ---- literal postprocess_masks entry: N x H x W bool masks in ---------------------------------
+// (for callers that keep Detectron2's own paste and hand over pred_masks as the reference does,
+//  nn_inference.py:325-327).  pixel_boxes: per instance the box [xmin, ymin, xmax + 1, ymax + 1]
+//  of its set pixels as float32 XYXY (all zeros for an empty mask), which the ordinary layout
+//  stage turns into a tile with a margin; pack_tiles then fills the tile plane M from the bytes.
+namespace uwcv {
+
+__global__ void __launch_bounds__(256)
+pixel_boxes_kernel(const uint8_t* __restrict__ masks, int H, int W, float* __restrict__ boxes) {
+  __shared__ int s_box[4];
+  const int64_t i = blockIdx.x;
+  if (threadIdx.x == 0) { s_box[0] = INT_MAX; s_box[1] = INT_MAX; s_box[2] = -1; s_box[3] = -1; }
+  __syncthreads();
+  const uint8_t* m = masks + i * (int64_t)H * W;
+  int x0 = INT_MAX, y0 = INT_MAX, x1 = -1, y1 = -1;
+  const int64_t total = (int64_t)H * W;
+  const bool vec = (W % 16 == 0) && ((reinterpret_cast<uintptr_t>(m) & 15) == 0);
+  if (vec) {
+    const uint4* v = reinterpret_cast<const uint4*>(m);
+    const int wq = W / 16;
+    for (int64_t k = threadIdx.x; k < total / 16; k += blockDim.x) {
+      const uint4 q = __ldg(v + k);
+      if (q.x | q.y | q.z | q.w) {
+        const int y = (int)(k / wq), xb = (int)(k - (int64_t)y * wq) * 16;
+        const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+          if (w[a]) {
+            const int lo = (__ffs(w[a]) - 1) >> 3, hi = (31 - __clz(w[a])) >> 3;
+            x0 = min(x0, xb + 4 * a + lo); x1 = max(x1, xb + 4 * a + hi);
+          }
+        y0 = min(y0, y); y1 = max(y1, y);
+      }
+    }
+  } else {
+    for (int64_t k = threadIdx.x; k < total; k += blockDim.x)
+      if (m[k]) {
+        const int y = (int)(k / W), x = (int)(k - (int64_t)y * W);
+        x0 = min(x0, x); x1 = max(x1, x); y0 = min(y0, y); y1 = max(y1, y);
+      }
+  }
+  if (x1 >= 0) {
+    atomicMin(&s_box[0], x0); atomicMin(&s_box[1], y0);
+    atomicMax(&s_box[2], x1); atomicMax(&s_box[3], y1);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const bool any = s_box[2] >= 0;
+    boxes[4 * i + 0] = any ? (float)s_box[0] : 0.f;
+    boxes[4 * i + 1] = any ? (float)s_box[1] : 0.f;
+    boxes[4 * i + 2] = any ? (float)(s_box[2] + 1) : 0.f;
+    boxes[4 * i + 3] = any ? (float)(s_box[3] + 1) : 0.f;
+  }
+}
+
+// one warp per instance: lane = pixel of a 32-pixel tile word
+__global__ void __launch_bounds__(kCleanThreads)
+pack_tiles_kernel(int64_t n, const uint8_t* __restrict__ masks, int H, int W, Workspace ws) {
+  const int lane = threadIdx.x & 31;
+  const int64_t i = ((int64_t)blockIdx.x * kCleanThreads + threadIdx.x) >> 5;
+  if (i >= n) return;
+  const TileDesc d = ws.desc[i];
+  uint32_t* M = ws.M + d.word_off;
+  const uint8_t* m = masks + i * (int64_t)H * W;
+  const int total = d.tw * d.th;
+  for (int k = 0; k < total; ++k) {
+    const int r = k / d.tw, w = k - r * d.tw;
+    const int x = (d.wx0 + w) * 32 + lane, y = d.y0 + r;
+    const bool bit = x < W && m[(int64_t)y * W + x] != 0;
+    const uint32_t word = __ballot_sync(kAll, bit);
+    if (lane == 0) M[k] = word;
+  }
+}
+
+// cleaned tiles -> N x H x W uint8 (0 / 1), the list the reference's postprocess_masks returns
+__global__ void __launch_bounds__(kCleanThreads)
+tiles_to_masks_kernel(int64_t n, int H, int W, Workspace ws, uint8_t* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t i = ((int64_t)blockIdx.x * kCleanThreads + threadIdx.x) >> 5;
+  if (i >= n) return;
+  const TileDesc d = ws.desc[i];
+  const uint32_t* M = ws.M + d.word_off;
+  uint8_t* o = out + i * (int64_t)H * W;
+  const int total = d.tw * d.th;
+  for (int k = 0; k < total; ++k) {
+    const uint32_t word = __ldg(M + k);
+    if (!word) continue;
+    const int r = k / d.tw, w = k - r * d.tw;
+    const int x = (d.wx0 + w) * 32 + lane;
+    if (x < W && ((word >> lane) & 1u)) o[(int64_t)(d.y0 + r) * W + x] = 1;
+  }
+}
+
+cudaError_t launch_pixel_boxes(const uint8_t* masks, int64_t n, int H, int W, float* boxes,
+                               cudaStream_t stream) {
+  if (n == 0) return cudaSuccess;
+  pixel_boxes_kernel<<<(unsigned)n, 256, 0, stream>>>(masks, H, W, boxes);
+  return cudaPeekAtLastError();
+}
+
+cudaError_t launch_pack_tiles(const uint8_t* masks, int64_t n, int H, int W, const Workspace& ws,
+                              cudaStream_t stream) {
+  if (n == 0) return cudaSuccess;
+  pack_tiles_kernel<<<warps_grid(n), kCleanThreads, 0, stream>>>(n, masks, H, W, ws);
+  return cudaPeekAtLastError();
+}
+
+cudaError_t launch_tiles_to_masks(int64_t n, int H, int W, const Workspace& ws, uint8_t* out,
+                                  cudaStream_t stream) {
+  if (n == 0) return cudaSuccess;
+  tiles_to_masks_kernel<<<warps_grid(n), kCleanThreads, 0, stream>>>(n, H, W, ws, out);
   return cudaPeekAtLastError();
 }
 

@@ -27,6 +27,9 @@ cudaError_t launch_clean(int64_t, int, int, const Workspace&, const int32_t*, co
                          const int32_t*, int32_t*, int64_t*, int64_t*, cudaStream_t);
 cudaError_t launch_rle_write(int64_t, int, int, const Workspace&, const int64_t*, int64_t*,
                              cudaStream_t);
+cudaError_t launch_pixel_boxes(const uint8_t*, int64_t, int, int, float*, cudaStream_t);
+cudaError_t launch_pack_tiles(const uint8_t*, int64_t, int, int, const Workspace&, cudaStream_t);
+cudaError_t launch_tiles_to_masks(int64_t, int, int, const Workspace&, uint8_t*, cudaStream_t);
 }  // namespace uwcv
 
 namespace {
@@ -227,6 +230,42 @@ int uwcv_ingest(const void* src_host_mapped, void* dst, size_t bytes, void* stre
   if (!src_host_mapped || !dst) return UWCV_E_NULL;
   if (misaligned(src_host_mapped) || misaligned(dst)) return UWCV_E_ALIGN;
   return uwcv::launch_ingest(src_host_mapped, dst, bytes, reinterpret_cast<cudaStream_t>(stream)) ==
+                 cudaSuccess
+             ? UWCV_OK : UWCV_E_LAUNCH;
+}
+
+int uwcv_mask_pixel_boxes(const uint8_t* masks, int64_t N, int H, int W, float* boxes, void* stream) {
+  if (N < 0 || H <= 0 || W <= 0) return UWCV_E_SHAPE;
+  if (H > 32768 || W > 32768) return UWCV_E_TOO_LARGE;
+  if (N == 0) return UWCV_OK;
+  if (!masks || !boxes) return UWCV_E_NULL;
+  return uwcv::launch_pixel_boxes(masks, N, H, W, boxes, reinterpret_cast<cudaStream_t>(stream)) ==
+                 cudaSuccess
+             ? UWCV_OK : UWCV_E_LAUNCH;
+}
+
+int uwcv_pack_mask_tiles(const uint8_t* masks, int64_t N, int H, int W, void* paste_workspace,
+                         size_t ws_bytes, void* stream) {
+  if (N < 0 || H <= 0 || W <= 0) return UWCV_E_SHAPE;
+  if (N == 0) return UWCV_OK;
+  if (!masks || !paste_workspace) return UWCV_E_NULL;
+  if (misaligned(paste_workspace)) return UWCV_E_ALIGN;
+  if (ws_bytes < uwcv::workspace_bytes(N, 4)) return UWCV_E_WORKSPACE;
+  const uwcv::Workspace ws = uwcv::carve(paste_workspace, ws_bytes, N);
+  return uwcv::launch_pack_tiles(masks, N, H, W, ws, reinterpret_cast<cudaStream_t>(stream)) ==
+                 cudaSuccess
+             ? UWCV_OK : UWCV_E_LAUNCH;
+}
+
+int uwcv_tiles_to_masks(const void* paste_workspace, size_t ws_bytes, int64_t N, int H, int W,
+                        uint8_t* out, void* stream) {
+  if (N < 0 || H <= 0 || W <= 0) return UWCV_E_SHAPE;
+  if (N == 0) return UWCV_OK;
+  if (!paste_workspace || !out) return UWCV_E_NULL;
+  if (misaligned(paste_workspace)) return UWCV_E_ALIGN;
+  if (ws_bytes < uwcv::workspace_bytes(N, 4)) return UWCV_E_WORKSPACE;
+  const uwcv::Workspace ws = uwcv::carve(const_cast<void*>(paste_workspace), ws_bytes, N);
+  return uwcv::launch_tiles_to_masks(N, H, W, ws, out, reinterpret_cast<cudaStream_t>(stream)) ==
                  cudaSuccess
              ? UWCV_OK : UWCV_E_LAUNCH;
 }

@@ -17,12 +17,12 @@ from .dist import (shard_indices, shard_instances_by_tile, take_instances,   # n
                    all_gather_table, sort_rows)
 from .union import UnionTable, measure_union                  # noqa: F401
 from .heads import SingleForward, fast_rcnn_inference         # noqa: F401
-from .cleanup import RleExport, export_rle, write_rle_csv     # noqa: F401
+from .cleanup import RleExport, export_rle, postprocess_masks, write_rle_csv     # noqa: F401
 
 __all__ = [
     "Boxes", "Instances", "Engine", "MeasurementTable", "MeasurementStream", "PendingTable",
     "submit_measure_instances", "measure_instances",
     "paste_masks_in_image", "detector_postprocess", "fast_rcnn_inference_single_image",
     "get_counts", "group_by_class", "write_classes_csv", "moving_average", "report_class",
-    "write_results_csv", "shard_indices", "shard_instances_by_tile", "take_instances", "all_gather_table", "sort_rows", "UnionTable", "measure_union", "SingleForward", "fast_rcnn_inference", "RleExport", "export_rle", "write_rle_csv",
+    "write_results_csv", "shard_indices", "shard_instances_by_tile", "take_instances", "all_gather_table", "sort_rows", "UnionTable", "measure_union", "SingleForward", "fast_rcnn_inference", "RleExport", "export_rle", "postprocess_masks", "write_rle_csv",
 ]

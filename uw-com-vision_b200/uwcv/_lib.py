@@ -62,6 +62,12 @@ def lib() -> C.CDLL:
     L.uwcv_rle_write.argtypes = [vp, sz, i64, i32, i32, vp, vp, vp]
     L.uwcv_ingest.restype = C.c_int
     L.uwcv_ingest.argtypes = [vp, vp, sz, vp]
+    L.uwcv_mask_pixel_boxes.restype = C.c_int
+    L.uwcv_mask_pixel_boxes.argtypes = [vp, i64, i32, i32, vp, vp]
+    L.uwcv_pack_mask_tiles.restype = C.c_int
+    L.uwcv_pack_mask_tiles.argtypes = [vp, i64, i32, i32, vp, sz, vp]
+    L.uwcv_tiles_to_masks.restype = C.c_int
+    L.uwcv_tiles_to_masks.argtypes = [vp, sz, i64, i32, i32, vp, vp]
     L.uwcv_unpack_planes.restype = C.c_int
     L.uwcv_unpack_planes.argtypes = [vp, i64, i32, i32, vp, vp]
     L.uwcv_union_workspace_bytes.restype = sz
@@ -81,6 +87,7 @@ def lib() -> C.CDLL:
 EXPORTS = ("uwcv_version", "uwcv_strerror", "uwcv_plane_row_words", "uwcv_workspace_bytes",
            "uwcv_paste_measure", "uwcv_paste_measure_stages", "uwcv_paste_measure_range", "uwcv_paste_measure_heads", "uwcv_paste_measure_gather",
            "uwcv_unpack_planes", "uwcv_ingest", "uwcv_mask_column_totals", "uwcv_clean_masks", "uwcv_rle_write",
+           "uwcv_mask_pixel_boxes", "uwcv_pack_mask_tiles", "uwcv_tiles_to_masks",
            "uwcv_union_workspace_bytes", "uwcv_union_measure", "uwcv_nms_workspace_bytes",
            "uwcv_nms_filter")
 

@@ -43,6 +43,84 @@ class RleExport:
         return len(self.encoded_pixels)
 
 
+def _clean_on_workspace(eng: Engine, n: int, H: int, W: int, d_slot, d_inst, counts, skip,
+                        min_crys_size: int):
+    """Column totals -> per-image limit (the reference's keep_ind quirk, :277-284) -> clean-up
+    kernels on the engine's tile workspace.  Returns device (limit, flags, area, run counts)."""
+    dev = eng.device
+    L = eng.L
+    ws = eng._ws
+    st = _stream_ptr(dev)
+    B = len(counts)
+    coltot = torch.zeros((B, W), dtype=torch.int32, device=dev)
+    _lib.check(L.uwcv_mask_column_totals(_ptr(ws), ws.numel(), n, W, _ptr(d_slot), _ptr(coltot), st),
+               "uwcv_mask_column_totals")
+    kcols = (coltot > int(min_crys_size)).sum(dim=1)
+    n_img = torch.tensor(counts, dtype=torch.int64, device=dev)
+    limit = torch.where(kcols < n_img, kcols, n_img)
+    limit = torch.where(torch.tensor(skip, device=dev), torch.zeros_like(limit), limit)
+    d_limit = limit.to(torch.int32).contiguous()
+    flags = torch.empty(n, dtype=torch.int32, device=dev)
+    area = torch.empty(n, dtype=torch.int64, device=dev)
+    nruns = torch.empty(n, dtype=torch.int64, device=dev)
+    _lib.check(L.uwcv_clean_masks(_ptr(ws), ws.numel(), n, H, W, _ptr(d_slot), _ptr(d_inst),
+                                  _ptr(d_limit), _ptr(flags), _ptr(area), _ptr(nruns), st),
+               "uwcv_clean_masks")
+    eng.launches += 3
+    return d_limit, flags, area, nruns
+
+
+def postprocess_masks(ori_mask, ori_score, image, min_crys_size: int = 2, *, device=None):
+    """The reference's ``postprocess_masks(ori_mask, ori_score, image, min_crys_size=2)``
+    (nn_inference.py:259-302) with the same arguments and return value: ``ori_mask`` N x H x W
+    bool (Detectron2's pasted ``pred_masks``, numpy or torch), ``ori_score`` N floats, ``image``
+    the H x W (x C) image or its shape; returns ``None`` when there is no mask or a score is
+    exactly zero (:274), else the list of cleaned H x W uint8 masks (possibly truncated, :277-284).
+    The masks are packed into bit tiles on the GPU and cleaned there (``csrc/cleanup.cu``)."""
+    dev = _require_cuda(device)
+    eng = Engine.get(dev)
+    m = torch.as_tensor(np.asarray(ori_mask) if not torch.is_tensor(ori_mask) else ori_mask)
+    sc = torch.as_tensor(np.asarray(ori_score) if not torch.is_tensor(ori_score) else ori_score)
+    shape = image.shape if hasattr(image, "shape") else tuple(image)
+    H, W = int(shape[0]), int(shape[1])
+    n = int(m.shape[0]) if m.dim() == 3 else 0
+    # ``len(ori_mask) == 0 or ori_score.all() < score_threshold``
+    if n == 0 or not bool((sc != 0).all()):
+        return None
+    if tuple(m.shape[1:]) != (H, W):
+        raise ValueError(f"masks {tuple(m.shape)} do not match the image {H} x {W}")
+    L = eng.L
+    with torch.cuda.device(dev):
+        d_m = m.to(dev).to(torch.uint8).contiguous()
+        st = _stream_ptr(dev)
+        d_boxes = torch.empty((n, 4), dtype=torch.float32, device=dev)
+        _lib.check(L.uwcv_mask_pixel_boxes(_ptr(d_m), n, H, W, _ptr(d_boxes), st), "uwcv_mask_pixel_boxes")
+        d_slot = torch.zeros(n, dtype=torch.int32, device=dev)
+        d_inst = torch.arange(n, dtype=torch.int32, device=dev)
+        rows_i = torch.empty((n, NUM_INT), dtype=torch.int64, device=dev)
+        rows_f = torch.empty((n, NUM_FLOAT), dtype=torch.float64, device=dev)
+        # the layout stage alone (tiles with a margin around every pixel box), then the tile
+        # plane is filled from the given masks instead of being pasted
+        eng.run(d_m, d_boxes, H, W, image_idx=d_slot, inst_idx=d_inst, rows_i=rows_i, rows_f=rows_f, stages=1,
+                n_tile_words=tile_words(d_boxes, H, W))
+        eng.check_status()
+        ws = eng._ws
+        _lib.check(L.uwcv_pack_mask_tiles(_ptr(d_m), n, H, W, _ptr(ws), ws.numel(), st),
+                   "uwcv_pack_mask_tiles")
+        d_limit, flags, _area, _nruns = _clean_on_workspace(eng, n, H, W, d_slot, d_inst, [n], [False],
+                                                            min_crys_size)
+        keep = int(d_limit.cpu()[0])
+        if keep == 0:
+            return []
+        # (the workspace is carved for all n instances; the masks beyond the limit are empty)
+        out = torch.zeros((n, H, W), dtype=torch.uint8, device=dev)
+        _lib.check(L.uwcv_tiles_to_masks(_ptr(ws), ws.numel(), n, H, W, _ptr(out), st),
+                   "uwcv_tiles_to_masks")
+        eng.launches += 3
+        host = out[:keep].cpu().numpy()
+    return [host[i] for i in range(keep)]
+
+
 def export_rle(instances, output_size: Optional[Tuple[int, int]] = None,
                names: Optional[Sequence[str]] = None, *, mask_threshold: float = 0.5,
                min_crys_size: int = 2, mask_channel_offset: int = 0, device=None) -> RleExport:
@@ -104,28 +182,15 @@ def export_rle(instances, output_size: Optional[Tuple[int, int]] = None,
         eng.check_status()
         ws = eng._ws
         st = _stream_ptr(dev)
-        # the reference's keep_ind (:277): image columns holding more than min_crys_size pixels
-        coltot = torch.zeros((B, W), dtype=torch.int32, device=dev)
-        _lib.check(L.uwcv_mask_column_totals(_ptr(ws), ws.numel(), n, W, _ptr(d_slot), _ptr(coltot), st),
-                   "uwcv_mask_column_totals")
-        kcols = (coltot > int(min_crys_size)).sum(dim=1)
-        n_img = torch.tensor(counts, dtype=torch.int64, device=dev)
-        limit = torch.where(kcols < n_img, kcols, n_img)
-        limit = torch.where(torch.tensor(skip, device=dev), torch.zeros_like(limit), limit)
-        d_limit = limit.to(torch.int32).contiguous()
-        flags = torch.empty(n, dtype=torch.int32, device=dev)
-        area = torch.empty(n, dtype=torch.int64, device=dev)
-        nruns = torch.empty(n, dtype=torch.int64, device=dev)
-        _lib.check(L.uwcv_clean_masks(_ptr(ws), ws.numel(), n, H, W, _ptr(d_slot), _ptr(d_inst),
-                                      _ptr(d_limit), _ptr(flags), _ptr(area), _ptr(nruns), st),
-                   "uwcv_clean_masks")
+        d_limit, flags, area, nruns = _clean_on_workspace(eng, n, H, W, d_slot, d_inst, counts, skip,
+                                                          min_crys_size)
         run_off = torch.zeros(n + 1, dtype=torch.int64, device=dev)
         torch.cumsum(nruns, 0, out=run_off[1:])
         total = int(run_off[-1].item())
         runs = torch.empty((max(total, 1), 2), dtype=torch.int64, device=dev)
         _lib.check(L.uwcv_rle_write(_ptr(ws), ws.numel(), n, H, W, _ptr(run_off), _ptr(runs), st),
                    "uwcv_rle_write")
-        eng.launches += 4
+        eng.launches += 1
         h_runs = runs[:total].cpu().numpy()
         h_off = run_off.cpu().numpy()
         h_flags = flags.cpu().numpy()
