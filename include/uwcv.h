@@ -84,7 +84,7 @@ size_t uwcv_workspace_bytes(int64_t N, int64_t tile_words);
  *   rows_f     [N, UWCV_NUM_FLOAT] float64 out
  *   workspace / ws_bytes   >= uwcv_workspace_bytes(N, tile_words)
  *   status     [4] int64 out (device): [0] 0 or UWCV_E_CAPACITY, [1] tile words needed,
- *              [2] tile rows needed, [3] reserved.  On E_CAPACITY no row is written.
+ *              [2] tile rows needed, [3] number of tiles above the one-instance-per-warp limit.  On E_CAPACITY no row is written.
  */
 int uwcv_paste_measure(const float* masks, const float* boxes, const int32_t* image_idx,
                        const int32_t* inst_idx, const int64_t* classes, const float* scores,

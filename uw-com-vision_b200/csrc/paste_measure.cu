@@ -23,6 +23,10 @@
 
 namespace uwcv {
 
+// rows-only contract: tiles up to this many words are pasted one instance per WARP
+// (tile_measure_kernel), larger ones by a whole CTA (paste_measure_kernel<false>, only_big)
+constexpr int kBigTileWords = 2048;
+
 // ---------------------------------------------------------------------------------
 // kernel 0: tile geometry + exclusive prefix sums (two passes over ceil(N / 1024) CTAs)
 // ---------------------------------------------------------------------------------
@@ -71,7 +75,8 @@ __device__ __forceinline__ void block_scan2(int64_t& a, int64_t& b, int64_t& tot
 // pass A: one instance per thread -- geometry, CTA-local exclusive offsets, CTA totals
 __global__ void __launch_bounds__(kLayoutThreads)
 layout_local_kernel(const float* __restrict__ boxes, int64_t n, int H, int W,
-                    TileDesc* __restrict__ desc, int64_t* __restrict__ block_sums) {
+                    TileDesc* __restrict__ desc, int64_t* __restrict__ block_sums,
+                    int64_t* __restrict__ big_tiles) {
   __shared__ int64_t s_words[kLayoutThreads];
   __shared__ int64_t s_rows[kLayoutThreads];
   const int64_t i = (int64_t)blockIdx.x * kLayoutThreads + threadIdx.x;
@@ -89,6 +94,10 @@ layout_local_kernel(const float* __restrict__ boxes, int64_t n, int H, int W,
     block_sums[2 * blockIdx.x] = tw_total;
     block_sums[2 * blockIdx.x + 1] = tr_total;
   }
+  // tiles too large for the one-instance-per-warp kernel of the rows-only contract
+  const int big = __syncthreads_count(i < n && (int64_t)tw * th > kBigTileWords);
+  if (threadIdx.x == 0 && big) atomicAdd(reinterpret_cast<unsigned long long*>(big_tiles),
+                                         (unsigned long long)big);
 }
 
 // pass B: every CTA sums the totals of the CTAs before it and rebases its descriptors;
@@ -178,6 +187,92 @@ __device__ __forceinline__ float sigmoid_as_torch(float a) {
   return __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-a)));
 }
 
+// Raw moments / pixel bbox accumulated by one lane (reduced over the warp afterwards)
+struct TileAcc {
+  long long m00 = 0, m10 = 0, m01 = 0, m20 = 0, m11 = 0, m02 = 0, m30 = 0, m21 = 0, m12 = 0, m03 = 0;
+  int xmin = INT_MAX, xmax = -1, ymin = INT_MAX, ymax = -1;
+};
+
+// One warp pastes the 32 tile rows starting at rbase: lane = column inside each 32-pixel strip,
+// rows broadcast by shuffle, __ballot_sync packs a row of 32 pixels into a word; the same bits
+// feed the per-lane column sums that fold into the raw moments.
+template <bool kPlanes>
+__device__ __forceinline__ void paste_rows(const TileDesc& d, int rbase, const float* __restrict__ mk,
+                                           float bx0, float by0, float bx1, float by1, float thr,
+                                           int W, int wpr, uint32_t* __restrict__ plane,
+                                           uint32_t* __restrict__ tM, int lane, TileAcc& a) {
+  int rowb; float rn, rs;
+  axis_coord(d.y0 + rbase + lane, by0, by1, rowb, rn, rs);
+  rowb *= kMaskPitch;
+  const int nrows = min(32, d.th - rbase);
+  for (int strip = 0; strip < d.tw; ++strip) {
+    const int px = (d.wx0 + strip) * 32 + lane;
+    int colb; float cw, ce;
+    axis_coord(px, bx0, bx1, colb, cw, ce);
+    const bool col_ok = px < W;
+    int S0 = 0, S1 = 0, S2 = 0, S3 = 0;
+    uint32_t myword = 0;
+#pragma unroll 4
+    for (int j = 0; j < 32; ++j) {
+      const int rb = __shfl_sync(0xffffffffu, rowb, j);
+      const float n_ = __shfl_sync(0xffffffffu, rn, j);
+      const float s_ = __shfl_sync(0xffffffffu, rs, j);
+      const float* mp = mk + rb + colb;
+      const float v_nw = mp[0], v_ne = mp[1], v_sw = mp[kMaskPitch], v_se = mp[kMaskPitch + 1];
+      const float nw = __fmul_rn(s_, ce), ne = __fmul_rn(s_, cw);
+      const float sw = __fmul_rn(n_, ce), se = __fmul_rn(n_, cw);
+      float out = __fmul_rn(v_nw, nw);
+      out = __fmaf_rn(v_ne, ne, out);
+      out = __fmaf_rn(v_sw, sw, out);
+      out = __fmaf_rn(v_se, se, out);
+      const bool bit = (out >= thr) && col_ok && (j < nrows);
+      const uint32_t word = __ballot_sync(0xffffffffu, bit);
+      if (lane == j) myword = word;
+      const int b = bit ? 1 : 0;
+      S0 += b; S1 += b * j; S2 += b * j * j; S3 += b * j * j * j;
+    }
+    // lane r holds the word of row rbase + r
+    if (lane < nrows) {
+      const int64_t o = (int64_t)(rbase + lane) * d.tw + strip;
+      tM[o] = myword;
+      if (kPlanes) plane[(int64_t)(d.y0 + rbase + lane) * wpr + d.wx0 + strip] = myword;
+      if (myword) { a.ymin = min(a.ymin, d.y0 + rbase + lane); a.ymax = max(a.ymax, d.y0 + rbase + lane); }
+    }
+    if (S0) {
+      // column sums over the 32 rows, shifted to frame coordinates (exact integers)
+      const long long yb = d.y0 + rbase, x = px;
+      const long long T0 = S0;
+      const long long T1 = S1 + yb * S0;
+      const long long T2 = S2 + 2 * yb * S1 + yb * yb * S0;
+      const long long T3 = S3 + 3 * yb * S2 + 3 * yb * yb * S1 + yb * yb * yb * S0;
+      const long long x2 = x * x, x3 = x2 * x;
+      a.m00 += T0; a.m10 += x * T0; a.m20 += x2 * T0; a.m30 += x3 * T0;
+      a.m01 += T1; a.m11 += x * T1; a.m21 += x2 * T1;
+      a.m02 += T2; a.m12 += x * T2;
+      a.m03 += T3;
+      a.xmin = min(a.xmin, px); a.xmax = max(a.xmax, px);
+    }
+  }
+}
+
+// mask source of one instance staged into a zero-framed 32 x 32 copy by `nthreads` threads
+__device__ __forceinline__ void stage_mask(const float* __restrict__ masks, const int64_t* __restrict__ classes,
+                                           int64_t inst, const MaskSource& src, float* __restrict__ mk,
+                                           int t, int nthreads) {
+  // probabilities as given, or (single-forward path) the predicted class's channel of the
+  // mask head's logits with the sigmoid of mask_rcnn_inference applied on the way in
+  int64_t chan = 0;
+  if (src.channels > 1) chan = (classes ? classes[inst] : 0) + src.channel_offset;
+  const bool chan_ok = chan >= 0 && chan < src.channels;       // bad class id: empty mask
+  const float* msrc = masks + inst * src.stride + (chan_ok ? chan : 0) * (kMaskSide * kMaskSide);
+  for (int k = t; k < kMaskSide * kMaskSide; k += nthreads) {
+    int r = k / kMaskSide, c = k - r * kMaskSide;
+    float v = chan_ok ? __ldg(msrc + k) : 0.f;
+    if (src.logits) v = chan_ok ? sigmoid_as_torch(v) : 0.f;
+    mk[(r + kPad) * kMaskPitch + c + kPad] = v;
+  }
+}
+
 template <bool kPlanes>
 __global__ void __launch_bounds__(kPasteThreads, 3)
 paste_measure_kernel(const float* __restrict__ masks, const float* __restrict__ boxes,
@@ -185,7 +280,8 @@ paste_measure_kernel(const float* __restrict__ masks, const float* __restrict__ 
                      const int64_t* __restrict__ classes, int64_t n, int H, int W, float thr,
                      uint32_t* __restrict__ planes, int64_t* __restrict__ rows_i,
                      Workspace ws, const int64_t* __restrict__ status, int zero_bytes,
-                     int rot_mul, int fill_mode, int debug_skip, int64_t first, MaskSource src) {
+                     int rot_mul, int fill_mode, int debug_skip, int64_t first, MaskSource src,
+                     int only_big) {
   extern __shared__ __align__(128) unsigned char s_zero[];     // zero_bytes (planes only)
   __shared__ __align__(16) float s_mask[kMaskPitch * kMaskPitch];
   __shared__ unsigned long long s_acc[10];
@@ -193,6 +289,7 @@ paste_measure_kernel(const float* __restrict__ masks, const float* __restrict__ 
   __shared__ long long s_next[2];
 
   if (status[0] != 0) return;                       // layout overflowed the workspace
+  if (only_big && status[3] == 0) return;           // nothing left for the whole-CTA pass
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int wpr = plane_row_words(W);
@@ -263,6 +360,11 @@ paste_measure_kernel(const float* __restrict__ masks, const float* __restrict__ 
     long long claim = 0;
     if (tid == 0) claim = first + atomicAdd(&ws.sched[1], 1u);
     const TileDesc d = ws.desc[inst];
+    if (only_big && (int64_t)d.tw * d.th <= kBigTileWords) {     // done by tile_measure_kernel
+      if (tid == 0) s_next[(it + 1) & 1] = claim;
+      compute_barrier();
+      continue;
+    }
     const float bx0 = boxes[4 * inst + 0], by0 = boxes[4 * inst + 1];
     const float bx1 = boxes[4 * inst + 2], by1 = boxes[4 * inst + 3];
     uint32_t* plane = kPlanes ? planes + inst * plane_words : nullptr;
@@ -288,83 +390,20 @@ paste_measure_kernel(const float* __restrict__ masks, const float* __restrict__ 
     }
 
     // ---- stage the 28x28 probabilities into the zero-framed copy --------------------
-    // probabilities as given, or (single-forward path) the predicted class's channel of the
-    // mask head's logits with the sigmoid of mask_rcnn_inference applied on the way in
-    int64_t chan = 0;
-    if (src.channels > 1) chan = (classes ? classes[inst] : 0) + src.channel_offset;
-    const bool chan_ok = chan >= 0 && chan < src.channels;       // bad class id: empty mask
-    const float* msrc = masks + inst * src.stride + (chan_ok ? chan : 0) * (kMaskSide * kMaskSide);
-    for (int k = tid; k < kMaskSide * kMaskSide; k += kComputeThreads) {
-      int r = k / kMaskSide, c = k - r * kMaskSide;
-      float v = chan_ok ? __ldg(msrc + k) : 0.f;
-      if (src.logits) v = chan_ok ? sigmoid_as_torch(v) : 0.f;
-      s_mask[(r + kPad) * kMaskPitch + c + kPad] = v;
-    }
+    stage_mask(masks, classes, inst, src, s_mask, tid, kComputeThreads);
     if (tid < 10) s_acc[tid] = 0ull;
     if (tid == 0) { s_bbox[0] = INT_MAX; s_bbox[1] = INT_MAX; s_bbox[2] = -1; s_bbox[3] = -1; }
     compute_barrier();
 
     // ---- the tile: each warp takes groups of 32 rows --------------------------------
-    long long m00 = 0, m10 = 0, m01 = 0, m20 = 0, m11 = 0, m02 = 0, m30 = 0, m21 = 0, m12 = 0,
-              m03 = 0;
-    int xmin = INT_MAX, xmax = -1, ymin = INT_MAX, ymax = -1;
     uint32_t* tM = ws.M + d.word_off;
 
-    for (int g = warp; g * 32 < d.th && !(debug_skip & 1); g += kPasteWarps) {
-      const int rbase = g * 32;
-      int rowb; float rn, rs;
-      axis_coord(d.y0 + rbase + lane, by0, by1, rowb, rn, rs);
-      rowb *= kMaskPitch;
-      const int nrows = min(32, d.th - rbase);
-      for (int strip = 0; strip < d.tw; ++strip) {
-        const int px = (d.wx0 + strip) * 32 + lane;
-        int colb; float cw, ce;
-        axis_coord(px, bx0, bx1, colb, cw, ce);
-        const bool col_ok = px < W;
-        int S0 = 0, S1 = 0, S2 = 0, S3 = 0;
-        uint32_t myword = 0;
-#pragma unroll 4
-        for (int j = 0; j < 32; ++j) {
-          const int rb = __shfl_sync(0xffffffffu, rowb, j);
-          const float n_ = __shfl_sync(0xffffffffu, rn, j);
-          const float s_ = __shfl_sync(0xffffffffu, rs, j);
-          const float* mp = s_mask + rb + colb;
-          const float v_nw = mp[0], v_ne = mp[1], v_sw = mp[kMaskPitch], v_se = mp[kMaskPitch + 1];
-          const float nw = __fmul_rn(s_, ce), ne = __fmul_rn(s_, cw);
-          const float sw = __fmul_rn(n_, ce), se = __fmul_rn(n_, cw);
-          float out = __fmul_rn(v_nw, nw);
-          out = __fmaf_rn(v_ne, ne, out);
-          out = __fmaf_rn(v_sw, sw, out);
-          out = __fmaf_rn(v_se, se, out);
-          const bool bit = (out >= thr) && col_ok && (j < nrows);
-          const uint32_t word = __ballot_sync(0xffffffffu, bit);
-          if (lane == j) myword = word;
-          const int b = bit ? 1 : 0;
-          S0 += b; S1 += b * j; S2 += b * j * j; S3 += b * j * j * j;
-        }
-        // lane r holds the word of row rbase + r
-        if (lane < nrows) {
-          const int64_t o = (int64_t)(rbase + lane) * d.tw + strip;
-          tM[o] = myword;
-          if (kPlanes) plane[(int64_t)(d.y0 + rbase + lane) * wpr + d.wx0 + strip] = myword;
-          if (myword) { ymin = min(ymin, d.y0 + rbase + lane); ymax = max(ymax, d.y0 + rbase + lane); }
-        }
-        if (S0) {
-          // column sums over the 32 rows, shifted to frame coordinates (exact integers)
-          const long long yb = d.y0 + rbase, x = px;
-          const long long T0 = S0;
-          const long long T1 = S1 + yb * S0;
-          const long long T2 = S2 + 2 * yb * S1 + yb * yb * S0;
-          const long long T3 = S3 + 3 * yb * S2 + 3 * yb * yb * S1 + yb * yb * yb * S0;
-          const long long x2 = x * x, x3 = x2 * x;
-          m00 += T0; m10 += x * T0; m20 += x2 * T0; m30 += x3 * T0;
-          m01 += T1; m11 += x * T1; m21 += x2 * T1;
-          m02 += T2; m12 += x * T2;
-          m03 += T3;
-          xmin = min(xmin, px); xmax = max(xmax, px);
-        }
-      }
-    }
+    TileAcc ta;
+    for (int g = warp; g * 32 < d.th && !(debug_skip & 1); g += kPasteWarps)
+      paste_rows<kPlanes>(d, g * 32, s_mask, bx0, by0, bx1, by1, thr, W, wpr, plane, tM, lane, ta);
+    const long long m00 = ta.m00, m10 = ta.m10, m01 = ta.m01, m20 = ta.m20, m11 = ta.m11, m02 = ta.m02,
+                    m30 = ta.m30, m21 = ta.m21, m12 = ta.m12, m03 = ta.m03;
+    int xmin = ta.xmin, xmax = ta.xmax, ymin = ta.ymin, ymax = ta.ymax;
     // ---- warp-shuffle reduction, one shared-memory atomic per warp and moment -------
     long long acc[10] = {m00, m10, m01, m20, m11, m02, m30, m21, m12, m03};
 #pragma unroll
@@ -418,6 +457,99 @@ paste_measure_kernel(const float* __restrict__ masks, const float* __restrict__ 
   }
 }
 
+// ---------------------------------------------------------------------------------
+// rows-only contract (no full-frame planes): one instance per WARP
+// ---------------------------------------------------------------------------------
+// With a whole CTA per instance only ceil(th / 32) of the seven compute warps have rows to work
+// on (two for a 60-row tile) and every instance pays three CTA barriers: ~12 us of latency per
+// CTA and instance, 1.7 ms per 64 000 instances.  Here every warp claims instances on its own
+// (device-wide counter), stages the mask in its own zero-framed copy, pastes / packs / reduces and
+// writes the integer row without any CTA-level synchronisation: 0.75 ms.  Tiles above
+// kBigTileWords are left to the whole-CTA kernel.
+constexpr int kTileWarps = 8;
+
+__global__ void __launch_bounds__(kTileWarps * 32, 3)
+tile_measure_kernel(const float* __restrict__ masks, const float* __restrict__ boxes,
+                    const int32_t* __restrict__ image_idx, const int32_t* __restrict__ inst_idx,
+                    const int64_t* __restrict__ classes, int64_t n, int H, int W, float thr,
+                    int64_t* __restrict__ rows_i, Workspace ws, const int64_t* __restrict__ status,
+                    int64_t first, MaskSource src) {
+  __shared__ __align__(16) float s_mask[kTileWarps * kMaskPitch * kMaskPitch];
+  if (status[0] != 0) return;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int wpr = plane_row_words(W);
+  for (int k = tid; k < kTileWarps * kMaskPitch * kMaskPitch; k += kTileWarps * 32) s_mask[k] = 0.f;
+  __syncthreads();
+  float* mk = s_mask + warp * (kMaskPitch * kMaskPitch);
+  long long c0 = 0;
+  if (lane == 0) c0 = first + atomicAdd(&ws.sched[1], 1u);
+  int64_t inst = __shfl_sync(0xffffffffu, c0, 0);
+  while (inst < n) {
+    long long claim = 0;                               // travels under this instance's work
+    if (lane == 0) claim = first + atomicAdd(&ws.sched[1], 1u);
+    const TileDesc d = ws.desc[inst];
+    if ((int64_t)d.tw * d.th <= kBigTileWords) {
+      const float bx0 = boxes[4 * inst + 0], by0 = boxes[4 * inst + 1];
+      const float bx1 = boxes[4 * inst + 2], by1 = boxes[4 * inst + 3];
+      stage_mask(masks, classes, inst, src, mk, lane, 32);
+      __syncwarp();
+      TileAcc a;
+      uint32_t* tM = ws.M + d.word_off;
+      for (int rbase = 0; rbase < d.th; rbase += 32)
+        paste_rows<false>(d, rbase, mk, bx0, by0, bx1, by1, thr, W, wpr, nullptr, tM, lane, a);
+      long long acc[10] = {a.m00, a.m10, a.m01, a.m20, a.m11, a.m02, a.m30, a.m21, a.m12, a.m03};
+#pragma unroll
+      for (int k = 0; k < 10; ++k) {
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], off);
+      }
+      int xmin = a.xmin, xmax = a.xmax, ymin = a.ymin, ymax = a.ymax;
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) {
+        xmin = min(xmin, __shfl_xor_sync(0xffffffffu, xmin, off));
+        ymin = min(ymin, __shfl_xor_sync(0xffffffffu, ymin, off));
+        xmax = max(xmax, __shfl_xor_sync(0xffffffffu, xmax, off));
+        ymax = max(ymax, __shfl_xor_sync(0xffffffffu, ymax, off));
+      }
+      if (lane < kNumInt) {                            // lane = column of the integer row
+        long long v = 0;
+        const long long area = acc[0];
+        switch (lane) {
+          case I_IMAGE: v = image_idx ? image_idx[inst] : 0; break;
+          case I_INST:  v = inst_idx ? inst_idx[inst] : inst; break;
+          case I_CLASS: v = classes ? classes[inst] : 0; break;
+          case I_VALID: v = area > 0; break;
+          case I_NCONT: v = 0; break;
+          case I_AREA:  v = area; break;
+          case I_BX0: v = area > 0 ? xmin : -1; break;
+          case I_BY0: v = area > 0 ? ymin : -1; break;
+          case I_BX1: v = area > 0 ? xmax : -1; break;
+          case I_BY1: v = area > 0 ? ymax : -1; break;
+          case I_NPTS: v = 0; break;
+          case I_M10: v = acc[1]; break;
+          case I_M01: v = acc[2]; break;
+          case I_M20: v = acc[3]; break;
+          case I_M11: v = acc[4]; break;
+          case I_M02: v = acc[5]; break;
+          case I_M30: v = acc[6]; break;
+          case I_M21: v = acc[7]; break;
+          case I_M12: v = acc[8]; break;
+          default: v = acc[9]; break;                  // I_M03
+        }
+        rows_i[inst * kNumInt + lane] = v;
+      }
+      __syncwarp();                                    // the mask copy is rewritten next round
+    }
+    inst = __shfl_sync(0xffffffffu, claim, 0);
+  }
+  // the last CTA out re-arms the counters for the next launch on this workspace
+  __syncthreads();
+  if (tid == 0) {
+    const unsigned int done = atomicAdd(&ws.sched[2], 1u);
+    if (done == gridDim.x - 1) { ws.sched[0] = 0u; ws.sched[1] = 0u; ws.sched[2] = 0u; }
+  }
+}
+
 // pass C: the visited / sign planes of the border trace start at zero (only the words the
 // layout handed out: status[1], known on the device)
 __global__ void __launch_bounds__(256)
@@ -440,7 +572,9 @@ zero_marks_kernel(uint32_t* __restrict__ V, uint32_t* __restrict__ G,
 cudaError_t launch_layout(const float* boxes, int64_t n, int H, int W, const Workspace& ws,
                           int64_t* status, int num_sms, cudaStream_t stream) {
   const int nblk = (int)layout_blocks(n);
-  layout_local_kernel<<<nblk, kLayoutThreads, 0, stream>>>(boxes, n, H, W, ws.desc, ws.block_sums);
+  if (cudaMemsetAsync(status + 3, 0, sizeof(int64_t), stream) != cudaSuccess) return cudaGetLastError();
+  layout_local_kernel<<<nblk, kLayoutThreads, 0, stream>>>(boxes, n, H, W, ws.desc, ws.block_sums,
+                                                           status + 3);
   layout_rebase_kernel<<<nblk, kLayoutThreads, 0, stream>>>(n, nblk, ws.desc, ws.block_sums,
                                                             ws.cap_words, status, ws.sched);
   zero_marks_kernel<<<num_sms * 4, 256, 0, stream>>>(ws.V, ws.G, status);
@@ -484,14 +618,29 @@ cudaError_t launch_paste_measure(const float* masks, const float* boxes, const i
   }
   int64_t grid = (int64_t)num_sms * per_sm;           // persistent: a whole number of waves
   if (grid > count) grid = count;
-  if (planes)
+  if (planes) {
     paste_measure_kernel<true><<<(unsigned)grid, kPasteThreads, dyn, stream>>>(
         masks, boxes, image_idx, inst_idx, classes, n, H, W, thr, planes, rows_i, ws, status,
-        zero_bytes, rot_mul, fill_mode, debug_skip, first, src);
-  else
-    paste_measure_kernel<false><<<(unsigned)grid, kPasteThreads, dyn, stream>>>(
-        masks, boxes, image_idx, inst_idx, classes, n, H, W, thr, planes, rows_i, ws, status,
-        zero_bytes, rot_mul, fill_mode, debug_skip, first, src);
+        zero_bytes, rot_mul, fill_mode, debug_skip, first, src, 0);
+    return cudaPeekAtLastError();
+  }
+  // rows only: one instance per warp for ordinary tiles, then the whole-CTA kernel for the
+  // few giant ones (it returns at once when the layout counted none)
+  const bool per_warp = !getenv("UWCV_TILE_PER_CTA");                       // profiling only
+  if (per_warp) {
+    int tper = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&tper, tile_measure_kernel, kTileWarps * 32,
+                                                      0) != cudaSuccess || tper < 1)
+      tper = 2;
+    int64_t tgrid = (int64_t)num_sms * tper;
+    const int64_t need = (count + kTileWarps - 1) / kTileWarps;
+    if (tgrid > need) tgrid = need;
+    tile_measure_kernel<<<(unsigned)tgrid, kTileWarps * 32, 0, stream>>>(
+        masks, boxes, image_idx, inst_idx, classes, n, H, W, thr, rows_i, ws, status, first, src);
+  }
+  paste_measure_kernel<false><<<(unsigned)grid, kPasteThreads, dyn, stream>>>(
+      masks, boxes, image_idx, inst_idx, classes, n, H, W, thr, planes, rows_i, ws, status,
+      zero_bytes, rot_mul, fill_mode, debug_skip, first, src, per_warp ? 1 : 0);
   return cudaPeekAtLastError();
 }
 
