@@ -37,6 +37,10 @@ for case in range(n_cases):
         inst2.set(k, uwcv.Boxes(v.tensor[order]) if hasattr(v, "tensor") else v[order])
     inst = inst2
     table, planes = uwcv.measure_instances(inst, (H, W), return_planes=True)
+    rows_only = uwcv.measure_instances(inst, (H, W))       # no planes: one instance per warp
+    tot["rows_only_mismatch"] = tot.get("rows_only_mismatch", 0) + int(
+        not (np.array_equal(rows_only.ints, table.ints) and
+             np.array_equal(rows_only.floats, table.floats, equal_nan=True)))
     ri, rf = P.oracle_table([inst], (H, W))
     assert table.ints.shape == ri.shape, (case, table.ints.shape, ri.shape)
     tot["cases"] += 1; tot["instances"] += len(ri)
