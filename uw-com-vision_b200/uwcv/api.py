@@ -336,8 +336,9 @@ class Engine:
                 int(n - first if count is None else count),
                 C.byref(gather) if (gather is not None and (stages & 4)) else None)
         _lib.check(rc, "uwcv_paste_measure")
-        if n > 0:        # layout = 3 kernels, paste = 1, contour = 1
-            self.launches += 3 * (stages & 1) + ((stages >> 1) & 1) + ((stages >> 2) & 1)
+        if n > 0:        # layout = 3 kernels, paste = 1 (rows only: 2), contour = 1
+            self.launches += 3 * (stages & 1) + ((stages >> 1) & 1) * (1 if planes is not None else 2) \
+                + ((stages >> 2) & 1)
         return rows_i, rows_f, status
 
     def run_overlapped(self, masks, boxes, H, W, *, paste_ranges=None, after=None, **kw):
