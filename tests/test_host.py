@@ -246,3 +246,17 @@ def test_scale_clip_equals_detectron2_column_ops_and_words_bound():
         bx, _ = api.scale_clip_boxes(torch.cat((c, c + wh), 1), (256, 256), (256, 256))
         assert api.tile_words_bound(bx) >= api.tile_words(bx, 256, 256)
     assert api.tile_words_bound(torch.zeros((0, 4))) == 0
+
+
+def test_gather_struct_mirrors_the_header():
+    """ctypes mirror of `uwcv_gather` (include/uwcv.h): 16 peers, pointer arrays after two
+    32-bit fields and the 64-bit row base."""
+    import ctypes as C
+    import re
+    from uwcv import _lib
+    hdr = open(os.path.join(ROOT, "include", "uwcv.h")).read()
+    peers = int(re.search(r"#define\s+UWCV_MAX_PEERS\s+(\d+)", hdr).group(1))
+    assert peers == _lib.MAX_PEERS
+    assert C.sizeof(_lib.Gather) == 4 + 4 + 8 + 2 * peers * 8
+    assert _lib.Gather.row_base.offset == 8
+    assert _lib.Gather.rows_i.offset == 16 and _lib.Gather.rows_f.offset == 16 + peers * 8
