@@ -281,8 +281,8 @@ paste_measure_kernel(const float* __restrict__ masks, const float* __restrict__ 
                      uint32_t* __restrict__ planes, int64_t* __restrict__ rows_i,
                      Workspace ws, const int64_t* __restrict__ status, int zero_bytes,
                      int rot_mul, int fill_mode, int debug_skip, int64_t first, MaskSource src,
-                     int only_big) {
-  extern __shared__ __align__(128) unsigned char s_zero[];     // zero_bytes (planes only)
+                     int only_big, int band_bytes_cap) {
+  extern __shared__ __align__(128) unsigned char s_zero[];     // zero_bytes (+ band buffer) (planes only)
   __shared__ __align__(16) float s_mask[kMaskPitch * kMaskPitch];
   __shared__ unsigned long long s_acc[10];
   __shared__ int s_bbox[4];
@@ -298,8 +298,13 @@ paste_measure_kernel(const float* __restrict__ masks, const float* __restrict__ 
   if (kPlanes) {
     for (int k = tid; k < zero_bytes / 16; k += kPasteThreads)
       reinterpret_cast<uint4*>(s_zero)[k] = make_uint4(0, 0, 0, 0);
+    // band buffer behind the zero source: the tile band of one instance is composed here
+    // (zeros + tile words) and leaves through a TMA bulk store as well
+    for (int k = tid; k < band_bytes_cap / 16; k += kPasteThreads)
+      reinterpret_cast<uint4*>(s_zero + zero_bytes)[k] = make_uint4(0, 0, 0, 0);
     fence_proxy_async_smem();                       // generic-proxy zeros -> visible to TMA
   }
+  uint32_t* s_band = reinterpret_cast<uint32_t*>(s_zero + zero_bytes);
   // the frame of the padded mask stays zero for the whole kernel
   for (int k = tid; k < kMaskPitch * kMaskPitch; k += kPasteThreads) s_mask[k] = 0.f;
   __syncthreads();
@@ -383,7 +388,9 @@ paste_measure_kernel(const float* __restrict__ masks, const float* __restrict__ 
 
     // ---- zero the band rows: whole rows as 16-byte stores (complete sectors); the tile words
     //      are stored over them after the barrier below
-    if (kPlanes && d.th > 0 && !(debug_skip & 2)) {
+    const int band_bytes = d.th * wpr * 4;
+    const bool band_tma = kPlanes && d.th > 0 && band_bytes <= band_bytes_cap;
+    if (kPlanes && d.th > 0 && !band_tma && !(debug_skip & 2)) {
       uint4* band = reinterpret_cast<uint4*>(plane + (int64_t)d.y0 * wpr);
       const int total = d.th * (wpr / 4);
       for (int k = tid; k < total; k += kComputeThreads) band[k] = make_uint4(0, 0, 0, 0);
@@ -400,7 +407,10 @@ paste_measure_kernel(const float* __restrict__ masks, const float* __restrict__ 
 
     TileAcc ta;
     for (int g = warp; g * 32 < d.th && !(debug_skip & 1); g += kPasteWarps)
-      paste_rows<kPlanes>(d, g * 32, s_mask, bx0, by0, bx1, by1, thr, W, wpr, plane, tM, lane, ta);
+      paste_rows<kPlanes>(d, g * 32, s_mask, bx0, by0, bx1, by1, thr, W, wpr,
+                          // band composed in shared memory: row y of the plane is row y - y0 of it
+                          band_tma ? s_band - (int64_t)d.y0 * wpr : plane, tM, lane, ta);
+    if (band_tma) fence_proxy_async_smem();           // my tile words -> visible to the TMA
     const long long m00 = ta.m00, m10 = ta.m10, m01 = ta.m01, m20 = ta.m20, m11 = ta.m11, m02 = ta.m02,
                     m30 = ta.m30, m21 = ta.m21, m12 = ta.m12, m03 = ta.m03;
     int xmin = ta.xmin, xmax = ta.xmax, ymin = ta.ymin, ymax = ta.ymax;
@@ -446,6 +456,21 @@ paste_measure_kernel(const float* __restrict__ masks, const float* __restrict__ 
       rows_i[inst * kNumInt + tid] = v;
     }
     if (tid == 0) s_next[(it + 1) & 1] = claim;
+    if (band_tma) {
+      // (the barrier after the reduction ordered every warp's tile words before this point)
+      if (tid == 0) {
+        bulk_store_zero(plane + (int64_t)d.y0 * wpr, (uint32_t)__cvta_generic_to_shared(s_band),
+                        (uint32_t)band_bytes);
+        bulk_commit();
+        bulk_wait_read_all();                          // the buffer is reused for the next band
+      }
+      compute_barrier();
+      for (int k = tid; k < d.th * d.tw; k += kComputeThreads) {     // back to all zeros
+        const int r = k / d.tw, c = k - r * d.tw;
+        s_band[r * wpr + d.wx0 + c] = 0u;
+      }
+      fence_proxy_async_smem();
+    }
     compute_barrier();                                 // s_mask / s_acc are rewritten next round
   }
   }
@@ -598,7 +623,10 @@ cudaError_t launch_paste_measure(const float* masks, const float* boxes, const i
   if (const char* v = getenv("UWCV_ZERO_KB")) zero_bytes = atoi(v) * 1024;
   if (const char* v = getenv("UWCV_PASTE_ROT")) rot_mul = atoi(v);
   if (zero_bytes < 1024 || zero_bytes > 160 * 1024 || (zero_bytes & 1023)) zero_bytes = kZeroBytesDefault;
-  const size_t dyn = planes ? (size_t)zero_bytes : 0;
+  int band_cap = 36 * 1024;                          // tile band composed in shared memory up to this size
+  if (const char* v = getenv("UWCV_BAND_KB")) band_cap = atoi(v) * 1024;       // 0: generic stores
+  if (band_cap < 0 || band_cap > 96 * 1024 || !planes) band_cap = 0;
+  const size_t dyn = planes ? (size_t)zero_bytes + band_cap : 0;
   if (planes) {
     if (dyn > 40 * 1024)
       cudaFuncSetAttribute(paste_measure_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -621,7 +649,7 @@ cudaError_t launch_paste_measure(const float* masks, const float* boxes, const i
   if (planes) {
     paste_measure_kernel<true><<<(unsigned)grid, kPasteThreads, dyn, stream>>>(
         masks, boxes, image_idx, inst_idx, classes, n, H, W, thr, planes, rows_i, ws, status,
-        zero_bytes, rot_mul, fill_mode, debug_skip, first, src, 0);
+        zero_bytes, rot_mul, fill_mode, debug_skip, first, src, 0, band_cap);
     return cudaPeekAtLastError();
   }
   // rows only: one instance per warp for ordinary tiles, then the whole-CTA kernel for the
@@ -640,7 +668,7 @@ cudaError_t launch_paste_measure(const float* masks, const float* boxes, const i
   }
   paste_measure_kernel<false><<<(unsigned)grid, kPasteThreads, dyn, stream>>>(
       masks, boxes, image_idx, inst_idx, classes, n, H, W, thr, planes, rows_i, ws, status,
-      zero_bytes, rot_mul, fill_mode, debug_skip, first, src, per_warp ? 1 : 0);
+      zero_bytes, rot_mul, fill_mode, debug_skip, first, src, per_warp ? 1 : 0, 0);
   return cudaPeekAtLastError();
 }
 
