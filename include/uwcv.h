@@ -235,7 +235,7 @@ int uwcv_union_measure(const void* paste_workspace, size_t paste_ws_bytes, int64
 
 /*
  * Mask clean-up + RLE export -- stands in for postprocess_masks
- * (nn_inference.py:259-302) and rle_encoding (:247-257) of the reference's export loop (:315-336).
+ * (nn_inference.py:265-306) and rle_encoding (:253-263) of the reference's export loop (:319-336).
  *
  * Call order on one stream: uwcv_paste_measure_stages(stages = 3) -> [uwcv_mask_column_totals,
  * host decides `limit`] -> uwcv_clean_masks -> exclusive scan of run_counts (caller) ->
@@ -268,7 +268,7 @@ int uwcv_rle_write(const void* paste_workspace, size_t ws_bytes, int64_t N, int 
                    const int64_t* run_offsets, int64_t* runs, void* stream);
 
 /*
- * Literal postprocess_masks(ori_mask, ...) entry (nn_inference.py:259, called at :325-327 with
+ * Literal postprocess_masks(ori_mask, ...) entry (nn_inference.py:265, called at :325-327 with
  * Detectron2's pasted pred_masks): N x H x W bool / uint8 masks in, cleaned masks out.
  *   uwcv_mask_pixel_boxes: boxes [N, 4] float32 = [xmin, ymin, xmax + 1, ymax + 1] of the set
  *     pixels of every mask (zeros for an empty one): feed them to uwcv_paste_measure_stages

@@ -1,11 +1,11 @@
 """Oracle restatement of the reference's mask clean-up + RLE export (TEST INFRASTRUCTURE).
 
 Follows /root/reference/nn_inference.py:
-  * ``rle_decode``        :231-245
-  * ``rle_encoding``      :247-257  (column-major, 1-based (start, length) pairs)
-  * ``postprocess_masks`` :259-302  (fill holes, dilate + erode, remove overlaps in list order,
+  * ``rle_decode``        :237-251
+  * ``rle_encoding``      :253-263  (column-major, 1-based (start, length) pairs)
+  * ``postprocess_masks`` :265-306  (fill holes, dilate + erode, remove overlaps in list order,
                                      drop masks that fall into more than one piece)
-  * the export loop       :315-336  (one ``ImageId, EncodedPixels`` row per returned mask)
+  * the export loop       :319-336  (one ``ImageId, EncodedPixels`` row per returned mask)
 
 Third-party pieces the reference calls and this image does not have (scikit-image, unpinned in
 the reference) are restated through the SciPy routines scikit-image itself wraps:
@@ -26,7 +26,7 @@ The quirks of the reference are kept (they are what its output is):
     leaves a W-vector; ``keep_ind`` therefore counts image COLUMNS holding more than
     ``min_crys_size`` mask pixels, and when there are fewer such columns than instances the
     instance list is truncated to that many entries (:277-284);
-  * ``overlap`` accumulates the cleaned masks before their own overlaps are cut (:294-295).
+  * ``overlap`` accumulates the cleaned masks before their own overlaps are cut (:297-298).
 """
 from __future__ import annotations
 
@@ -40,7 +40,7 @@ _FULL = np.ones((3, 3), dtype=bool)
 
 
 def rle_decode(mask_rle: str, shape: Tuple[int, int]) -> np.ndarray:
-    """nn_inference.py:231-245."""
+    """nn_inference.py:237-251."""
     s = mask_rle.split()
     starts, lengths = [np.asarray(x, dtype=int) for x in (s[0:][::2], s[1:][::2])]
     starts -= 1
@@ -52,7 +52,7 @@ def rle_decode(mask_rle: str, shape: Tuple[int, int]) -> np.ndarray:
 
 
 def rle_encoding(x: np.ndarray) -> List[int]:
-    """nn_inference.py:247-257 (vectorised: same list)."""
+    """nn_inference.py:253-263 (vectorised: same list)."""
     dots = np.where(x.T.flatten() == 1)[0]
     if dots.size == 0:
         return []
@@ -66,7 +66,7 @@ def rle_encoding(x: np.ndarray) -> List[int]:
 
 
 def rle_encoding_literal(x: np.ndarray) -> List[int]:
-    """The loop exactly as written (:247-257); used to pin the vectorised form."""
+    """The loop exactly as written (:253-263); used to pin the vectorised form."""
     dots = np.where(x.T.flatten() == 1)[0]
     run_lengths: List[int] = []
     prev = -2
@@ -92,7 +92,7 @@ def label_count(mask: np.ndarray) -> int:
 
 def postprocess_masks(ori_mask: np.ndarray, ori_score: np.ndarray, image_hw: Tuple[int, int],
                       min_crys_size: int = 2) -> Optional[List[np.ndarray]]:
-    """nn_inference.py:259-302.  ``ori_mask`` N x H x W bool, ``ori_score`` N float."""
+    """nn_inference.py:265-306.  ``ori_mask`` N x H x W bool, ``ori_score`` N float."""
     height, width = image_hw
     score_threshold = 0.5
     if len(ori_mask) == 0 or ori_score.all() < score_threshold:
@@ -120,8 +120,8 @@ def postprocess_masks(ori_mask: np.ndarray, ori_score: np.ndarray, image_hw: Tup
 
 def export_rows(names: Sequence[str], masks_per_image: Sequence[np.ndarray],
                 scores_per_image: Sequence[np.ndarray], image_hw: Tuple[int, int]):
-    """nn_inference.py:315-332: (ImageId, EncodedPixels) rows of a folder of images."""
-    conv = lambda l: ' '.join(map(str, l))          # noqa: E731  (:313)
+    """nn_inference.py:319-332: (ImageId, EncodedPixels) rows of a folder of images."""
+    conv = lambda l: ' '.join(map(str, l))          # noqa: E731  (:317)
     img_id, encoded = [], []
     for name, m, s in zip(names, masks_per_image, scores_per_image):
         masks = postprocess_masks(np.asarray(m), np.asarray(s), image_hw)

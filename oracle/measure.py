@@ -286,8 +286,17 @@ def instance_rows(bool_masks: Iterable, classes: np.ndarray, scores: np.ndarray,
 # report layer  (nn_inference.py:500-570)
 # --------------------------------------------------------------------------
 
+# Entry types of the nine lists in CSV column order, as the reference's own code produces them
+# (observed by executing nn_inference.py:371-459, oracle/ref_exec.py): imutils' order_points
+# returns float32, so dA / dB and everything divided from them is np.float32; ``np.sqrt`` yields
+# np.float64; the rest stays a Python float.
+CSV_ENTRY_TYPES = [np.float32, np.float32, np.float32, float, np.float64,
+                   np.float32, np.float32, np.float64, float]
+
+
 def moving_average(lst: Sequence[float], window_size: int = 3) -> List[float]:
-    """:523-527 -- window mean rounded to 2 dp (Python ``round``)."""
+    """:523-527 -- window mean rounded to 2 dp with ``round`` (np.round for NumPy scalars,
+    Python's for floats); the arithmetic runs in the type of the list entries."""
     out = []
     i = 0
     while i < (len(lst) - window_size + 1):
@@ -297,12 +306,30 @@ def moving_average(lst: Sequence[float], window_size: int = 3) -> List[float]:
     return out
 
 
+def typed_lists(rows: np.ndarray) -> List[list]:
+    """K x 9 float64 rows -> the nine lists holding the reference's scalar types."""
+    rows = np.asarray(rows, dtype=np.float64).reshape(-1, len(CSV_COLUMNS))
+    return [[t(v) for v in rows[:, j]] for j, t in enumerate(CSV_ENTRY_TYPES)]
+
+
 def report_class(rows: np.ndarray, window_size: int = 3):
     """rows K x 9 in CSV column order -> (smoothed rows K' x 9, {column: np.histogram})."""
-    cols = [moving_average(list(rows[:, j]), window_size) for j in range(rows.shape[1])]
-    sm = np.array(cols, dtype=np.float64).T.reshape(-1, rows.shape[1])
+    cols = [moving_average(lst, window_size) for lst in typed_lists(rows)]
+    sm = np.array([[float(v) for v in c] for c in cols], dtype=np.float64).T.reshape(-1, len(CSV_COLUMNS))
     hists = {}
     for j, name in enumerate(CSV_COLUMNS):
         if sm.shape[0]:
-            hists[name] = np.histogram(sm[:, j])
+            hists[name] = np.histogram(np.asarray(cols[j]))
     return sm, hists
+
+
+def shape_descriptor_text(rows: np.ndarray, window_size: int = 3) -> str:
+    """The text of ShapeDescriptor.csv (:554-559) for the rows of one class keyword."""
+    import csv
+    import io
+    cols = [moving_average(lst, window_size) for lst in typed_lists(rows)]
+    buf = io.StringIO()
+    w = csv.writer(buf)
+    for row in zip(*cols):
+        w.writerow(row)
+    return buf.getvalue().replace("\r\n", "\n")     # as read back in text mode

@@ -20,35 +20,7 @@ RTOL = 1e-5      # north_star tolerance for float measurements
 IC, FC = schema.ICOL, schema.FCOL
 
 
-def compare_tables(table, ri, rf, skip_int=()):
-    assert table.ints.shape == ri.shape and table.floats.shape == rf.shape
-    for name, j in IC.items():
-        if name in skip_int:
-            continue
-        bad = np.flatnonzero(table.ints[:, j] != ri[:, j])
-        assert bad.size == 0, f"int column {name}: {bad.size} rows differ, first {bad[:5]}: " \
-                              f"{table.ints[bad[:5], j]} vs {ri[bad[:5], j]}"
-    exact = 0
-    m00 = np.maximum(ri[:, IC["area_px"]].astype(np.float64), 1.0)
-    for name, j in FC.items():
-        a, b = table.floats[:, j], rf[:, j]
-        assert np.array_equal(np.isnan(a), np.isnan(b)), name
-        ok = ~np.isnan(b)
-        a, b = a[ok], b[ok]
-        exact += int(np.array_equal(a, b))
-        scale = np.abs(b)
-        if name in ("mu30", "mu21", "mu12", "mu03"):
-            # third-order central moments cancel to ~0 for symmetric blobs: floor at the
-            # rounding noise of the subtraction (|m_pq| * eps) relative to m00 * r^3
-            scale = np.maximum(scale, m00[ok] ** 2.5 * 1e-6)
-        if name in ("mu11", "ell_theta"):
-            scale = np.maximum(scale, 1e-6 * (m00[ok] ** 2 if name == "mu11" else 1.0))
-        err = np.abs(a - b)
-        lim = RTOL * scale + 1e-300
-        bad = np.flatnonzero(err > lim)
-        assert bad.size == 0, f"float column {name}: {bad.size} rows off, first {bad[:5]}: " \
-                              f"{a[bad[:5]]} vs {b[bad[:5]]}"
-    return exact
+from oracle.compare import compare_tables  # noqa: E402,F401  (the per-column parity rule)
 
 
 def plane_crcs(planes):

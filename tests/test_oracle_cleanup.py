@@ -1,5 +1,5 @@
 """CPU tests of the clean-up / RLE oracle (oracle/cleanup.py) against hand-checkable cases and
-the loops exactly as the reference writes them (nn_inference.py:231-302)."""
+the loops exactly as the reference writes them (nn_inference.py:237-306)."""
 import numpy as np
 import pytest
 

@@ -1,6 +1,6 @@
 // Mask clean-up + RLE export on the bit tiles.
 //
-// Replaces postprocess_masks (nn_inference.py:259-302) and rle_encoding (:247-257):
+// Replaces postprocess_masks (nn_inference.py:265-306) and rle_encoding (:253-263):
 //   for every instance of an image, in list (= score) order:
 //     mask = binary_fill_holes(mask)                       scipy: background 4-connected to the border stays
 //     mask = erosion(dilation(mask))                       skimage defaults: 3 x 3 cross, reflected border

@@ -12,7 +12,7 @@ from .api import (Engine, MeasurementTable, MeasurementStream, PendingTable,
                   detector_postprocess, fast_rcnn_inference_single_image, get_counts,
                   scale_clip_boxes, tile_words)
 from .grouping import (group_by_class, write_classes_csv, moving_average, report_class,  # noqa: F401
-                       write_results_csv)
+                       write_results_csv, write_shape_descriptor_csv, smoothed_columns)
 from .dist import (shard_indices, shard_instances_by_tile, take_instances,   # noqa: F401
                    all_gather_table, sort_rows)
 from .union import UnionTable, measure_union                  # noqa: F401
@@ -24,5 +24,5 @@ __all__ = [
     "submit_measure_instances", "measure_instances",
     "paste_masks_in_image", "detector_postprocess", "fast_rcnn_inference_single_image",
     "get_counts", "group_by_class", "write_classes_csv", "moving_average", "report_class",
-    "write_results_csv", "shard_indices", "shard_instances_by_tile", "take_instances", "all_gather_table", "sort_rows", "UnionTable", "measure_union", "SingleForward", "fast_rcnn_inference", "RleExport", "export_rle", "postprocess_masks", "write_rle_csv",
+    "write_results_csv", "write_shape_descriptor_csv", "smoothed_columns", "shard_indices", "shard_instances_by_tile", "take_instances", "all_gather_table", "sort_rows", "UnionTable", "measure_union", "SingleForward", "fast_rcnn_inference", "RleExport", "export_rle", "postprocess_masks", "write_rle_csv",
 ]

@@ -1,8 +1,8 @@
 """Mask clean-up + RLE export.
 
-Replaces the reference's export loop nn_inference.py:315-336 -- ``postprocess_masks``
-(:259-302: fill holes, dilate + erode, cut overlaps in score order, empty masks that fall into
-several pieces) and ``rle_encoding`` (:247-257: column-major, 1-based (start, length) pairs) --
+Replaces the reference's export loop nn_inference.py:319-336 -- ``postprocess_masks``
+(:265-306: fill holes, dilate + erode, cut overlaps in score order, empty masks that fall into
+several pieces) and ``rle_encoding`` (:253-263: column-major, 1-based (start, length) pairs) --
 and the ``R50_flip_.csv`` it writes (``ImageId, EncodedPixels``).
 
 ``export_rle`` takes the RAW predictor output (as ``measure_instances`` does), pastes the masks
@@ -72,7 +72,7 @@ def _clean_on_workspace(eng: Engine, n: int, H: int, W: int, d_slot, d_inst, cou
 
 def postprocess_masks(ori_mask, ori_score, image, min_crys_size: int = 2, *, device=None):
     """The reference's ``postprocess_masks(ori_mask, ori_score, image, min_crys_size=2)``
-    (nn_inference.py:259-302) with the same arguments and return value: ``ori_mask`` N x H x W
+    (nn_inference.py:265-306) with the same arguments and return value: ``ori_mask`` N x H x W
     bool (Detectron2's pasted ``pred_masks``, numpy or torch), ``ori_score`` N floats, ``image``
     the H x W (x C) image or its shape; returns ``None`` when there is no mask or a score is
     exactly zero (:274), else the list of cleaned H x W uint8 masks (possibly truncated, :277-284).
@@ -128,7 +128,7 @@ def export_rle(instances, output_size: Optional[Tuple[int, int]] = None,
 
     ``instances``: one ``Instances`` per image (or a single one) with the raw predictor output,
     in Detectron2's order (score descending) -- the order decides who keeps an overlap.
-    ``names``: image file names (``.tif`` is stripped for ``ImageId``, :330); default "0", "1", ...
+    ``names``: image file names (``.tif`` is stripped for ``ImageId``, :331); default "0", "1", ...
     """
     single = not isinstance(instances, (list, tuple))
     batch = [instances] if single else list(instances)
@@ -233,7 +233,7 @@ def export_rle(instances, output_size: Optional[Tuple[int, int]] = None,
 def write_rle_csv(path: str, export: RleExport) -> None:
     """``pd.DataFrame({"ImageId": ..., "EncodedPixels": ...}).to_csv(path, index=False)`` (:335-336)."""
     with open(path, "w", newline="") as f:
-        w = csv.writer(f)
+        w = csv.writer(f, lineterminator="\n")            # pandas' line terminator
         w.writerow(["ImageId", "EncodedPixels"])
         for a, b in zip(export.image_id, export.encoded_pixels):
             w.writerow([a, b])

@@ -14,7 +14,8 @@ from typing import Dict, List, Sequence
 
 import numpy as np
 
-from .schema import (CLASS_KEYWORDS, CLASS_NAMES, CSV_COLUMNS, CSV_SOURCE, FCOL, FLOAT_COLUMNS)
+from .schema import (CLASS_KEYWORDS, CLASS_NAMES, CSV_COLUMNS, CSV_KINDS, CSV_SOURCE, FCOL,
+                     FLOAT_COLUMNS)
 
 
 def group_by_class(table, min_contour_area: float = 100.0, num_classes: int = len(CLASS_NAMES)
@@ -48,21 +49,43 @@ def write_classes_csv(path: str, table, min_contour_area: float = 100.0) -> None
             w.writerow(r)
 
 
-def moving_average(values: Sequence[float], window_size: int = 3) -> List[float]:
-    """nn_inference.py:523-527: mean of each length-3 window, Python ``round(.., 2)``."""
-    vals = [float(v) for v in values]
+_KIND_TYPE = {"f32": np.float32, "f64": np.float64, "py": float}
+
+
+def moving_average(values: Sequence[float], window_size: int = 3, kind: str = "py") -> List:
+    """nn_inference.py:523-527: ``round(sum(window) / window_size, 2)`` of each length-3 window,
+    evaluated in the type the reference's list holds (``schema.CSV_KINDS``): np.float32 entries
+    sum, divide and round (np.round) in float32, np.float64 entries round with np.round, Python
+    floats with the correctly rounded built-in."""
+    t = _KIND_TYPE[kind]
+    vals = [t(v) for v in values]
     return [round(sum(vals[i:i + window_size]) / window_size, 2)
             for i in range(len(vals) - window_size + 1)]
 
 
+def smoothed_columns(rows: np.ndarray, window_size: int = 3) -> List[List]:
+    """The nine ``MA_*`` lists (:507-529) in CSV column order, entries typed as the reference's."""
+    rows = np.asarray(rows, dtype=np.float64).reshape(-1, len(CSV_COLUMNS))
+    return [moving_average(rows[:, j], window_size, CSV_KINDS[j]) for j in range(rows.shape[1])]
+
+
 def report_class(rows: np.ndarray, window_size: int = 3):
     """rows K x 9 in CSV column order -> (smoothed K-2 x 9 rows, {column: (hist, edges)})."""
-    rows = np.asarray(rows, dtype=np.float64).reshape(-1, len(CSV_COLUMNS))
-    cols = [moving_average(rows[:, j], window_size) for j in range(rows.shape[1])]
-    sm = np.array(cols, dtype=np.float64).T.reshape(-1, rows.shape[1])
-    hists = {name: np.histogram(sm[:, j]) for j, name in enumerate(CSV_COLUMNS)} \
+    cols = smoothed_columns(rows, window_size)
+    sm = np.array([[float(v) for v in c] for c in cols], dtype=np.float64).T.reshape(-1, len(CSV_COLUMNS))
+    hists = {name: np.histogram(np.asarray(cols[j])) for j, name in enumerate(CSV_COLUMNS)} \
         if sm.shape[0] else {}
     return sm, hists
+
+
+def write_shape_descriptor_csv(path: str, rows: np.ndarray, window_size: int = 3) -> None:
+    """``ShapeDescriptor.csv`` (:554-559): the smoothed rows through ``csv.writer`` -- the same
+    text as the reference's file, float32 entries printed as float32."""
+    cols = smoothed_columns(rows, window_size)
+    with open(path, "w") as f:
+        w = csv.writer(f)
+        for row in zip(*cols):
+            w.writerow(row)
 
 
 def write_results_csv(path: str, smoothed_rows: np.ndarray) -> None:

@@ -30,9 +30,17 @@ CSV_COLUMNS = ("Feret Diameter", "Aspect Ratio", "Roundness", "Circularity", "Sp
 CSV_SOURCE = ("Feret", "Aspect_Ratio", "Roundness", "Circularity", "Sphericity",
               "Length", "Width", "CircularED", "Chords")
 
+# Type of the entries the reference appends to its nine lists (nn_inference.py:451-459), in CSV
+# column order: order_points returns float32, so everything derived from dA / dB stays np.float32;
+# np.sqrt gives np.float64; cv2.contourArea / arcLength arithmetic stays a Python float.  The
+# moving average (:523-527) sums, divides and rounds in that type (np.round for the NumPy
+# scalars, Python's correctly rounded round() for floats) -- pinned by executing the reference's
+# own loop (tests/golden/ref_exec_manifest.json "dtypes").
+CSV_KINDS = ("f32", "f32", "f32", "py", "f64", "f32", "f32", "f64", "py")
+
 # nn_inference.py:170 (thing_classes) and :485 (keywds)
 CLASS_NAMES = ("Scale bar", "Wall thickness of polyHIPEs", "Pore throats of polyHIPEs",
                "Pores of polyHIPEs")
 CLASS_KEYWORDS = ("Scale", "WThick", "PThroat", "Pore")
-# nn_inference.py:232 (things_colors)
+# nn_inference.py:233 (things_colors)
 CLASS_COLORS = ((115, 254, 248), (239, 254, 21), (146, 19, 26), (47, 213, 218))
