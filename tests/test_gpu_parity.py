@@ -713,3 +713,48 @@ def test_postprocess_masks_literal_drop_in():
         thin[:, 20:40, 30:32] = True
         g2, w2 = uwcv.postprocess_masks(thin, scores[:5], (H, W)), OC.postprocess_masks(thin.copy(), scores[:5], (H, W))
         assert len(g2) == len(w2) == 2 and all(np.array_equal(a, b) for a, b in zip(g2, w2))
+
+
+def test_fused_gather_branch_on_one_gpu():
+    """The GatherDst branch of the trace kernel (contour.cu: rows stored into every peer's table at
+    this rank's row offset) exercised on ONE device: three 'ranks' are three calls on different
+    inputs, the three 'peer' tables are three local buffers; every table must end up holding the
+    concatenation of the three plain results."""
+    from uwcv import _lib
+    dev = torch.device("cuda", 0)
+    eng = uwcv.Engine.get(dev)
+    H, W = 300, 420
+    world = 3
+    parts = []
+    for r in range(world):
+        inst = synth.blob_instances(r, 37 + 11 * r, H, W, seed=90)
+        b, keep = api.scale_clip_boxes(inst.pred_boxes.tensor, inst.image_size, (H, W))
+        parts.append((inst.pred_masks[keep, 0].contiguous().to(dev), b[keep].contiguous().to(dev),
+                      inst.scores[keep].to(dev), inst.pred_classes[keep].to(dev)))
+    counts = [int(p[1].shape[0]) for p in parts]
+    total = sum(counts)
+    tabs_i = [torch.full((total, schema.NUM_INT), -7, dtype=torch.int64, device=dev) for _ in range(world)]
+    tabs_f = [torch.full((total, schema.NUM_FLOAT), -7.0, dtype=torch.float64, device=dev) for _ in range(world)]
+    plain = []
+    base = 0
+    for r, (m, b, s, c) in enumerate(parts):
+        g = _lib.Gather()
+        g.world, g.row_base = world, base
+        for p in range(world):
+            g.rows_i[p] = tabs_i[p].data_ptr()
+            g.rows_f[p] = tabs_f[p].data_ptr()
+        img = torch.full((counts[r],), r, dtype=torch.int32, device=dev)
+        ri, rf, _ = eng.run(m, b, H, W, image_idx=img, classes=c, scores=s, gather=g)
+        eng.check_status()
+        plain.append((ri.clone(), rf.clone()))
+        base += counts[r]
+    torch.cuda.synchronize()
+    want_i = torch.cat([p[0] for p in plain])
+    want_f = torch.cat([p[1] for p in plain])
+    for p in range(world):
+        assert torch.equal(tabs_i[p], want_i), p
+        assert torch.equal(tabs_f[p].nan_to_num(), want_f.nan_to_num()), p
+    # and the rows equal a call without the gather
+    ri, rf, _ = eng.run(parts[1][0], parts[1][1], H, W, classes=parts[1][3], scores=parts[1][2],
+                        image_idx=torch.full((counts[1],), 1, dtype=torch.int32, device=dev))
+    assert torch.equal(ri, plain[1][0]) and torch.equal(rf.nan_to_num(), plain[1][1].nan_to_num())

@@ -260,3 +260,16 @@ def test_gather_struct_mirrors_the_header():
     assert C.sizeof(_lib.Gather) == 4 + 4 + 8 + 2 * peers * 8
     assert _lib.Gather.row_base.offset == 8
     assert _lib.Gather.rows_i.offset == 16 and _lib.Gather.rows_f.offset == 16 + peers * 8
+
+
+def test_release_library_reads_no_environment_knobs():
+    """the sweep / elimination knobs (UWCV_DEBUG_SKIP skips the paste!) exist
+    only in the -DUWCV_TUNING build; the shipped library does not even contain their names (the
+    only getenv importer left is the static CUDA runtime) and exports no tuning entry point."""
+    import subprocess
+    blob = open(LIB_PATH, "rb").read()
+    for knob in (b"UWCV_DEBUG_SKIP", b"UWCV_FILL", b"UWCV_ZERO_KB", b"UWCV_PASTE_ROT", b"UWCV_BAND_KB",
+                 b"UWCV_PASTE_CTAS", b"UWCV_TILE_PER_CTA", b"UWCV_TRACE_LANES"):
+        assert knob not in blob, knob
+    assert "uwcv_tuning_" not in subprocess.run(["nm", "-D", "--defined-only", LIB_PATH],
+                                                capture_output=True, text=True).stdout

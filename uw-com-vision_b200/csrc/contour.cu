@@ -24,11 +24,17 @@
 //   * boxPoints -> int truncation -> imutils order_points -> midpoints -> dA, dB -> the
 //     nine descriptors of nn_inference.py:434-449.
 // Compiled with -fmad=false: no contraction anywhere in this file.
+#include <cstdlib>
 #include "contour_common.cuh"
 
 namespace uwcv {
 
 constexpr int kContourThreads = 64;
+#ifdef UWCV_TUNING
+// per-instance iteration counts of the state machine (scan steps, border steps, contours, loop
+// iteration at which the lane finished): tools/trace_stats.py
+__device__ int32_t* g_trace_stats = nullptr;
+#endif
 static_assert((kNumInt * 8) % 16 == 0 && (kNumFloat * 8) % 16 == 0, "rows are copied as 16-byte words");
 static_assert(F_CHORDS - F_CAREA == 15, "describe_contour writes 16 contiguous float columns");
 
@@ -122,8 +128,16 @@ contour_measure_kernel(int64_t first, int64_t n, int lanes, const float* __restr
   };
   uint64_t m_next = (state == kScan && y <= yhi) ? load_pair(t.M, y, 0) : 0ull;
   bool fresh = true;                                     // the next scan step opens a new pair
+#ifdef UWCV_TUNING
+  int st_scan = 0, st_trace = 0, st_iter = 0, st_end = 0;
+#endif
   while (__any_sync(kFull, state != kDone)) {
     bool finished = false;                               // a contour was completed this iteration
+#ifdef UWCV_TUNING
+    ++st_iter;
+    if (state == kScan) ++st_scan; else if (state == kTrace) ++st_trace;
+    if (state != kDone) st_end = st_iter;
+#endif
     if (state == kScan) {
       if (fresh) {
         if (y > yhi) {
@@ -184,6 +198,12 @@ contour_measure_kernel(int64_t first, int64_t n, int lanes, const float* __restr
   }
   if (work) { ri[I_NCONT] = ncont; ri[I_NPTS] = best_npts; }
   const bool have = work && ncont > 0;
+#ifdef UWCV_TUNING
+  if (g_trace_stats && live) {
+    int32_t* o = g_trace_stats + 4 * inst;
+    o[0] = st_scan; o[1] = st_trace; o[2] = ncont; o[3] = st_end;
+  }
+#endif
 
   // ---- hull, min-area rectangle and descriptor block of the best contour ----------------
   describe_contour(have, best, best + d.th, best_y, best_ymax, d.wx0 * 32, d.y0, best_a2,
@@ -226,6 +246,9 @@ cudaError_t launch_contour_measure(int64_t first, int64_t count, const float* sc
   const int64_t resident_warps = (int64_t)num_sms * per_sm * (kContourThreads / 32);
   int lanes = (int)((n + resident_warps - 1) / resident_warps);
   lanes = lanes < 1 ? 1 : (lanes > 32 ? 32 : lanes);
+#ifdef UWCV_TUNING
+  if (const char* v = getenv("UWCV_TRACE_LANES")) { const int l = atoi(v); if (l >= 1 && l <= 32) lanes = l; }
+#endif
   const int64_t warps = (n + lanes - 1) / lanes;
   const unsigned grid = (unsigned)((warps * 32 + kContourThreads - 1) / kContourThreads);
   contour_measure_kernel<<<grid, kContourThreads, 0, stream>>>(first, first + count, lanes, scores,
@@ -235,3 +258,9 @@ cudaError_t launch_contour_measure(int64_t first, int64_t count, const float* sc
 }
 
 }  // namespace uwcv
+
+#ifdef UWCV_TUNING
+extern "C" int uwcv_tuning_set_trace_stats(int32_t* dev_ptr) {
+  return cudaMemcpyToSymbol(uwcv::g_trace_stats, &dev_ptr, sizeof(dev_ptr)) == cudaSuccess ? 0 : -6;
+}
+#endif

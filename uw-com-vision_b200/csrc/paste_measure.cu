@@ -616,15 +616,20 @@ cudaError_t launch_paste_measure(const float* masks, const float* boxes, const i
   const int64_t n = first + count;
   int per_sm = 0;
   cudaError_t e;
-  // tuning knobs (defaults chosen on B200, see profiles/): zero-source size and rotation
+  // defaults chosen on B200 (profiles/): 16 KB zero source, unbounded bulk stores in flight, TMA
+  // fill, tile band composed in shared memory up to 36 KB.  The release library reads NO
+  // environment variable; the sweep knobs exist only in the -DUWCV_TUNING build
+  // (lib/libuwcv_tuning.so, used by tools/*.sh).
   int zero_bytes = kZeroBytesDefault, rot_mul = 0, fill_mode = 0, debug_skip = 0;
-  if (const char* v = getenv("UWCV_DEBUG_SKIP")) debug_skip = atoi(v);   // profiling only
-  if (const char* v = getenv("UWCV_FILL")) fill_mode = atoi(v);
+  int band_cap = 36 * 1024;
+#ifdef UWCV_TUNING
+  if (const char* v = getenv("UWCV_DEBUG_SKIP")) debug_skip = atoi(v) & 3;
+  if (const char* v = getenv("UWCV_FILL")) { fill_mode = atoi(v); if (fill_mode < 0 || fill_mode > 2) fill_mode = 0; }
   if (const char* v = getenv("UWCV_ZERO_KB")) zero_bytes = atoi(v) * 1024;
   if (const char* v = getenv("UWCV_PASTE_ROT")) rot_mul = atoi(v);
   if (zero_bytes < 1024 || zero_bytes > 160 * 1024 || (zero_bytes & 1023)) zero_bytes = kZeroBytesDefault;
-  int band_cap = 36 * 1024;                          // tile band composed in shared memory up to this size
   if (const char* v = getenv("UWCV_BAND_KB")) band_cap = atoi(v) * 1024;       // 0: generic stores
+#endif
   if (band_cap < 0 || band_cap > 96 * 1024 || !planes) band_cap = 0;
   const size_t dyn = planes ? (size_t)zero_bytes + band_cap : 0;
   if (planes) {
@@ -639,11 +644,13 @@ cudaError_t launch_paste_measure(const float* masks, const float* boxes, const i
   }
   if (e != cudaSuccess) return e;
   if (per_sm < 1) per_sm = 1;
-  // UWCV_PASTE_CTAS (profiling) caps the CTAs per SM: 1 -> 4 780, 2 -> 5 590, 3 -> 5 640 GB/s
+#ifdef UWCV_TUNING
+  // caps the CTAs per SM: 1 -> 4 780, 2 -> 5 590, 3 -> 5 640 GB/s (static split, r01)
   if (const char* v = getenv("UWCV_PASTE_CTAS")) {
     const int cap = atoi(v);
     if (cap >= 1 && cap < per_sm) per_sm = cap;
   }
+#endif
   int64_t grid = (int64_t)num_sms * per_sm;           // persistent: a whole number of waves
   if (grid > count) grid = count;
   if (planes) {
@@ -654,7 +661,10 @@ cudaError_t launch_paste_measure(const float* masks, const float* boxes, const i
   }
   // rows only: one instance per warp for ordinary tiles, then the whole-CTA kernel for the
   // few giant ones (it returns at once when the layout counted none)
-  const bool per_warp = !getenv("UWCV_TILE_PER_CTA");                       // profiling only
+  bool per_warp = true;
+#ifdef UWCV_TUNING
+  per_warp = !getenv("UWCV_TILE_PER_CTA");
+#endif
   if (per_warp) {
     int tper = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&tper, tile_measure_kernel, kTileWarps * 32,

@@ -5,9 +5,22 @@ from __future__ import annotations
 import ctypes as C
 import os
 
+from . import build as _build
 from .build import LIB_PATH
 
 _lib = None
+_path = LIB_PATH
+
+
+def use_library_variant(variant: str) -> str:
+    """Development only (tools/): load lib/libuwcv_<variant>.so ("tuning": environment sweep
+    knobs, "check": device-side bounds traps) instead of the release library.  Must be called
+    before the first entry point is used; the product path never calls it."""
+    global _path
+    if _lib is not None:
+        raise RuntimeError("the library is already loaded")
+    _path = _build.build(variant=variant)
+    return _path
 
 MAX_PEERS = 16
 
@@ -30,11 +43,11 @@ def lib() -> C.CDLL:
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
+    if not os.path.exists(_path):
         raise RuntimeError(
-            f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+            f"{_path} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
             "(the uwcv hot path has no CPU or PyTorch fallback)")
-    L = C.CDLL(LIB_PATH)
+    L = C.CDLL(_path)
     vp, i64, i32, f32, f64, sz = C.c_void_p, C.c_int64, C.c_int, C.c_float, C.c_double, C.c_size_t
     L.uwcv_version.restype = C.c_int
     L.uwcv_strerror.restype = C.c_char_p

@@ -9,6 +9,12 @@ PKG_DIR = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_DIR = os.path.join(PKG_DIR, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libuwcv.so")
+# the same sources with -DUWCV_TUNING: sweep / elimination knobs read from the environment
+# (tools/*.sh, tools/*probe*.py).  Never loaded by the product path; see _lib.use_tuning_library.
+TUNING_LIB_PATH = os.path.join(LIB_DIR, "libuwcv_tuning.so")
+# -DUWCV_CHECK: device-side bounds traps on every tile / plane / scratch index (memory-safety
+# substitute for compute-sanitizer, which is closed on the GPU pool)
+CHECK_LIB_PATH = os.path.join(LIB_DIR, "libuwcv_check.so")
 SOURCES = ["uwcv_capi.cu", "paste_measure.cu", "contour.cu", "union.cu", "nms.cu", "unpack.cu", "cleanup.cu"]
 
 NVCC_FLAGS = [
@@ -19,27 +25,31 @@ NVCC_FLAGS = [
 ]
 
 
-def needs_build() -> bool:
-    if not os.path.exists(LIB_PATH):
+def needs_build(path: str = LIB_PATH) -> bool:
+    if not os.path.exists(path):
         return True
-    t = os.path.getmtime(LIB_PATH)
+    t = os.path.getmtime(path)
     deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)]
     deps.append(os.path.join(os.path.dirname(PKG_DIR), "include", "uwcv.h"))
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not needs_build():
-        return LIB_PATH
+def build(force: bool = False, verbose: bool = False, variant: str = "") -> str:
+    """variant: "" (release), "tuning" (-DUWCV_TUNING) or "check" (-DUWCV_CHECK)."""
+    out = {"": LIB_PATH, "tuning": TUNING_LIB_PATH, "check": CHECK_LIB_PATH}[variant]
+    if not force and not needs_build(out):
+        return out
     os.makedirs(LIB_DIR, exist_ok=True)
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + ["-o", LIB_PATH] + [os.path.join(CSRC, s) for s in SOURCES]
+    extra = ["-DUWCV_" + variant.upper()] if variant else []
+    cmd = [nvcc] + NVCC_FLAGS + extra + ["-o", out] + [os.path.join(CSRC, s) for s in SOURCES]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
         print(" ".join(cmd))
     subprocess.run(cmd, check=True)
-    return LIB_PATH
+    return out
 
 
 if __name__ == "__main__":
-    print(build(force=True, verbose=True))
+    import sys
+    print(build(force=True, verbose=True, variant=sys.argv[1] if len(sys.argv) > 1 else ""))
