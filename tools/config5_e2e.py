@@ -27,9 +27,16 @@ ap.add_argument("--side", type=int, default=1024)
 ap.add_argument("--batch", type=int, default=4)
 ap.add_argument("--backbone", default="resnet101")
 ap.add_argument("--detections", type=int, default=1000)
+ap.add_argument("--deterministic", action="store_true",
+                help="cudnn deterministic, no autotune, no TF32: bit-reproducible network output")
 ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "classes_config5.csv"))
 args = ap.parse_args()
 
+if args.deterministic:
+    torch.backends.cudnn.deterministic = True
+    torch.backends.cudnn.benchmark = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
 world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0"))
 local = int(os.environ.get("LOCAL_RANK", "0"))
 torch.cuda.set_device(local)
@@ -85,9 +92,15 @@ def build_model(backbone_name, side, detections, device):
 model = build_model(args.backbone, args.side, args.detections, dev)
 sf = uwcv.SingleForward(model, score_thresh=0.05, nms_thresh=0.5, detections_per_image=args.detections)
 
-g = torch.Generator().manual_seed(100 + rank)
-images = [torch.rand((1, args.side, args.side), generator=g).expand(3, -1, -1).contiguous()
-          for _ in range(args.images)]                      # grayscale replicated, as cv2.imread yields
+# image b of the whole set is seeded by b alone and rank r owns the contiguous block
+# [r * images, (r + 1) * images): an N-rank job and a 1-rank job over N * images images see the
+# same images in the same batches, so their classes.csv must be identical (--deterministic)
+def make_image(b):
+    g = torch.Generator().manual_seed(100 + b)
+    return torch.rand((1, args.side, args.side), generator=g).expand(3, -1, -1).contiguous()
+
+
+images = [make_image(rank * args.images + i) for i in range(args.images)]   # grayscale replicated
 batches = [images[i:i + args.batch] for i in range(0, len(images), args.batch)]
 
 
@@ -117,6 +130,7 @@ table = uwcv.MeasurementTable.concat(tables)
 rows_i = torch.from_numpy(table.ints.copy()).to(dev)
 rows_f = torch.from_numpy(table.floats.copy()).to(dev)
 gi, gf = uwcv.all_gather_table(rows_i, rows_f)
+gi, gf = uwcv.sort_rows(gi, gf)                            # image-major, instance order
 whole = uwcv.MeasurementTable(gi.cpu().numpy(), gf.cpu().numpy())
 if rank == 0:
     os.makedirs(os.path.dirname(args.out), exist_ok=True)
@@ -131,6 +145,8 @@ if rank == 0:
         "images_per_s_total": world * args.images / t_all,
         "instances_per_s_total": len(whole) / t_all,
         "per_class_counts": {r["class_name"]: r["count"] for r in recs},
+        "deterministic": bool(args.deterministic),
+        "table_crc32": __import__("zlib").crc32(whole.ints.tobytes() + whole.floats.tobytes()),
         "classes_csv": os.path.relpath(args.out, ROOT)}))
 if world > 1:
     dist.destroy_process_group()

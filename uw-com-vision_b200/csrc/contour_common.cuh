@@ -14,16 +14,51 @@ struct TileView {
   int tw, th;
 };
 
+// Where a tile (mask bits, marks, per-row extremes) lives.  GlobalMem: the tile workspace in HBM /
+// L2 (stand-alone trace kernel, union mode).  SharedMem: a slot of the paste kernel's shared-memory
+// arena, owned by ONE tracer lane (fused trace): plain ld.shared, result-less red.shared -- the
+// serial chain of a border walk then waits ~30 cycles per load instead of an L2 / DRAM round trip.
+struct GlobalMem {
+  static __device__ __forceinline__ uint32_t ldm(const uint32_t* p) { return __ldg(p); }   // mask bits: read-only
+  static __device__ __forceinline__ uint32_t ld(const uint32_t* p) { return *p; }
+  static __device__ __forceinline__ void st(uint32_t* p, uint32_t v) { *p = v; }
+  static __device__ __forceinline__ void or_(uint32_t* p, uint32_t v) { atomicOr(p, v); }
+  static __device__ __forceinline__ void min_(uint32_t* p, uint32_t v) { atomicMin(p, v); }
+  static __device__ __forceinline__ void max_(uint32_t* p, uint32_t v) { atomicMax(p, v); }
+};
+struct SharedMem {
+  static __device__ __forceinline__ uint32_t sa(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+  static __device__ __forceinline__ uint32_t ldm(const uint32_t* p) { return ld(p); }
+  static __device__ __forceinline__ uint32_t ld(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(sa(p)) : "memory");
+    return v;
+  }
+  static __device__ __forceinline__ void st(uint32_t* p, uint32_t v) {
+    asm volatile("st.shared.u32 [%0], %1;" :: "r"(sa(p)), "r"(v) : "memory");
+  }
+  static __device__ __forceinline__ void or_(uint32_t* p, uint32_t v) {
+    asm volatile("red.shared.or.b32 [%0], %1;" :: "r"(sa(p)), "r"(v) : "memory");
+  }
+  static __device__ __forceinline__ void min_(uint32_t* p, uint32_t v) {
+    asm volatile("red.shared.min.u32 [%0], %1;" :: "r"(sa(p)), "r"(v) : "memory");
+  }
+  static __device__ __forceinline__ void max_(uint32_t* p, uint32_t v) {
+    asm volatile("red.shared.max.u32 [%0], %1;" :: "r"(sa(p)), "r"(v) : "memory");
+  }
+};
+
 // direction s: 0 = east, then counter-clockwise on a y-up plane (1 = x+1, y-1 on screen)
 __device__ __forceinline__ int dir_dx(int s) { return (int)((0x901Au >> (2 * s)) & 3u) - 1; }
 __device__ __forceinline__ int dir_dy(int s) { return (int)((0xA901u >> (2 * s)) & 3u) - 1; }
 
 // 64-pixel window of tile row y starting at word wb (words outside the tile read as zero)
+template <class Mem = GlobalMem>
 __device__ __forceinline__ uint64_t load_row64(const TileView& t, int y, int wb) {
   if ((unsigned)y >= (unsigned)t.th) return 0ull;
   const uint32_t* row = t.M + y * t.tw;
-  const uint32_t lo = ((unsigned)wb < (unsigned)t.tw) ? __ldg(row + wb) : 0u;
-  const uint32_t hi = ((unsigned)(wb + 1) < (unsigned)t.tw) ? __ldg(row + wb + 1) : 0u;
+  const uint32_t lo = ((unsigned)wb < (unsigned)t.tw) ? Mem::ldm(row + wb) : 0u;
+  const uint32_t hi = ((unsigned)(wb + 1) < (unsigned)t.tw) ? Mem::ldm(row + wb + 1) : 0u;
   return (uint64_t)lo | ((uint64_t)hi << 32);
 }
 
@@ -32,11 +67,12 @@ __device__ __forceinline__ uint64_t load_row64(const TileView& t, int y, int wb)
 struct Window {
   uint64_t r0, r1, r2;
   int wb;                                  // first word of the window
+  template <class Mem = GlobalMem>
   __device__ __forceinline__ void load(const TileView& t, int x, int y) {
     wb = (x >> 5) - (((x & 31) < 16) ? 1 : 0);         // x - 32 wb in [16, 48)
-    r0 = load_row64(t, y - 1, wb);
-    r1 = load_row64(t, y, wb);
-    r2 = load_row64(t, y + 1, wb);
+    r0 = load_row64<Mem>(t, y - 1, wb);
+    r1 = load_row64<Mem>(t, y, wb);
+    r2 = load_row64<Mem>(t, y + 1, wb);
   }
   // bit s of the result = neighbour in direction s is foreground
   __device__ __forceinline__ uint32_t neighbours(int x) const {
@@ -46,12 +82,13 @@ struct Window {
     return (mid >> 2) | ((up >> 2) << 1) | (((up >> 1) & 1u) << 2) | ((up & 1u) << 3) |
            ((mid & 1u) << 4) | ((dn & 1u) << 5) | (((dn >> 1) & 1u) << 6) | ((dn >> 2) << 7);
   }
+  template <class Mem = GlobalMem>
   __device__ __forceinline__ void move(const TileView& t, int x, int y, int dy) {
     // (x, y) is the new position, dy the vertical part of the step just taken
-    if (dy < 0) { r2 = r1; r1 = r0; r0 = load_row64(t, y - 1, wb); }
-    else if (dy > 0) { r0 = r1; r1 = r2; r2 = load_row64(t, y + 1, wb); }
+    if (dy < 0) { r2 = r1; r1 = r0; r0 = load_row64<Mem>(t, y - 1, wb); }
+    else if (dy > 0) { r0 = r1; r1 = r2; r2 = load_row64<Mem>(t, y + 1, wb); }
     const int sx = x - wb * 32;
-    if (sx < 1 || sx > 62) load(t, x, y);
+    if (sx < 1 || sx > 62) load<Mem>(t, x, y);
   }
 };
 
@@ -72,15 +109,15 @@ struct Trace {
   bool active;
 };
 
-template <bool kMark, bool kExt>
+template <bool kMark, bool kExt, class Mem = GlobalMem>
 __device__ __forceinline__ void trace_begin(const TileView& t, Trace& c, int x0, int y0,
                                             uint32_t* ext_l, uint32_t* ext_r) {
   c.area2 = 0; c.perim = 0.0; c.npts = 0; c.ymax = y0;
   c.x0 = x0; c.y0 = y0; c.x3 = x0; c.y3 = y0;
   c.fvx = c.fvy = c.lvx = c.lvy = 0;
-  c.w.load(t, x0, y0);
+  c.w.template load<Mem>(t, x0, y0);
   c.nb = c.w.neighbours(x0);
-  if (kExt) { ext_l[y0] = (uint32_t)x0; ext_r[y0] = (uint32_t)x0; }
+  if (kExt) { Mem::st(ext_l + y0, (uint32_t)x0); Mem::st(ext_r + y0, (uint32_t)x0); }
   // first search: clockwise from west (3, 2, 1, 0, 7, 6, 5)
   int s = -1;
 #pragma unroll
@@ -91,7 +128,7 @@ __device__ __forceinline__ void trace_begin(const TileView& t, Trace& c, int x0,
   if (s < 0) {                                // isolated pixel
     const int o = y0 * t.tw + (x0 >> 5);
     const uint32_t b = 1u << (x0 & 31);
-    if (kMark) { atomicOr(t.V + o, b); atomicOr(t.G + o, b); }
+    if (kMark) { Mem::or_(t.V + o, b); Mem::or_(t.G + o, b); }
     c.npts = 1;
     c.active = false;
     c.s = 0; c.prev_s = 0; c.x1 = x0; c.y1 = y0;
@@ -103,7 +140,7 @@ __device__ __forceinline__ void trace_begin(const TileView& t, Trace& c, int x0,
   c.active = true;
 }
 
-template <bool kMark, bool kExt>
+template <bool kMark, bool kExt, class Mem = GlobalMem>
 __device__ __forceinline__ void trace_step(const TileView& t, Trace& c, uint32_t* ext_l,
                                            uint32_t* ext_r) {
   const int s_end = c.s;
@@ -114,8 +151,8 @@ __device__ __forceinline__ void trace_step(const TileView& t, Trace& c, uint32_t
   if (kMark) {
     const int o = y3 * t.tw + (x3 >> 5);
     const uint32_t b = 1u << (x3 & 31);
-    atomicOr(t.V + o, b);
-    if ((unsigned)(s - 1) < (unsigned)s_end) atomicOr(t.G + o, b);
+    Mem::or_(t.V + o, b);
+    if ((unsigned)(s - 1) < (unsigned)s_end) Mem::or_(t.G + o, b);
   }
   if (s != c.prev_s) {                        // CHAIN_APPROX_SIMPLE vertex
     if (c.npts == 0) { c.fvx = x3; c.fvy = y3; }
@@ -141,28 +178,148 @@ __device__ __forceinline__ void trace_step(const TileView& t, Trace& c, uint32_t
   c.x3 = x4; c.y3 = y4;
   if (y4 > c.ymax) {                          // rows are first reached in increasing order
     c.ymax = y4;
-    if (kExt) { ext_l[y4] = (uint32_t)x4; ext_r[y4] = (uint32_t)x4; }
+    if (kExt) { Mem::st(ext_l + y4, (uint32_t)x4); Mem::st(ext_r + y4, (uint32_t)x4); }
   } else if (kExt) {
-    atomicMin(ext_l + y4, (uint32_t)x4);
-    atomicMax(ext_r + y4, (uint32_t)x4);
+    Mem::min_(ext_l + y4, (uint32_t)x4);
+    Mem::max_(ext_r + y4, (uint32_t)x4);
   }
-  c.w.move(t, x4, y4, dy);
+  c.w.template move<Mem>(t, x4, y4, dy);
   c.nb = c.w.neighbours(x4);
   c.s = (s + 4) & 7;
 }
 
 // sign of the last marked pixel in words [0, wi) of row y: 0 none, +1 positive, -1 negative
+template <class Mem = GlobalMem>
 static __device__ int last_mark_before(const TileView& t, int wi, int y) {
   const int row = y * t.tw;
   for (--wi; wi >= 0; --wi) {
-    const uint32_t v = t.V[row + wi];
+    const uint32_t v = Mem::ld(t.V + row + wi);
     if (v) {
       const int b = 31 - __clz(v);
-      return ((t.G[row + wi] >> b) & 1u) ? -1 : +1;
+      return ((Mem::ld(t.G + row + wi) >> b) & 1u) ? -1 : +1;
     }
   }
   return 0;
 }
+
+// Raster scan + border following of ONE instance as a resumable per-lane state machine: every
+// call of step() advances the lane by one 64-pixel scan step (two tile words, the next pair
+// prefetched) or by one border step; the largest external contour (by |area|, the raster-first
+// one on ties) and its per-row extremes are kept.  Used lane-per-instance by the stand-alone
+// trace kernel (GlobalMem) and by the tracer warp of the paste kernel (SharedMem).
+template <class Mem>
+struct LaneTracer {
+  enum { kScan = 0, kTrace = 1, kDone = 2 };
+  TileView t;
+  uint32_t* cur;                           // extremes of the contour being traced: l = cur, r = cur + estride
+  uint32_t* best;                          // ... of the best contour so far
+  int estride;
+  int ncont, best_y, best_npts, best_ymax;
+  long long best_a2;
+  double best_perim;
+  int y, yhi, wi, cy_, cwi, sy, state;
+  uint64_t carry, start_mask, cand, vpair, gpair, m_next;
+  bool fresh;                              // the next scan step opens a new pair
+  Trace tr;
+
+  __device__ __forceinline__ uint64_t load_pair(const uint32_t* plane, int yy, int w0) const {
+    const uint32_t* row = plane + yy * t.tw;
+    const uint32_t lo = Mem::ld(row + w0);
+    const uint32_t hi = (w0 + 1 < t.tw) ? Mem::ld(row + w0 + 1) : 0u;
+    return (uint64_t)lo | ((uint64_t)hi << 32);
+  }
+  __device__ __forceinline__ uint64_t load_pair_m(int yy, int w0) const {
+    const uint32_t* row = t.M + yy * t.tw;
+    const uint32_t lo = Mem::ldm(row + w0);
+    const uint32_t hi = (w0 + 1 < t.tw) ? Mem::ldm(row + w0 + 1) : 0u;
+    return (uint64_t)lo | ((uint64_t)hi << 32);
+  }
+  static __device__ __forceinline__ int sign_of_top(uint64_t v, uint64_t g) {      // v != 0
+    const int top = 63 - __clzll((long long)v);
+    return ((g >> top) & 1ull) ? -1 : +1;
+  }
+
+  __device__ __forceinline__ void idle() {
+    t.M = nullptr; t.V = t.G = nullptr; t.tw = t.th = 0;
+    cur = best = nullptr; estride = 0;
+    ncont = 0; best_a2 = -1; best_y = 0; best_npts = 0; best_ymax = -1; best_perim = 0.0;
+    y = 0; yhi = -1; wi = 0; cy_ = cwi = sy = 0; state = kDone;
+    carry = start_mask = cand = vpair = gpair = m_next = 0ull;
+    fresh = true;
+    tr.active = false;
+  }
+  // rows [y_first, y_last] (tile coordinates) are the only ones that can hold a start pixel
+  __device__ __forceinline__ void begin(const TileView& tv, uint32_t* ext_a, uint32_t* ext_b,
+                                        int ext_stride, int y_first, int y_last) {
+    idle();
+    t = tv; cur = ext_a; best = ext_b; estride = ext_stride;
+    y = y_first; yhi = y_last;
+    state = kScan;
+    m_next = (y <= yhi) ? load_pair_m(y, 0) : 0ull;
+  }
+  __device__ __forceinline__ bool done() const { return state == kDone; }
+
+  __device__ __forceinline__ void step() {
+    bool finished = false;                               // a contour was completed this step
+    if (state == kScan) {
+      if (fresh) {
+        if (y > yhi) {
+          state = kDone;
+        } else {
+          const uint64_t m = m_next;
+          start_mask = m & ~((m << 1) | carry);          // foreground with background on the left
+          carry = m >> 63;
+          cy_ = y; cwi = wi;
+          wi += 2;
+          if (wi >= t.tw) { wi = 0; ++y; carry = 0; }
+          if (y <= yhi) m_next = load_pair_m(y, wi);     // prefetch the next pair
+          // marks are only consulted where the pair holds start candidates (V), and their
+          // signs only where a candidate is still unvisited (G)
+          vpair = start_mask ? load_pair(t.V, cy_, cwi) : 0ull;
+          cand = start_mask & ~vpair;
+          gpair = cand ? load_pair(t.G, cy_, cwi) : 0ull;
+          fresh = cand == 0;
+        }
+      }
+      if (state == kScan && !fresh) {
+        // resolve the candidates of this pair in registers: a candidate starts an external
+        // border unless the last marked pixel to its left carries a positive mark
+        bool start = false;
+        int b = 0;
+        while (cand) {
+          b = __ffsll((long long)cand) - 1;
+          cand &= cand - 1;
+          const uint64_t below = vpair & ((1ull << b) - 1ull);
+          // last marked pixel to the left: in this pair, else search the earlier words
+          const int sgn = below ? sign_of_top(below, gpair) : last_mark_before<Mem>(t, cwi, cy_);
+          if (sgn <= 0) { start = true; break; }
+        }
+        if (start) {
+          sy = cy_;
+          trace_begin<true, true, Mem>(t, tr, cwi * 32 + b, cy_, cur, cur + estride);
+          if (tr.active) state = kTrace; else finished = true;
+        } else {
+          fresh = true;
+        }
+      }
+    } else if (state == kTrace) {
+      trace_step<true, true, Mem>(t, tr, cur, cur + estride);
+      if (!tr.active) { finished = true; state = kScan; }
+    }
+    if (finished) {
+      ++ncont;
+      const long long a2 = tr.area2 < 0 ? -tr.area2 : tr.area2;
+      if (a2 > best_a2) {
+        best_a2 = a2; best_y = sy; best_npts = tr.npts; best_perim = tr.perim;
+        best_ymax = tr.ymax;
+        uint32_t* tmp = cur; cur = best; best = tmp;
+      }
+      // the trace marked pixels of this row (never to the left of its start): reload
+      vpair = load_pair(t.V, cy_, cwi); gpair = load_pair(t.G, cy_, cwi);
+      cand &= ~vpair;
+    }
+  }
+};
 
 __device__ __forceinline__ uint32_t pk(int x, int y) { return (uint32_t)x | ((uint32_t)y << 16); }
 __device__ __forceinline__ int pkx(uint32_t p) { return (int)(p & 0xffffu); }

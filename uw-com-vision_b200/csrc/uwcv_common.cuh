@@ -62,13 +62,29 @@ struct GatherDst {
   double* rows_f[kMaxPeers];       // [total_rows, kNumFloat] per peer
 };
 
+// Result of the border trace of one instance, handed from the kernel that traced it (the tracer
+// warps of the paste kernel, or the stand-alone trace) to the descriptor kernel: the largest
+// external contour's twice-area, arc length, first / last row (tile coordinates) and vertex count;
+// its per-row extremes are the first extremes set of the instance in Workspace::scratch.
+struct __align__(16) TraceRec {
+  long long a2;        // |twice the contour area| of the best contour
+  double perim;
+  int32_t best_y;      // tile row of its raster-first pixel
+  int32_t best_ymax;   // last tile row it reaches
+  int32_t npts;        // CHAIN_APPROX_SIMPLE vertices
+  int32_t ncont;       // external contours of the instance; kNotTraced: still to be traced
+};
+constexpr int32_t kNotTraced = -1;
+
 // Workspace carve-up, computed identically on host and device.
 constexpr int kLayoutThreads = 1024;   // instances per layout CTA
 
 struct Workspace {
   TileDesc* desc;      // [N]
+  TraceRec* rec;       // [N]
+  int32_t* order;      // [N]  paste order of a launch's range: large tiles first (their traces are the long ones)
   int64_t* block_sums; // [2 * ceil(N / 1024)]  per-CTA (tile words, tile rows) of the layout
-  unsigned int* sched; // [4]  work counters of the paste kernel (fill, tile, CTAs done); zero between launches
+  unsigned int* sched; // [8]  work counters of the paste kernel (fill, tile, CTAs done, ...); zero between launches
   uint32_t* M;         // [cap_words]  mask bits
   uint32_t* V;         // [cap_words]  border-visited marks
   uint32_t* G;         // [cap_words]  "right neighbour was background" marks (negative marks)
@@ -82,7 +98,8 @@ __host__ __device__ inline size_t layout_blocks(int64_t n) {
   return (size_t)((n + kLayoutThreads - 1) / kLayoutThreads);
 }
 __host__ __device__ inline size_t header_bytes(int64_t n) {
-  return align_up((size_t)n * sizeof(TileDesc), 256) + align_up(layout_blocks(n) * 16 + 16, 256) + 256;
+  return align_up((size_t)n * sizeof(TileDesc), 256) + align_up((size_t)n * sizeof(TraceRec), 256) +
+         align_up((size_t)n * sizeof(int32_t), 256) + align_up(layout_blocks(n) * 16 + 16, 256) + 256;
 }
 __host__ __device__ inline size_t workspace_bytes(int64_t n, int64_t tile_words) {
   return header_bytes(n) + (size_t)tile_words * 28 + 256;
@@ -92,7 +109,12 @@ __host__ __device__ inline Workspace carve(void* ws, size_t ws_bytes, int64_t n)
   Workspace w;
   char* p = (char*)ws;
   w.desc = (TileDesc*)p;
-  w.block_sums = (int64_t*)(p + align_up((size_t)n * sizeof(TileDesc), 256));
+  size_t o = align_up((size_t)n * sizeof(TileDesc), 256);
+  w.rec = (TraceRec*)(p + o);
+  o += align_up((size_t)n * sizeof(TraceRec), 256);
+  w.order = (int32_t*)(p + o);
+  o += align_up((size_t)n * sizeof(int32_t), 256);
+  w.block_sums = (int64_t*)(p + o);
   size_t d = header_bytes(n);
   w.sched = (unsigned int*)(p + d - 256);
   int64_t cap = ws_bytes > d + 256 ? (int64_t)((ws_bytes - d - 256) / 28) : 0;
