@@ -89,5 +89,15 @@ for _ in range(a.steps):
 main.wait_stream(eng.trace_stream)
 e1.record(); e1.synchronize()
 res["overlapped_step"] = e0.elapsed_time(e1) / a.steps
+if a.variant.startswith("tuning"):
+    import ctypes as C
+    L = _lib.lib()
+    buf = (C.c_ulonglong * 4)()
+    L.uwcv_tuning_fused_stats(buf, 1)
+    eng.run(d_masks, d_boxes, H, W, rows_i=rows[0][0], rows_f=rows[0][1], **kw)
+    torch.cuda.synchronize()
+    L.uwcv_tuning_fused_stats(buf, 1)
+    res["fused_stats_one_step"] = dict(alloc_retries=buf[0], tracer_idle_polls=buf[1], tracer_warp_iters=buf[2],
+                                       tracer_lane_steps=buf[3])
 res["checksum"] = [int(rows[0][0].sum().item()), float(rows[0][1].nan_to_num().sum().item())]
 print(json.dumps(res))

@@ -92,111 +92,47 @@ contour_measure_kernel(int64_t first, int64_t n, int lanes, const float* __restr
   }
 
   // ---- raster scan + border following; keep the largest contour and its row extremes ---
-  // Per-lane state machine: each iteration of the warp-uniform loop advances a lane either
-  // by one 64-pixel scan step (two tile words, the next pair prefetched) or by one border
-  // step, so no lane waits for another lane's contour.
+  // Instances whose tile was traced by the tracer warps of the paste kernel (from shared
+  // memory, under the HBM-bound plane fill) arrive with their result in ws.rec and their
+  // extremes in the first extremes set; everything else (rows-only contract, tiles too large
+  // for a shared-memory slot) is traced here, lane per instance: each iteration of the
+  // warp-uniform loop advances a lane by one 64-pixel scan step or one border step
+  // (LaneTracer), so no lane waits for another lane's contour.
+  TraceRec rec;
+  rec.ncont = kNotTraced; rec.a2 = -1; rec.perim = 0.0; rec.best_y = 0; rec.best_ymax = -1; rec.npts = 0;
+  if (live) rec = ws.rec[inst];
+  const bool pre = live && rec.ncont != kNotTraced;
   TileView t;
   t.M = ws.M + d.word_off; t.V = ws.V + d.word_off; t.G = ws.G + d.word_off;
   t.tw = d.tw; t.th = d.th;
-  int ncont = 0;
-  long long best_a2 = -1;
-  int best_y = 0, best_npts = 0, best_ymax = -1;
-  double best_perim = 0.0;
   // two sets of per-row extremes (left | right): the contour being traced and the best so far
-  uint32_t* cur = ws.scratch + 4 * d.row_off;
-  uint32_t* best = cur + 2 * d.th;
+  uint32_t* ext0 = ws.scratch + 4 * d.row_off;
+  LaneTracer<GlobalMem> T;
+  T.idle();
   // rows outside the pixel bbox cannot hold a start pixel
-  int y = work ? (int)ri[I_BY0] - d.y0 : 0;
-  const int yhi = work ? (int)ri[I_BY1] - d.y0 : -1;
-  int wi = 0;
-  uint64_t carry = 0, start_mask = 0, cand = 0, vpair = 0, gpair = 0;
-  int cy_ = 0, cwi = 0;                                  // row / first word of the candidates
-  int sy = 0;
-  enum { kScan = 0, kTrace = 1, kDone = 2 };
-  int state = work ? kScan : kDone;
-  Trace tr;
-  tr.active = false;
-  auto load_pair = [&](const uint32_t* plane, int yy, int w0) -> uint64_t {
-    const uint32_t* row = plane + yy * t.tw;
-    const uint32_t lo = row[w0];
-    const uint32_t hi = (w0 + 1 < t.tw) ? row[w0 + 1] : 0u;
-    return (uint64_t)lo | ((uint64_t)hi << 32);
-  };
-  auto sign_of_top = [](uint64_t v, uint64_t g) -> int {      // v != 0
-    const int top = 63 - __clzll((long long)v);
-    return ((g >> top) & 1ull) ? -1 : +1;
-  };
-  uint64_t m_next = (state == kScan && y <= yhi) ? load_pair(t.M, y, 0) : 0ull;
-  bool fresh = true;                                     // the next scan step opens a new pair
+  if (work && !pre) T.begin(t, ext0, ext0 + 2 * d.th, d.th, (int)ri[I_BY0] - d.y0, (int)ri[I_BY1] - d.y0);
 #ifdef UWCV_TUNING
   int st_scan = 0, st_trace = 0, st_iter = 0, st_end = 0;
 #endif
-  while (__any_sync(kFull, state != kDone)) {
-    bool finished = false;                               // a contour was completed this iteration
+  while (__any_sync(kFull, !T.done())) {
 #ifdef UWCV_TUNING
     ++st_iter;
-    if (state == kScan) ++st_scan; else if (state == kTrace) ++st_trace;
-    if (state != kDone) st_end = st_iter;
+    if (T.state == LaneTracer<GlobalMem>::kScan) ++st_scan;
+    else if (T.state == LaneTracer<GlobalMem>::kTrace) ++st_trace;
+    if (!T.done()) st_end = st_iter;
 #endif
-    if (state == kScan) {
-      if (fresh) {
-        if (y > yhi) {
-          state = kDone;
-        } else {
-          const uint64_t m = m_next;
-          start_mask = m & ~((m << 1) | carry);          // foreground with background on the left
-          carry = m >> 63;
-          cy_ = y; cwi = wi;
-          wi += 2;
-          if (wi >= t.tw) { wi = 0; ++y; carry = 0; }
-          if (y <= yhi) m_next = load_pair(t.M, y, wi);  // prefetch the next pair
-          // marks are only consulted where the pair holds start candidates (V), and their
-          // signs only where a candidate is still unvisited (G)
-          vpair = start_mask ? load_pair(t.V, cy_, cwi) : 0ull;
-          cand = start_mask & ~vpair;
-          gpair = cand ? load_pair(t.G, cy_, cwi) : 0ull;
-          fresh = cand == 0;
-        }
-      }
-      if (state == kScan && !fresh) {
-        // resolve the candidates of this pair in registers: a candidate starts an external
-        // border unless the last marked pixel to its left carries a positive mark
-        bool start = false;
-        int b = 0;
-        while (cand) {
-          b = __ffsll((long long)cand) - 1;
-          cand &= cand - 1;
-          const uint64_t below = vpair & ((1ull << b) - 1ull);
-          // last marked pixel to the left: in this pair, else search the earlier words
-          const int sgn = below ? sign_of_top(below, gpair) : last_mark_before(t, cwi, cy_);
-          if (sgn <= 0) { start = true; break; }
-        }
-        if (start) {
-          sy = cy_;
-          trace_begin<true, true>(t, tr, cwi * 32 + b, cy_, cur, cur + d.th);
-          if (tr.active) state = kTrace; else finished = true;
-        } else {
-          fresh = true;
-        }
-      }
-    } else if (state == kTrace) {
-      trace_step<true, true>(t, tr, cur, cur + d.th);
-      if (!tr.active) { finished = true; state = kScan; }
-    }
-    if (finished) {
-      ++ncont;
-      const long long a2 = tr.area2 < 0 ? -tr.area2 : tr.area2;
-      if (a2 > best_a2) {
-        best_a2 = a2; best_y = sy; best_npts = tr.npts; best_perim = tr.perim;
-        best_ymax = tr.ymax;
-        uint32_t* tmp = cur; cur = best; best = tmp;
-      }
-      // the trace marked pixels of this row (never to the left of its start): reload
-      vpair = load_pair(t.V, cy_, cwi); gpair = load_pair(t.G, cy_, cwi);
-      cand &= ~vpair;
-    }
+    if (!T.done()) T.step();
   }
-  if (work) { ri[I_NCONT] = ncont; ri[I_NPTS] = best_npts; }
+  int ncont = T.ncont, best_npts = T.best_npts, best_y = T.best_y, best_ymax = T.best_ymax;
+  long long best_a2 = T.best_a2;
+  double best_perim = T.best_perim;
+  uint32_t* best = T.best;
+  if (pre) {
+    ncont = rec.ncont; best_npts = rec.npts; best_y = rec.best_y; best_ymax = rec.best_ymax;
+    best_a2 = rec.a2; best_perim = rec.perim; best = ext0;
+  } else if (work) {
+    ri[I_NCONT] = ncont; ri[I_NPTS] = best_npts;
+  }
   const bool have = work && ncont > 0;
 #ifdef UWCV_TUNING
   if (g_trace_stats && live) {

@@ -35,13 +35,19 @@ def needs_build(path: str = LIB_PATH) -> bool:
 
 
 def build(force: bool = False, verbose: bool = False, variant: str = "") -> str:
-    """variant: "" (release), "tuning" (-DUWCV_TUNING) or "check" (-DUWCV_CHECK)."""
-    out = {"": LIB_PATH, "tuning": TUNING_LIB_PATH, "check": CHECK_LIB_PATH}[variant]
+    """variant: "" (release), "tuning" (-DUWCV_TUNING) or "check" (-DUWCV_CHECK); development
+    sweeps may append compile-time overrides, e.g. "tuning,TRACER_WARPS=2" ->
+    lib/libuwcv_tuning_TRACER_WARPS_2.so built with -DUWCV_TUNING -DUWCV_TRACER_WARPS=2."""
+    parts = [v for v in variant.split(",") if v]
+    base = parts[0] if parts else ""
+    out = {"": LIB_PATH, "tuning": TUNING_LIB_PATH, "check": CHECK_LIB_PATH}[base]
+    if len(parts) > 1:
+        out = out[:-3] + "_" + "_".join(p.replace("=", "_") for p in parts[1:]) + ".so"
     if not force and not needs_build(out):
         return out
     os.makedirs(LIB_DIR, exist_ok=True)
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    extra = ["-DUWCV_" + variant.upper()] if variant else []
+    extra = (["-DUWCV_" + base.upper()] if base else []) + ["-DUWCV_" + p for p in parts[1:]]
     cmd = [nvcc] + NVCC_FLAGS + extra + ["-o", out] + [os.path.join(CSRC, s) for s in SOURCES]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
