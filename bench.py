@@ -4,12 +4,15 @@
     python bench.py --gpus N --steps K --warmup W            our arm (CUDA, C ABI)
     python bench.py --impl reference --gpus N --steps K ...  the reference's CPU path
 
-Workload (BASELINE.json configs[1]): per GPU a batch of 64 synthetic 2048 x 2048 images
+Workload at N = 1 (BASELINE.json configs[1]): a batch of 64 synthetic 2048 x 2048 images
 with 1000 Mask R-CNN-shaped instances each (28 x 28 mask probabilities, boxes, scores,
-classes; uwcv/synth.py).  One step = one pass of the hot path over that batch:
+classes; uwcv/synth.py).  At N > 1 (configs[2], as written): 256 such images, image b on rank
+b % N (strong scaling: 128 / 64 / 32 images per GPU at 2 / 4 / 8), with the weak-scaling
+measurement (64 images per GPU) reported beside it as ``weak_scaling``; ``--images`` forces a
+fixed number of images per GPU.  One step = one pass of the hot path over the rank's batch:
 tile layout -> fused paste / threshold / bit-pack (Detectron2-literal full-frame
-planes, 1 bit / pixel) / moments -> border trace + descriptors; at N > 1 ranks an
-all-gather of the measurement table follows (image-sharded, weak scaling).
+planes, 1 bit / pixel) / moments -> border trace + descriptors; at N > 1 ranks the gather of the
+measurement table follows.
 
 Printed JSON keys (driver contract): metric/value/unit (instances measured per second,
 whole job), ms_per_step, mp_per_sec, e2e (same metric through the public call,
@@ -40,10 +43,13 @@ import torch  # noqa: E402
 
 H = W = 2048
 IMAGES_PER_GPU = 64
+CONFIG2_IMAGES = 256
 INSTANCES_PER_IMAGE = 1000
 METRIC = "instances_measured_per_sec"
 UNIT = "instances/s"
 WORKLOAD = "configs[1]: 64 synthetic 2048x2048 images x 1000 instances per GPU, full-frame bit-planes"
+WORKLOAD2 = ("configs[2]: 256 synthetic 2048x2048 images x 1000 instances, image b on rank b % N, "
+             "full-frame bit-planes, gather of the measurement table")
 
 
 def algorithmic_bytes_per_instance(h: int, w: int) -> int:
@@ -197,6 +203,139 @@ def run_reference(args):
 # our arm
 # ---------------------------------------------------------------------------------------
 
+class DeviceBatch:
+    """Device-resident inputs + outputs of one rank's batch (the `value` leg)."""
+
+    def __init__(self, eng, batch, rank, world, dev, with_planes=True):
+        import uwcv
+        from uwcv import api
+        self.eng, self.dev = eng, dev
+        boxes = torch.cat([api.scale_clip_boxes(b.pred_boxes.tensor, (H, W), (H, W))[0] for b in batch])
+        self.n = n = int(boxes.shape[0])
+        self.words = api.tile_words(boxes, H, W)
+        self.boxes = boxes.to(dev)
+        self.masks = torch.cat([b.pred_masks[:, 0] for b in batch]).contiguous().to(dev)
+        self.scores = torch.cat([b.scores for b in batch]).to(dev)
+        self.classes = torch.cat([b.pred_classes for b in batch]).to(dev)
+        self.img = torch.cat([torch.full((len(b),), rank + i * world, dtype=torch.int32)
+                              for i, b in enumerate(batch)]).to(dev)
+        self.inst = torch.cat([torch.arange(len(b), dtype=torch.int32) for b in batch]).to(dev)
+        self.planes = eng.alloc_planes(n, H, W) if with_planes else None
+        # two row tables / status words, used in turn: the border trace of step i runs on the
+        # engine's trace stream under the paste of step i + 1 (Engine.run_overlapped)
+        self.rows = [(torch.empty((n, 20), dtype=torch.int64, device=dev),
+                      torch.empty((n, 30), dtype=torch.float64, device=dev)) for _ in range(2)]
+        self.stat = [torch.zeros(4, dtype=torch.int64, device=dev) for _ in range(2)]
+        self.tick = 0
+
+    def args(self, planes=True):
+        return dict(image_idx=self.img, inst_idx=self.inst, classes=self.classes, scores=self.scores,
+                    planes=self.planes if planes else None, n_tile_words=self.words)
+
+    def stage(self, stages):                 # one kernel group alone, for the per-kernel times
+        self.eng.run(self.masks, self.boxes, H, W, rows_i=self.rows[0][0], rows_f=self.rows[0][1],
+                     stages=stages, **self.args())
+
+    def step(self, gather=None, after=None, planes=True):
+        k = self.tick & 1
+        self.tick += 1
+        ri, rf = self.rows[k]
+        self.eng.run_overlapped(self.masks, self.boxes, H, W, rows_i=ri, rows_f=rf, status=self.stat[k],
+                                gather=gather, after=after, **self.args(planes))
+        return k
+
+    def check_status(self):
+        for st in self.stat:
+            if int(st.cpu()[0]) != 0:
+                raise RuntimeError(f"workspace overflow: {st.cpu().tolist()}")
+
+
+def timed_steps(db, steps, warmup, barrier, step_fn):
+    """W warm-up steps, then exactly K steps between CUDA events on the launching stream, a
+    barrier + synchronize on both sides.  Returns (ms, wall0, wall1)."""
+    main = torch.cuda.current_stream(db.dev)
+    for _ in range(warmup):
+        step_fn()
+    barrier()
+    db.check_status()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    wall0 = time.time()
+    e0.record()
+    for _ in range(steps):
+        step_fn()
+    main.wait_stream(db.eng.trace_stream)       # the last traces (and gathers) end the region
+    e1.record()
+    barrier()
+    wall1 = time.time()
+    return e0.elapsed_time(e1), wall0, wall1
+
+
+def other_configs(eng, dev):
+    """configs[0] and configs[3] (parity-test shapes, not bench lines) with their kernel breakdown:
+    device-resident, full-frame planes, CUDA events per kernel group."""
+    import uwcv
+    from uwcv import api, synth
+
+    def breakdown(masks, boxes, Hc, Wc, reps=10):
+        n = int(boxes.shape[0])
+        words = api.tile_words(boxes.cpu(), Hc, Wc)
+        planes = eng.alloc_planes(n, Hc, Wc)
+        ri = torch.empty((n, 20), dtype=torch.int64, device=dev)
+        rf = torch.empty((n, 30), dtype=torch.float64, device=dev)
+        kw = dict(planes=planes, n_tile_words=words, rows_i=ri, rows_f=rf)
+        for _ in range(3):
+            eng.run(masks, boxes, Hc, Wc, **kw)
+        t = {1: [], 2: [], 4: []}
+        for _ in range(reps):
+            for st in (1, 2, 4):
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record(); eng.run(masks, boxes, Hc, Wc, stages=st, **kw); b.record(); b.synchronize()
+                t[st].append(a.elapsed_time(b))
+        lay, pas, tra = (statistics.mean(t[k]) for k in (1, 2, 4))
+        tot = lay + pas + tra
+        bpi = algorithmic_bytes_per_instance(Hc, Wc)
+        del planes
+        return {"instances": n, "image": f"{Hc}x{Wc}",
+                "kernel_ms": {"layout": lay, "paste_measure": pas, "contour": tra}, "ms": tot,
+                "instances_per_s": n / tot * 1e3, "paste_gbs_algorithmic": n * bpi / (pas * 1e-3) / 1e9,
+                "bytes_per_instance": bpi}
+
+    out = {}
+    gp = os.path.join(ROOT, "tests", "golden", "c1_maskrcnn.npz")
+    if os.path.exists(gp):
+        g = np.load(gp)
+        bx, keep = api.scale_clip_boxes(torch.from_numpy(g["boxes"]), (1024, 1024), (1024, 1024))
+        m = torch.from_numpy(g["masks"])[keep, 0].contiguous()
+        out["configs[0]_raw_maskrcnn_heads"] = breakdown(m.to(dev), bx[keep].contiguous().to(dev), 1024, 1024)
+        out["configs[0]_raw_maskrcnn_heads"]["note"] = (
+            "200 raw random-init head outputs: sub-pixel and 1024-px boxes, up to 90 speckle contours "
+            "per mask -- an edge-case parity input, one CTA / one trace lane per instance")
+    inst = synth.blob_instances(0, 200, 1024, 1024, seed=1234)
+    bx, keep = api.scale_clip_boxes(inst.pred_boxes.tensor, (1024, 1024), (1024, 1024))
+    out["configs[0]_shape_blob_source"] = breakdown(inst.pred_masks[keep, 0].contiguous().to(dev),
+                                                    bx[keep].contiguous().to(dev), 1024, 1024)
+    # configs[3]: 4096 x 4096, ~20 k clustered candidates -> score filter + per-class NMS -> ~5 k instances
+    Hc = Wc = 4096
+    cb, cs, cc = synth.clustered_candidates(5000, Hc, Wc, seed=99)
+    dcb, dcs, dcc = cb.to(dev), cs.to(dev), cc.to(dev)
+    for _ in range(3):
+        keep, cnt = eng.nms(dcb, dcs, dcc, [0, len(cb)], 0.05, 0.5, 6000)
+    tn = []
+    for _ in range(5):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); keep, cnt = eng.nms(dcb, dcs, dcc, [0, len(cb)], 0.05, 0.5, 6000); b.record(); b.synchronize()
+        tn.append(a.elapsed_time(b))
+    k = int(cnt[0])
+    keep = keep[:k].cpu()
+    gg = torch.Generator().manual_seed(8)
+    rec = breakdown(synth.blob_probs(k, gg).to(dev), cb[keep].contiguous().to(dev), Hc, Wc, reps=5)
+    rec["candidates"] = int(len(cb))
+    rec["kernel_ms"]["nms"] = statistics.mean(tn)
+    out["configs[3]_4096_dense"] = rec
+    return out
+
+
 def run_ours(args):
     import torch.distributed as dist
     import uwcv
@@ -215,8 +354,12 @@ def run_ours(args):
         os.environ.setdefault("TORCH_NCCL_HIGH_PRIORITY", "1")
         dist.init_process_group("nccl", device_id=dev)
 
-    n_img, n_inst = args.images, args.instances
-    # weak scaling: rank r owns images r, r + world, ... of a (n_img * world)-image set
+    # N = 1: configs[1].  N > 1: configs[2] as written (256 images over the ranks, strong scaling)
+    # unless --images fixes the images per GPU (weak scaling)
+    strong = world > 1 and args.images is None and CONFIG2_IMAGES % world == 0
+    n_img = CONFIG2_IMAGES // world if strong else (args.images or IMAGES_PER_GPU)
+    n_inst = args.instances
+    # rank r owns images r, r + world, ... of the (n_img * world)-image set
     batch = synth.blob_batch(n_img, n_inst, H, W, seed=1234, first_image=rank, stride=world)
     for inst in batch:                                  # pinned host copies for the e2e leg
         for k, v in list(inst.get_fields().items()):
@@ -225,25 +368,8 @@ def run_ours(args):
             else:
                 inst.set(k, uwcv.Boxes(v.tensor.pin_memory()))
     eng = api.Engine.get(dev)
-
-    # ---- device-resident inputs for `value` ------------------------------------------
-    boxes = torch.cat([api.scale_clip_boxes(b.pred_boxes.tensor, (H, W), (H, W))[0] for b in batch])
-    n = int(boxes.shape[0])
-    words = api.tile_words(boxes, H, W)
-    d_boxes = boxes.to(dev)
-    d_masks = torch.cat([b.pred_masks[:, 0] for b in batch]).contiguous().to(dev)
-    d_scores = torch.cat([b.scores for b in batch]).to(dev)
-    d_classes = torch.cat([b.pred_classes for b in batch]).to(dev)
-    d_img = torch.cat([torch.full((len(b),), rank + i * world, dtype=torch.int32)
-                       for i, b in enumerate(batch)]).to(dev)
-    d_inst = torch.cat([torch.arange(len(b), dtype=torch.int32) for b in batch]).to(dev)
-    planes = eng.alloc_planes(n, H, W)
-    # two row tables / status words, used in turn: the border trace of step i runs on the
-    # engine's trace stream under the paste of step i + 1 (Engine.run_overlapped)
-    rows = [(torch.empty((n, 20), dtype=torch.int64, device=dev),
-             torch.empty((n, 30), dtype=torch.float64, device=dev)) for _ in range(2)]
-    stat = [torch.zeros(4, dtype=torch.int64, device=dev) for _ in range(2)]
-    rows_i, rows_f = rows[0]
+    db = DeviceBatch(eng, batch, rank, world, dev)
+    n = db.n
     counts = None
     if world > 1:
         c = torch.tensor([n], dtype=torch.int64, device=dev)
@@ -252,39 +378,29 @@ def run_ours(args):
         counts = cs.cpu().tolist()
     total_instances = sum(counts) if counts else n
     main = torch.cuda.current_stream(dev)
-    tick = [0]
-
-    def step(stages=7):
-        args = dict(image_idx=d_img, inst_idx=d_inst, classes=d_classes, scores=d_scores,
-                    planes=planes, n_tile_words=words)
-        if stages != 7:                     # one kernel group alone, for the per-kernel times
-            eng.run(d_masks, d_boxes, H, W, rows_i=rows_i, rows_f=rows_f, stages=stages, **args)
-            return
-        k = tick[0] & 1
-        tick[0] += 1
-        ri, rf = rows[k]
-        if world > 1 and fused is not None:
-            # the one collective of the path, fused: the trace kernel stores the rows into every
-            # rank's table over NVLink, a symmetric-memory barrier completes them
-            g, gset, _total = fused.begin(counts)
-            eng.run_overlapped(d_masks, d_boxes, H, W, rows_i=ri, rows_f=rf, status=stat[k],
-                               gather=g, after=lambda: fused.barrier(gset), **args)
-            return
-        after = (lambda: udist.all_gather_table(ri, rf, counts=counts)) if world > 1 else None
-        eng.run_overlapped(d_masks, d_boxes, H, W, rows_i=ri, rows_f=rf, status=stat[k],
-                           after=after, **args)
-
     fused = eng.fused_gather() if world > 1 else None
+
+    def make_step(d, cts):
+        def step():
+            if world > 1 and fused is not None:
+                # the one collective of the path, fused: the trace kernel stores the rows into every
+                # rank's table over NVLink, a symmetric-memory barrier completes them
+                g, gset, _total = fused.begin(cts)
+                d.step(gather=g, after=lambda: fused.barrier(gset))
+            elif world > 1:
+                k = d.tick & 1
+                ri, rf = d.rows[k]
+                d.step(after=lambda: udist.all_gather_table(ri, rf, counts=cts))
+            else:
+                d.step()
+        return step
+
+    step = make_step(db, counts)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize(dev)
-
-    def check_status():
-        for st in stat:
-            if int(st.cpu()[0]) != 0:
-                raise RuntimeError(f"workspace overflow: {st.cpu().tolist()}")
 
     sampler = ClockSampler(local)
     if rank == 0:
@@ -292,16 +408,16 @@ def run_ours(args):
     for _ in range(max(args.warmup, 3)):
         step()
     barrier()
-    check_status()
+    db.check_status()
     gather_check = None
     if world > 1 and fused is not None:
         # one-time check of the fused gather against the NCCL all-gather of the same rows
         step()
         main.wait_stream(eng.trace_stream)
         torch.cuda.synchronize(dev)
-        k = (tick[0] - 1) & 1
+        k = (db.tick - 1) & 1
         ti, tf = fused.tables(fused.parity ^ 1, total_instances)
-        ni, nf = udist.all_gather_table(rows[k][0], rows[k][1], counts=counts)
+        ni, nf = udist.all_gather_table(db.rows[k][0], db.rows[k][1], counts=counts)
         same = torch.equal(ti, ni) and torch.equal(tf.nan_to_num(), nf.nan_to_num())
         flag = torch.tensor([int(same)], device=dev)
         dist.all_reduce(flag, op=dist.ReduceOp.MIN)
@@ -311,17 +427,7 @@ def run_ours(args):
 
     # ---- timed region: exactly K steps, CUDA events, max over ranks -------------------
     launches0 = eng.launches
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    wall0 = time.time()
-    e0.record()
-    for _ in range(args.steps):
-        step()
-    main.wait_stream(eng.trace_stream)          # the last traces (and all-gathers) end the region
-    e1.record()
-    barrier()
-    wall1 = time.time()
-    ms = e0.elapsed_time(e1)
+    ms, wall0, wall1 = timed_steps(db, args.steps, 0, barrier, step)
     launches = eng.launches - launches0
     clocks = None
     if rank == 0:
@@ -334,10 +440,7 @@ def run_ours(args):
             # (rank 0 only: the kernels without the collective, which the other ranks do not join)
             c0 = time.time()
             while time.time() - c0 < 1.0:
-                eng.run_overlapped(d_masks, d_boxes, H, W, rows_i=rows[0][0], rows_f=rows[0][1],
-                                   status=stat[0], image_idx=d_img, inst_idx=d_inst,
-                                   classes=d_classes, scores=d_scores, planes=planes,
-                                   n_tile_words=words)
+                db.step()
                 torch.cuda.synchronize(dev)
             time.sleep(0.12)
             fields = sampler.window(wall0, time.time())
@@ -357,7 +460,7 @@ def run_ours(args):
         for st in (1, 2, 4):
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
-            step(st)
+            db.stage(st)
             b.record()
             b.synchronize()
             kt[st].append(a.elapsed_time(b))
@@ -368,41 +471,90 @@ def run_ours(args):
     for _ in range(3):
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
-        planes.zero_()
+        db.planes.zero_()
         b.record()
         b.synchronize()
         mt.append(a.elapsed_time(b))
-    memset_gbs = planes.numel() * 4 / (min(mt) * 1e-3) / 1e9
+    memset_gbs = db.planes.numel() * 4 / (min(mt) * 1e-3) / 1e9
     peak, peak_src = measured_peak_gbs()
     bpi = algorithmic_bytes_per_instance(H, W)
     achieved = n * bpi / (k_paste * 1e-3) / 1e9
-    traffic = None
+    traffic, traffic_source = None, None
     tp = os.path.join(ROOT, "profiles", "paste_kernel_traffic.json")
     if os.path.exists(tp):
         try:
-            traffic = json.load(open(tp))["dram_bytes_per_instance"] * n
+            tj = json.load(open(tp))
+            traffic = tj["dram_bytes_per_instance"] * n
+            traffic_source = ("replayed from the committed ncu --set full capture, not measured in this "
+                              "run: " + tj.get("source", "profiles/paste_kernel_traffic.json"))
         except Exception:
             traffic = None
 
+    # ---- rows-only contract (no full-frame planes): the arithmetic alone, compute-bound --------
+    barrier()
+    ro_steps = max(3, min(args.steps, 20))
+    ro_ms, _, _ = timed_steps(db, ro_steps, 3, barrier, lambda: db.step(planes=False))
+    if world > 1:
+        t = torch.tensor([ro_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ro_ms = float(t.item())
+    rows_only = {"ms_per_step": ro_ms / ro_steps, "value": ro_steps * total_instances / (ro_ms * 1e-3),
+                 "unit": UNIT, "steps": ro_steps,
+                 "note": "same step without writing the full-frame planes (cropped contract, SURVEY 8(d)): "
+                         "~4.2 KB algorithmic bytes per instance, bound by the paste arithmetic and the "
+                         "serial border walks, not by HBM; no gather in this leg"}
+
+    # ---- weak-scaling line beside the strong configs[2] one (64 images per GPU) -----------------
+    weak = None
+    if strong:
+        if n_img == IMAGES_PER_GPU:
+            weak = {"value": value, "ms_per_step": ms / args.steps, "images_per_gpu": n_img,
+                    "note": "identical to the main line at this N"}
+        else:
+            planes_main = db.planes
+            db.planes = None
+            del planes_main
+            wb = batch[:IMAGES_PER_GPU]
+            wdb = DeviceBatch(eng, wb, rank, world, dev)
+            wc = torch.tensor([wdb.n], dtype=torch.int64, device=dev)
+            wcs = torch.empty(world, dtype=torch.int64, device=dev)
+            dist.all_gather_into_tensor(wcs, wc)
+            wcounts = wcs.cpu().tolist()
+            wsteps = max(3, min(args.steps, 20))
+            wms, _, _ = timed_steps(wdb, wsteps, 3, barrier, make_step(wdb, wcounts))
+            t = torch.tensor([wms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            wms = float(t.item())
+            weak = {"value": wsteps * sum(wcounts) / (wms * 1e-3), "ms_per_step": wms / wsteps,
+                    "images_per_gpu": IMAGES_PER_GPU, "steps": wsteps, "unit": UNIT}
+            del wdb
+
     # ---- e2e: the public call with pinned host inputs -----------------------------------
     h2d = sum(int(b.pred_masks.numel()) * 4 + len(b) * (16 + 4 + 8 + 4 + 4) for b in batch)
-    d2h = total_instances * (20 * 8 + 30 * 8) + 32     # rank 0 at N > 1: the gathered table
-    del planes
-    # at N > 1 the whole job's table goes to the host of rank 0 (the other ranks read their own
-    # rows): every rank's device holds the gathered table either way
+    d2h = n * (20 * 8 + 30 * 8) + 32 + (8 if world > 1 else 0)   # every rank: its own rows (+ flag word)
+    db.planes = None
+    del db
+    # at N > 1 the whole job's table is gathered to the host of rank 0: every rank copies its own
+    # rows into ONE host table shared by the ranks of the node (uwcv.dist.SharedHostTable); nothing
+    # moves between the devices and no rank reads another rank's rows over PCIe
     kw = dict(write_planes=True, gather=world > 1, gather_counts=counts,
               gather_dst=0 if world > 1 else None)
+    sink = None
+    if world > 1:
+        sink = "shared host table" if eng.host_table() is not None else "device all-gather + one read"
     if os.environ.get("UWCV_BENCH_E2E_NOGATHER"):            # probe: independent ranks
         kw = dict(write_planes=True)
-    for _ in range(3):                     # (keeps a table alive, as the timed loop does)
+    e2e_steps = args.steps
+    for _ in range(3):
         table = uwcv.measure_instances(batch, (H, W), device=dev, **kw)
     # (a) one synchronous call per step (latency form)
     barrier()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
+    for _ in range(e2e_steps):
         table = uwcv.measure_instances(batch, (H, W), device=dev, **kw)
     barrier()
     sync_s = time.perf_counter() - t0
+    del table
     # (b) the throughput form of the same call: uwcv.MeasurementStream keeps two calls in
     #     flight, so the H2D of step i + 1 and the D2H of step i - 1 run under the kernels of
     #     step i.  Every step still copies its inputs from pinned host memory and reads its
@@ -413,23 +565,50 @@ def run_ours(args):
     barrier()
     t0 = time.perf_counter()
     got = 0
-    for table in stream.map((batch for _ in range(args.steps)), (H, W), **kw):
+    crc = 0
+    for table in stream.map((batch for _ in range(e2e_steps)), (H, W), **kw):
         got += len(table)
+        crc ^= int(table.ints[-1, 5]) if len(table) else 0      # touch the last row on the host
     barrier()
     e2e_s = time.perf_counter() - t0
+    del table
     if not os.environ.get("UWCV_BENCH_E2E_NOGATHER"):
-        assert got == args.steps * (total_instances if rank == 0 else n), (got, total_instances, n)
+        assert got == e2e_steps * (total_instances if rank == 0 else n), (got, total_instances, n)
     if os.environ.get("UWCV_BENCH_VERBOSE"):
-        print(f"rank {rank}: e2e {e2e_s / args.steps * 1e3:.2f} ms/step, sync {sync_s / args.steps * 1e3:.2f}",
+        print(f"rank {rank}: e2e {e2e_s / e2e_steps * 1e3:.2f} ms/step, sync {sync_s / e2e_steps * 1e3:.2f}",
               file=sys.stderr, flush=True)
     if world > 1:
         t = torch.tensor([e2e_s, sync_s], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s, sync_s = float(t[0].item()), float(t[1].item())
-    e2e_val = args.steps * total_instances / e2e_s
+    e2e_val = e2e_steps * total_instances / e2e_s
 
-    # ---- CPU baseline (rank 0, N = 1 only) ------------------------------------------------
-    cpu = None
+    # ---- (c) the same call with DEVICE-resident inputs (what a caller holding the network's
+    #      outputs on the GPU pays: no mask H2D, rows still read back to the host every step)
+    dbatch = []
+    for inst in batch:
+        o = uwcv.Instances(inst.image_size)
+        for k, v in inst.get_fields().items():
+            o.set(k, uwcv.Boxes(v.tensor.to(dev)) if hasattr(v, "tensor") else v.to(dev))
+        dbatch.append(o)
+    for table in stream.map((dbatch for _ in range(3)), (H, W), **kw):
+        pass
+    barrier()
+    t0 = time.perf_counter()
+    for table in stream.map((dbatch for _ in range(e2e_steps)), (H, W), **kw):
+        pass
+    barrier()
+    dres_s = time.perf_counter() - t0
+    del table, dbatch
+    if world > 1:
+        t = torch.tensor([dres_s], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dres_s = float(t.item())
+
+    # ---- other configs + CPU baselines (rank 0, N = 1 only) ---------------------------------
+    cpu = cpu_b = others = None
+    if world == 1 and not args.no_other_configs:
+        others = other_configs(eng, dev)
     if world == 1 and not args.no_cpu_baseline:
         nc = 250
         sample = synth.blob_instances(0, nc, H, W, seed=1234)
@@ -439,31 +618,45 @@ def run_ours(args):
         cpu = {"value": done / dt, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
                "sample": f"1 image 2048x2048 x {nc} instances, detector_postprocess + "
                          f"4 x GetMask_Contours (oracle restatement), {dt:.1f} s"}
+        # BASELINE.md section 4, baseline B ("per-instance"): oracle paste -> cv2.moments, bbox,
+        # external contours, descriptor block per instance
+        from oracle import pipeline as P
+        t0 = time.perf_counter()
+        ri_, _rf = P.oracle_table([sample], (H, W))
+        dt = time.perf_counter() - t0
+        cpu_b = {"value": ri_.shape[0] / dt, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                 "sample": f"1 image 2048x2048 x {nc} instances, per-instance CPU paste + cv2.moments + "
+                           f"findContours + descriptor block (oracle.pipeline.oracle_table), {dt:.1f} s"}
 
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic",
-            "config": {"workload": WORKLOAD, "images_per_gpu": n_img,
+            "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD2 if strong else WORKLOAD, "images_per_gpu": n_img,
+                       "images_total": n_img * world,
                        "instances_per_image": n_inst, "image": f"{H}x{W}",
                        "instances_per_gpu": n, "mask_output": "full-frame bit-planes in HBM",
-                       "l2": "inputs (200 MB) and outputs (33.5 GB) per step exceed the 126 MB L2",
+                       "l2": "inputs (200 MB) and outputs (33.5 GB) per 64 images exceed the 126 MB L2",
                        "collective": "none" if world == 1 else
                        ("all-gather of the row table fused into the trace kernel (peer stores "
                         "over NVLink into symmetric memory + signal barrier)" if fused is not None
                         else "NCCL all_gather of the row table")},
             "mp_per_sec": args.steps * world * n_img * H * W / 1e6 / (ms * 1e-3),
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": d2h, "ms_per_step": e2e_s / args.steps * 1e3,
+                    "d2h_bytes_per_step": d2h, "ms_per_step": e2e_s / e2e_steps * 1e3,
                     "call": "uwcv.MeasurementStream(depth=2).map (pinned host Instances in, "
                             "host MeasurementTable out, every step)",
-                    "sync_call_ms_per_step": sync_s / args.steps * 1e3},
+                    "sync_call_ms_per_step": sync_s / e2e_steps * 1e3,
+                    "device_resident_inputs_ms_per_step": dres_s / e2e_steps * 1e3,
+                    "device_resident_inputs_value": e2e_steps * total_instances / dres_s},
             "gpu_launches": launches,
             "kernel_ms": {"layout": k_layout, "paste_measure": k_paste, "contour": k_contour},
+            "rows_only": rows_only,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                         "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_source,
+                         "peak_source": peak_src,
                          "kernel": "paste_measure_kernel<true>",
                          "bytes_per_instance": bpi, "instances_per_launch": n,
                          "frac_of_nominal_8000": achieved / 8000.0,
@@ -473,10 +666,19 @@ def run_ours(args):
                          "frac_of_zero_fill": achieved / memset_gbs},
             "clocks": clocks,
         }
+        if world > 1:
+            line["e2e"]["gather_sink"] = sink
+            line["e2e"]["d2h_note"] = "per rank: its own rows into the node-shared host table"
         if gather_check is not None:
             line["config"]["fused_gather_equals_nccl"] = gather_check
+        if weak is not None:
+            line["weak_scaling"] = weak
+        if others is not None:
+            line["other_configs"] = others
         if cpu is not None:
             line["cpu_baseline"] = cpu
+        if cpu_b is not None:
+            line["cpu_baseline_b"] = cpu_b
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -485,10 +687,13 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=200,
+                    help="timed steps (default: a timed region above one second)")
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--images", type=int, default=IMAGES_PER_GPU)
+    ap.add_argument("--images", type=int, default=None,
+                    help="images per GPU (default: 64 at N = 1; 256 / N at N > 1, configs[2])")
+    ap.add_argument("--no-other-configs", action="store_true")
     ap.add_argument("--instances", type=int, default=INSTANCES_PER_IMAGE)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

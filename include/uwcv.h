@@ -151,6 +151,8 @@ int uwcv_paste_measure_heads(const float* masks, int mask_channels, int channel_
  * complete on every rank once all ranks have passed a barrier issued on `stream` after this
  * call (the caller's: e.g. a symmetric-memory signal barrier); no NCCL kernel is involved.
  * gather == NULL or gather->world == 0: no gather.  Stage 4 must cover the whole call.
+ * gather->dst_plus_1 = p + 1 restricts the stores to rank p's table (the other pointers may be
+ * NULL): a gather to one destination costs one copy of the rows over NVLink instead of `world`.
  *
  * Stands in for the dist all-gather the image-sharded job ends with (there is none in the
  * single-process reference; nn_inference.py:485-498 loops over all images in one process).
@@ -158,7 +160,8 @@ int uwcv_paste_measure_heads(const float* masks, int mask_channels, int channel_
 #define UWCV_MAX_PEERS 16
 typedef struct uwcv_gather {
   int32_t world;                       /* number of ranks, <= UWCV_MAX_PEERS */
-  int32_t reserved;
+  int32_t dst_plus_1;                  /* 0: store into every rank's table (all-gather);
+                                          p + 1: only into the table of rank p (gather to p) */
   int64_t row_base;                    /* first row of this rank in the gathered tables */
   int64_t* rows_i[UWCV_MAX_PEERS];     /* [total_rows, UWCV_NUM_INT] of rank p   */
   double* rows_f[UWCV_MAX_PEERS];      /* [total_rows, UWCV_NUM_FLOAT] of rank p */
@@ -181,7 +184,7 @@ int uwcv_unpack_planes(const uint32_t* bitplanes, int64_t N, int H, int W, uint8
                        void* stream);
 
 /*
- * uwcv_ingest -- copy `bytes` (rounded up to 16: both buffers must be padded accordingly) from
+ * uwcv_ingest -- copy `bytes` (a multiple of 16, else UWCV_E_SHAPE) from
  * pinned, device-mapped HOST memory (cudaHostAlloc / torch pin_memory under unified addressing)
  * to device memory with a kernel instead of the copy engine.  For the small per-call arrays
  * (boxes, scores, classes, indices): a cudaMemcpyAsync of 1 MB issued behind the 200 MB of mask

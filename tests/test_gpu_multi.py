@@ -21,6 +21,7 @@ def _worker(rank, world, port, q):
     from uwcv import synth
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
+    os.environ["LOCAL_WORLD_SIZE"] = str(world)            # one node, as torchrun would say
     torch.cuda.set_device(rank)
     dev = torch.device("cuda", rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
@@ -38,11 +39,23 @@ def _worker(rank, world, port, q):
         offs = [rank]                                          # image index = position in the whole set
         for t in stream.map(batches, (H, W), gather=True):
             outs.append((t.ints.copy(), t.floats.copy()))
+        # gather to rank 0 with the HOST as the sink (node-shared pinned table; every rank copies
+        # its own rows), then with the device gather restricted to the destination's table
+        host_ok = eng.host_table() is not None
+        dst_outs = {}
+        for sink in (("host",) if host_ok else ()) + ("device",):
+            got = []
+            for t in stream.map(batches, (H, W), gather=True, gather_dst=0, gather_sink=sink):
+                got.append((t.ints.copy(), t.floats.copy()))
+                del t
+            dst_outs[sink] = got
         # the NCCL path on the same inputs
         os.environ["UWCV_NO_FUSED_GATHER"] = "1"
         eng._fused = None
         ref = [uwcv.measure_instances(b, (H, W), gather=True, device=dev) for b in batches]
-        q.put((rank, fused, outs, [(r.ints.copy(), r.floats.copy()) for r in ref]))
+        own = [uwcv.measure_instances(b, (H, W), device=dev, image_idx_offset=0) for b in batches]
+        q.put((rank, fused, outs, [(r.ints.copy(), r.floats.copy()) for r in ref], host_ok, dst_outs,
+               [(r.ints.copy(), r.floats.copy()) for r in own]))
     finally:
         dist.destroy_process_group()
 
@@ -61,10 +74,20 @@ def test_fused_gather_equals_nccl_all_gather():
         p.join(timeout=120)
         assert p.exitcode == 0
     assert all(r[1] for r in res), "symmetric-memory gather was not available on this box"
-    for rank, fused, outs, ref in res:
+    for rank, fused, outs, ref, host_ok, dst_outs, own in res:
         for (gi, gf), (ri, rf) in zip(outs, ref):
             assert np.array_equal(gi, ri)
             assert np.array_equal(gf, rf, equal_nan=True)
+        assert host_ok, "the node-shared host table was not available on this box"
+        for sink, got in dst_outs.items():
+            for k, (gi, gf) in enumerate(got):
+                if rank == 0:                      # the destination holds the whole job's table
+                    assert np.array_equal(gi, ref[k][0]), (sink, k)
+                    assert np.array_equal(gf, ref[k][1], equal_nan=True), (sink, k)
+                else:                              # the others their own rows (image index aside)
+                    assert gi.shape == own[k][0].shape, (sink, k)
+                    assert np.array_equal(gi[:, 1:], own[k][0][:, 1:]), (sink, k)
+                    assert np.array_equal(gf, own[k][1], equal_nan=True), (sink, k)
     # both ranks hold the same whole-job table
     for a, b in zip(res[0][2], res[1][2]):
         assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1], equal_nan=True)

@@ -758,3 +758,36 @@ def test_fused_gather_branch_on_one_gpu():
     ri, rf, _ = eng.run(parts[1][0], parts[1][1], H, W, classes=parts[1][3], scores=parts[1][2],
                         image_idx=torch.full((counts[1],), 1, dtype=torch.int32, device=dev))
     assert torch.equal(ri, plain[1][0]) and torch.equal(rf.nan_to_num(), plain[1][1].nan_to_num())
+
+
+def test_device_resident_inputs_take_the_sync_free_path_and_fall_back():
+    """Predictor output that already lives on the GPU (the single-forward path) is measured without
+    a host synchronisation: 'no box is dropped' is assumed and verified by a device flag read back
+    with the rows.  Same table as with host inputs; a batch with an empty box falls back to the
+    general path and still equals the host result (the box is dropped, as Boxes.nonempty does)."""
+    dev = torch.device("cuda", 0)
+    H, W = 240, 336
+    batch = [synth.blob_instances(k, 30 + 5 * k, H, W, seed=410) for k in range(3)]
+
+    def to_dev(b):
+        out = []
+        for inst in b:
+            o = uwcv.Instances(inst.image_size)
+            for k, v in inst.get_fields().items():
+                o.set(k, uwcv.Boxes(v.tensor.to(dev)) if hasattr(v, "tensor") else v.to(dev))
+            out.append(o)
+        return out
+
+    want = uwcv.measure_instances(batch, (H, W), device=dev)
+    got = uwcv.measure_instances(to_dev(batch), (H, W), device=dev)
+    assert np.array_equal(got.ints, want.ints) and np.array_equal(got.floats, want.floats, equal_nan=True)
+    stream = uwcv.MeasurementStream(dev, depth=2)
+    for t in stream.map([to_dev(batch)] * 3, (H, W)):
+        assert np.array_equal(t.ints, want.ints)
+    # an empty (zero-width) box in image 1: dropped by detector_postprocess
+    bad = [synth.blob_instances(k, 30 + 5 * k, H, W, seed=410) for k in range(3)]
+    bad[1].pred_boxes.tensor[4, 2] = bad[1].pred_boxes.tensor[4, 0]
+    want = uwcv.measure_instances(bad, (H, W), device=dev)
+    got = uwcv.measure_instances(to_dev(bad), (H, W), device=dev)
+    assert len(want) == sum(len(b) for b in batch) - 1
+    assert np.array_equal(got.ints, want.ints) and np.array_equal(got.floats, want.floats, equal_nan=True)

@@ -98,10 +98,8 @@ contour_measure_kernel(int64_t first, int64_t n, int lanes, const float* __restr
   // for a shared-memory slot) is traced here, lane per instance: each iteration of the
   // warp-uniform loop advances a lane by one 64-pixel scan step or one border step
   // (LaneTracer), so no lane waits for another lane's contour.
-  TraceRec rec;
-  rec.ncont = kNotTraced; rec.a2 = -1; rec.perim = 0.0; rec.best_y = 0; rec.best_ymax = -1; rec.npts = 0;
-  if (live) rec = ws.rec[inst];
-  const bool pre = live && rec.ncont != kNotTraced;
+  const int pre_ncont = live ? ws.rec[inst].ncont : kNotTraced;
+  const bool pre = pre_ncont != kNotTraced;
   TileView t;
   t.M = ws.M + d.word_off; t.V = ws.V + d.word_off; t.G = ws.G + d.word_off;
   t.tw = d.tw; t.th = d.th;
@@ -128,6 +126,7 @@ contour_measure_kernel(int64_t first, int64_t n, int lanes, const float* __restr
   double best_perim = T.best_perim;
   uint32_t* best = T.best;
   if (pre) {
+    const TraceRec rec = ws.rec[inst];
     ncont = rec.ncont; best_npts = rec.npts; best_y = rec.best_y; best_ymax = rec.best_ymax;
     best_a2 = rec.a2; best_perim = rec.perim; best = ext0;
   } else if (work) {
@@ -159,6 +158,7 @@ contour_measure_kernel(int64_t first, int64_t n, int lanes, const float* __restr
       const uint4* sf = reinterpret_cast<const uint4*>(rows_f + w0 * kNumFloat);
       const int ni = cnt * (kNumInt * 8 / 16), nf = cnt * (kNumFloat * 8 / 16);
       for (int p = 0; p < g.world; ++p) {
+        if (g.only >= 0 && p != g.only) continue;      // gather to one destination
         uint4* di = reinterpret_cast<uint4*>(g.rows_i[p] + (g.row_base + w0) * kNumInt);
         uint4* df = reinterpret_cast<uint4*>(g.rows_f[p] + (g.row_base + w0) * kNumFloat);
         for (int k = lane; k < ni; k += 32) di[k] = si[k];

@@ -100,13 +100,19 @@ int uwcv_paste_measure_gather(const float* masks, int mask_channels, int channel
   if (N < 0 || H <= 0 || W <= 0) return UWCV_E_SHAPE;
   uwcv::GatherDst gd;
   gd.world = 0;
+  gd.only = -1;
   gd.row_base = 0;
   if (gather && gather->world > 0) {
     if (gather->world > UWCV_MAX_PEERS || gather->row_base < 0) return UWCV_E_SHAPE;
     if ((stages & 4) && (first != 0 || count != N)) return UWCV_E_SHAPE;   // whole-call traces only
+    if (gather->dst_plus_1 < 0 || gather->dst_plus_1 > gather->world) return UWCV_E_SHAPE;
     gd.world = gather->world;
+    gd.only = gather->dst_plus_1 - 1;
     gd.row_base = gather->row_base;
     for (int p = 0; p < gather->world; ++p) {
+      gd.rows_i[p] = nullptr;
+      gd.rows_f[p] = nullptr;
+      if (gd.only >= 0 && p != gd.only) continue;     // only the destination's table is touched
       if (!gather->rows_i[p] || !gather->rows_f[p]) return UWCV_E_NULL;
       if (misaligned(gather->rows_i[p]) || misaligned(gather->rows_f[p])) return UWCV_E_ALIGN;
       gd.rows_i[p] = gather->rows_i[p];
@@ -229,6 +235,7 @@ int uwcv_ingest(const void* src_host_mapped, void* dst, size_t bytes, void* stre
   if (bytes == 0) return UWCV_OK;
   if (!src_host_mapped || !dst) return UWCV_E_NULL;
   if (misaligned(src_host_mapped) || misaligned(dst)) return UWCV_E_ALIGN;
+  if (bytes % 16) return UWCV_E_SHAPE;                 // whole 16-byte words: nothing is read or written past the buffers
   return uwcv::launch_ingest(src_host_mapped, dst, bytes, reinterpret_cast<cudaStream_t>(stream)) ==
                  cudaSuccess
              ? UWCV_OK : UWCV_E_LAUNCH;

@@ -57,6 +57,7 @@ struct MaskSource {
 constexpr int kMaxPeers = 16;
 struct GatherDst {
   int world;                       // 0: no gather
+  int only;                        // -1: every rank's table; p: the table of rank p alone
   int64_t row_base;                // first row of this rank in the gathered tables
   int64_t* rows_i[kMaxPeers];      // [total_rows, kNumInt]   per peer (this rank included)
   double* rows_f[kMaxPeers];       // [total_rows, kNumFloat] per peer

@@ -27,7 +27,7 @@ MAX_PEERS = 16
 
 class Gather(C.Structure):
     """uwcv_gather of include/uwcv.h."""
-    _fields_ = [("world", C.c_int32), ("reserved", C.c_int32), ("row_base", C.c_int64),
+    _fields_ = [("world", C.c_int32), ("dst_plus_1", C.c_int32), ("row_base", C.c_int64),
                 ("rows_i", C.c_void_p * MAX_PEERS), ("rows_f", C.c_void_p * MAX_PEERS)]
 
 E_CAPACITY = -7

@@ -55,8 +55,8 @@ def _stream_ptr(device: torch.device) -> int:
 # box glue: the three Detectron2 ops that must be bit-identical
 # ----------------------------------------------------------------------------------
 
-def scale_clip_boxes(boxes: torch.Tensor, in_size: Tuple[int, int], out_size: Tuple[int, int]
-                     ) -> Tuple[torch.Tensor, torch.Tensor]:
+def scale_clip_boxes(boxes: torch.Tensor, in_size: Tuple[int, int], out_size: Tuple[int, int],
+                     check: bool = True) -> Tuple[torch.Tensor, torch.Tensor]:
     """Boxes.scale + Boxes.clip + Boxes.nonempty of detector_postprocess.
     Returns (output-space boxes, keep mask); works on whatever device ``boxes`` is on.
     Same float32 operations as Detectron2's column-wise ``tensor[:, 0::2] *= scale_x`` /
@@ -71,7 +71,8 @@ def scale_clip_boxes(boxes: torch.Tensor, in_size: Tuple[int, int], out_size: Tu
         b = b * scale_x if scale_x != 1.0 else b.clone()
     else:
         b = b * torch.tensor([scale_x, scale_y, scale_x, scale_y], **kw)
-    if b.numel() and not bool(b.abs().max() < float("inf")):          # inf or NaN anywhere
+    # (``check=False``: the caller verifies finiteness itself, without a host synchronisation)
+    if check and b.numel() and not bool(b.abs().max() < float("inf")):          # inf or NaN anywhere
         raise AssertionError("Box tensor contains infinite or NaN!")   # Boxes.clip asserts
     if out_w == out_h:
         b = b.clamp_(min=0, max=out_w)
@@ -176,6 +177,22 @@ class MeasurementTable:
         return df
 
 
+class HostLease:
+    """Owner object of a span of (pinned or shared) host memory handed to the caller as numpy
+    arrays: ``array()`` is an int64 view whose ``.base`` is the lease, every view derived from
+    it keeps the lease alive, and ``on_release`` runs once when the last one is gone."""
+
+    def __init__(self, ptr: int, n_int64: int, on_release, keep=None):
+        import weakref
+        self.__array_interface__ = {"shape": (int(n_int64),), "typestr": "<i8",
+                                    "data": (int(ptr), False), "version": 3}
+        self._keep = keep                      # whatever owns the memory (tensor, mmap)
+        weakref.finalize(self, on_release)
+
+    def array(self) -> np.ndarray:
+        return np.asarray(self)
+
+
 # ----------------------------------------------------------------------------------
 # the engine: buffers + the C-ABI calls
 # ----------------------------------------------------------------------------------
@@ -220,24 +237,30 @@ class Engine:
         self._fused = None
 
     def host_rows(self, r: int):
-        """Pinned host memory for one call's rows, recycled once the table that was handed out
-        with it is gone: returns (torch int64 [r,20], torch float64 [r,30], and the numpy views
-        of the same memory that the MeasurementTable will own).  A buffer is free when nothing
-        but the pool refers to its root array (every numpy view keeps a reference to it)."""
-        import sys
+        """Pinned host memory for one call's rows: returns (torch int64 [r,20], torch float64
+        [r,30], and the numpy views of the same memory that the MeasurementTable will own).
+        Ownership is explicit: the numpy views hang off a ``HostLease`` (their ``.base``), and
+        the buffer goes back to the pool when the lease dies, i.e. when the table AND every
+        slice the caller took from it are gone -- no reference counting by hand."""
         need = max(r * (NUM_INT + NUM_FLOAT), 1)
         entry = None
         for e in self._host_pool:
-            if e[0].numel() >= need and sys.getrefcount(e[1]) == 2:
+            if e["free"] and e["buf"].numel() >= need:
                 entry = e
                 break
         if entry is None:
-            self._host_pool = [e for e in self._host_pool
-                               if sys.getrefcount(e[1]) > 2 or e[0].numel() >= need]
+            # drop free buffers that are too small; leased ones stay until their lease ends
+            self._host_pool = [e for e in self._host_pool if not e["free"]]
             buf = torch.empty(int(need * 1.1) + 64, dtype=torch.int64).pin_memory()
-            entry = [buf, buf.numpy()]
+            entry = {"buf": buf, "free": True}
             self._host_pool.append(entry)
-        buf, arr = entry
+        entry["free"] = False
+        buf = entry["buf"]
+
+        def give_back(e=entry):
+            e["free"] = True
+
+        arr = HostLease(buf.data_ptr(), buf.numel(), give_back, keep=buf).array()
         a, b = r * NUM_INT, r * (NUM_INT + NUM_FLOAT)
         t_i = buf[:a].view(r, NUM_INT)
         t_f = buf[a:b].view(torch.float64).view(r, NUM_FLOAT)
@@ -272,6 +295,34 @@ class Engine:
                 if int(t.item()) == 1:
                     self._fused = fg
         return self._fused or None
+
+    def host_table(self):
+        """The node-shared host table of this device's process group (created on first use, a
+        collective), or None when it cannot be set up on every rank (not one node, shared memory
+        or cudaHostRegister unavailable): the caller then gathers on the devices."""
+        if getattr(self, "_host_table", None) is None:
+            self._host_table = False
+            import os
+            import torch.distributed as dist
+            if dist_is_multi() and dist.get_backend() == "nccl":
+                one_node = int(os.environ.get("LOCAL_WORLD_SIZE", "0")) == dist.get_world_size()
+                ok = 1 if one_node else 0
+                ht = None
+                if ok:
+                    try:
+                        from .dist import SharedHostTable
+                        ht = SharedHostTable(self.device)
+                        ht.ensure(1024)
+                    except Exception as e:                  # noqa: BLE001
+                        import warnings
+                        warnings.warn(f"uwcv: shared host table unavailable ({type(e).__name__}: {e}); "
+                                      "gathering on the devices")
+                        ok = 0
+                t = torch.tensor([ok], dtype=torch.int32, device=self.device)
+                dist.all_reduce(t, op=dist.ReduceOp.MIN)
+                if int(t.item()) == 1:
+                    self._host_table = ht
+        return self._host_table or None
 
     def slot(self, k: int = 0) -> "_Slot":
         s = self._slots.get(k)
@@ -612,6 +663,9 @@ class PendingTable:
         self._slot = slot
         self._retry = retry
         self._done = None
+        self._redo = None
+        self.hp_ok = None
+        self._after_sync = None
         self._value = None
         self.n = 0
         self.planes = None
@@ -628,6 +682,16 @@ class PendingTable:
         if self._value is not None:
             return self._value[0]
         self._done.synchronize()
+        if self._after_sync is not None:
+            self._after_sync()
+            self._after_sync = None
+        if self.hp_ok is not None and int(self.hp_ok[0]) == 0:
+            # the optimistic device-input path met an empty or non-finite box: general path
+            redo = self._redo
+            self._release()
+            value = redo()
+            self._value = (value,)
+            return value
         st = self.hp_s
         code = int(st[0])
         if code != 0:
@@ -658,7 +722,8 @@ def measure_instances(instances: Union[object, Sequence[object]],
                       image_idx_offset: int = 0, return_planes: bool = False,
                       write_planes: bool = False, gather: bool = False,
                       gather_counts: Optional[Sequence[int]] = None,
-                      gather_dst: Optional[int] = None, mask_channel_offset: int = 0,
+                      gather_dst: Optional[int] = None, gather_sink: str = "auto",
+                      mask_channel_offset: int = 0,
                       pipeline_chunks: int = 4, device=None, _exact_words: bool = False):
     """Per-instance measurement rows for one image or a batch of images.
 
@@ -675,8 +740,13 @@ def measure_instances(instances: Union[object, Sequence[object]],
     process per GPU, images sharded over ranks) all-gathers the device rows of every rank
     before the host read, so each rank returns the whole job's table; ``gather_counts``
     (rows per rank, when the caller knows them) skips the count exchange; ``gather_dst=r``
-    brings the whole table to the host of rank r only (the other ranks return their own rows:
-    N times less device->host traffic on the box).
+    brings the whole table to the host of rank r only (the other ranks return their own rows).
+    With a destination and all ranks on one node the HOST is the sink (``gather_sink="auto"`` /
+    ``"host"``): every rank copies its own rows into one host table shared by the ranks
+    (``uwcv.dist.SharedHostTable``), nothing is gathered on the devices and no rank reads another
+    rank's rows over PCIe; ``gather_sink="device"`` keeps the device all-gather + one big read.
+    Tables of host-gathered calls are views of that shared memory: copy or drop them within two
+    calls.
 
     Single-forward form: instead of ``pred_masks`` the instances may carry
     ``pred_mask_logits`` (N x K x 28 x 28, the mask head's raw output); the kernel reads channel
@@ -691,7 +761,7 @@ def measure_instances(instances: Union[object, Sequence[object]],
         instances, output_size, classes_of_interest, mask_threshold=mask_threshold,
         pixels_per_metric=pixels_per_metric, image_idx_offset=image_idx_offset,
         return_planes=return_planes, write_planes=write_planes, gather=gather,
-        gather_counts=gather_counts, gather_dst=gather_dst,
+        gather_counts=gather_counts, gather_dst=gather_dst, gather_sink=gather_sink,
         mask_channel_offset=mask_channel_offset, pipeline_chunks=pipeline_chunks, device=device,
         _exact_words=_exact_words).result()
 
@@ -733,9 +803,10 @@ def submit_measure_instances(instances, output_size=None, classes_of_interest=No
                              image_idx_offset: int = 0, return_planes: bool = False,
                              write_planes: bool = False, gather: bool = False,
                              gather_counts: Optional[Sequence[int]] = None,
-                             gather_dst: Optional[int] = None, mask_channel_offset: int = 0,
+                             gather_dst: Optional[int] = None, gather_sink: str = "auto",
+                             mask_channel_offset: int = 0,
                              pipeline_chunks: int = 4, device=None, _exact_words: bool = False,
-                             _slot: int = 0) -> PendingTable:
+                             _slot: int = 0, _no_fast: bool = False) -> PendingTable:
     """Enqueue one ``measure_instances`` call (same arguments) and return its handle."""
     single = not isinstance(instances, (list, tuple))
     batch: List[object] = [instances] if single else list(instances)
@@ -791,6 +862,27 @@ def submit_measure_instances(instances, output_size=None, classes_of_interest=No
             counts_fast = lens
         else:
             early = None
+    d_ok = None
+    if counts_fast is None and not _no_fast and len(sizes) == 1 and classes_of_interest is None and \
+            all(_as_box_tensor(i.pred_boxes).is_cuda and _as_box_tensor(i.pred_boxes).device == dev
+                for i in batch) and not any(_has(i, "orig_idx") for i in batch):
+        # device-resident predictor output (the single-forward path): nothing here may wait for
+        # the GPU, so "no box is dropped, every box is finite" is ASSUMED, computed on the device
+        # as a flag and read back with the rows; a call whose flag is false is repeated through
+        # the general path below (rare: empty or non-finite boxes after clipping)
+        lens = [len(i) for i in batch]
+        allb = torch.cat([_as_box_tensor(i.pred_boxes) for i in batch]).to(torch.float32)
+        b_all, keep_all = scale_clip_boxes(allb, batch[0].image_size, (H, W), check=False)
+        d_ok = (keep_all.all() & torch.isfinite(allb).all()).to(torch.int64).reshape(1)
+        bl = [b_all]
+        sl = [i.scores.to(torch.float32) for i in batch]
+        cl = [i.pred_classes.to(torch.int64) for i in batch]
+        ml = [m.to(torch.float32).reshape(-1, mrow) for m, _ in mfields]
+        lt = torch.tensor(lens, dtype=torch.int64)
+        il = [torch.repeat_interleave(torch.arange(len(batch), dtype=torch.int32) + image_idx_offset, lt)]
+        offs = torch.cumsum(lt, 0) - lt
+        jl = [(torch.arange(int(lt.sum()), dtype=torch.int64) - torch.repeat_interleave(offs, lt)).to(torch.int32)]
+        counts_fast = lens
     for k, inst in enumerate(batch if counts_fast is None else []):
         boxes, scores, classes, masks = _gather_fields(inst, classes_of_interest)
         out_sz = (H, W)
@@ -826,8 +918,8 @@ def submit_measure_instances(instances, output_size=None, classes_of_interest=No
     # (a gathered call must not be repeated on one rank only: it is sized by an upper bound)
     if _exact_words:
         n_words = tile_words(boxes, H, W)
-    elif eng._ws is None or gathered:
-        n_words = tile_words_bound(boxes)
+    elif eng._ws is None or (gathered and not boxes.is_cuda):
+        n_words = tile_words_bound(boxes)             # (device boxes: one synchronising read, first call only)
     else:
         n_words = eng._cap_words
     counts = counts_fast if counts_fast is not None else [int(b.shape[0]) for b in bl]
@@ -839,12 +931,24 @@ def submit_measure_instances(instances, output_size=None, classes_of_interest=No
             instances, output_size, classes_of_interest, mask_threshold=mask_threshold,
             pixels_per_metric=pixels_per_metric, image_idx_offset=image_idx_offset,
             return_planes=return_planes, write_planes=write_planes, gather=gather,
-            gather_counts=gather_counts, gather_dst=gather_dst,
+            gather_counts=gather_counts, gather_dst=gather_dst, gather_sink=gather_sink,
             mask_channel_offset=mask_channel_offset, pipeline_chunks=pipeline_chunks,
             device=device, _exact_words=True)
 
     pend = PendingTable(slot, None if _exact_words else retry)
     pend.return_planes = return_planes
+    if d_ok is not None:
+        def redo():
+            if gathered:
+                raise RuntimeError("uwcv: empty or non-finite boxes in a gathered call with device-resident "
+                                   "inputs; filter them (Boxes.nonempty) before the call")
+            return submit_measure_instances(
+                instances, output_size, classes_of_interest, mask_threshold=mask_threshold,
+                pixels_per_metric=pixels_per_metric, image_idx_offset=image_idx_offset,
+                return_planes=return_planes, write_planes=write_planes,
+                mask_channel_offset=mask_channel_offset, pipeline_chunks=pipeline_chunks,
+                device=device, _no_fast=True).result()
+        pend._redo = redo
     with torch.cuda.device(dev):
         if early is None:
             early = _issue_mask_copies(eng, slot, dev, ml, counts, pipeline_chunks)
@@ -918,8 +1022,24 @@ def submit_measure_instances(instances, output_size=None, classes_of_interest=No
             from .dist import all_gather_table
             out["i"], out["f"] = all_gather_table(rows_i, rows_f, counts=gather_counts)
 
-        fg = eng.fused_gather() if gathered else None
+        if gather_sink not in ("auto", "host", "device"):
+            raise ValueError("gather_sink must be 'auto', 'host' or 'device'")
+        ht = None
+        if gathered and gather_dst is not None and gather_sink != "device":
+            ht = eng.host_table()
+            if ht is None and gather_sink == "host":
+                raise RuntimeError("uwcv: the shared host table is not available for this group")
+        fg = eng.fused_gather() if (gathered and ht is None) else None
         gstruct = gset = None
+        if ht is not None:
+            cts = gather_counts
+            if cts is None:
+                import torch.distributed as dist
+                c_l = torch.tensor([n], dtype=torch.int64, device=dev)
+                c_all = torch.empty(ht.world, dtype=torch.int64, device=dev)
+                dist.all_gather_into_tensor(c_all, c_l)
+                cts = c_all.cpu().tolist()
+            hk, hseq, hbase, htotal = ht.begin(cts)
         if fg is not None:
             # fused all-gather: the trace kernel stores the rows into every rank's table
             # (symmetric memory over NVLink), a signal barrier completes them -- no collective
@@ -931,7 +1051,7 @@ def submit_measure_instances(instances, output_size=None, classes_of_interest=No
                 c_all = torch.empty(fg.world, dtype=torch.int64, device=dev)
                 dist.all_gather_into_tensor(c_all, c_l)
                 cts = c_all.cpu().tolist()
-            gstruct, gset, g_total = fg.begin(cts)
+            gstruct, gset, g_total = fg.begin(cts, dst=gather_dst)
         if n > 0:
             rows_done = eng.run_overlapped(
                 d_masks, d_boxes, H, W,
@@ -948,6 +1068,8 @@ def submit_measure_instances(instances, output_size=None, classes_of_interest=No
                 rows_done.record(eng.trace_stream)
         if fg is not None:
             out["i"], out["f"] = fg.tables(gset, g_total)
+        elif ht is not None:
+            pass                                   # the host is the sink: nothing moves between devices
         elif gathered:
             # NCCL fallback: the collective stays on the main stream, behind the trace: an NCCL
             # kernel issued from the trace stream would have to wait for SMs held by the next
@@ -957,7 +1079,31 @@ def submit_measure_instances(instances, output_size=None, classes_of_interest=No
             gather_rows()
             rows_done = torch.cuda.Event()
             rows_done.record(main)
-        out_i, out_f = (out["i"], out["f"]) if gathered else (rows_i, rows_f)
+        out_i, out_f = (out["i"], out["f"]) if (gathered and ht is None) else (rows_i, rows_f)
+        if ht is not None:
+            import torch.distributed as dist
+            is_dst = dist.get_rank() == int(gather_dst)
+            hp_s = slot.pinned("status", (4,), torch.int64)
+            with torch.cuda.stream(eng.d2h_stream):
+                eng.d2h_stream.wait_event(rows_done)
+                ht.copy_rows(hk, hseq, hbase, rows_i, rows_f)
+                hp_s.copy_(status, **nb)
+                if d_ok is not None:
+                    pend.hp_ok = slot.pinned("ok", (1,), torch.int64)
+                    pend.hp_ok.copy_(d_ok, **nb)
+                    d_ok.record_stream(eng.d2h_stream)
+                done = torch.cuda.Event()
+                done.record(eng.d2h_stream)
+            lo, hi = (0, htotal) if is_dst else (hbase, hbase + n)
+            pend.np_i, pend.np_f = ht.arrays(hk, hseq, lo, hi, whole=is_dst)
+            if is_dst:
+                pend._after_sync = lambda: ht.wait_all(hk, hseq)
+            pend.n = hi - lo
+            pend.hp_i = pend.hp_f = None
+            pend.hp_s = hp_s
+            pend._done = done
+            slot.pending = pend
+            return pend
         if gathered and gather_dst is not None:
             import torch.distributed as dist
             if dist.get_rank() != int(gather_dst):
@@ -972,6 +1118,10 @@ def submit_measure_instances(instances, output_size=None, classes_of_interest=No
             hp_i.copy_(out_i, **nb)
             hp_f.copy_(out_f, **nb)
             hp_s.copy_(status, **nb)
+            if d_ok is not None:
+                pend.hp_ok = slot.pinned("ok", (1,), torch.int64)
+                pend.hp_ok.copy_(d_ok, **nb)
+                d_ok.record_stream(eng.d2h_stream)
             done = torch.cuda.Event()
             done.record(eng.d2h_stream)
         if fg is not None:

@@ -149,8 +149,9 @@ class FusedGather:
         self.cap = cap
         self.read_done = [None, None]
 
-    def begin(self, counts):
-        """-> (ctypes uwcv_gather for this rank, set index, total rows)."""
+    def begin(self, counts, dst=None):
+        """-> (ctypes uwcv_gather for this rank, set index, total rows).  ``dst``: only rank
+        ``dst``'s table receives the rows (a gather to one rank: 1 / world of the NVLink stores)."""
         import ctypes as C
         from ._lib import Gather
         from .schema import NUM_FLOAT, NUM_INT  # noqa: F401
@@ -162,6 +163,7 @@ class FusedGather:
         buf, hdl = self.sets[k]
         g = Gather()
         g.world = self.world
+        g.dst_plus_1 = 0 if dst is None else int(dst) + 1
         g.row_base = sum(counts[:self.rank])
         off_f = self._offsets(self.cap)
         ptrs = list(hdl.buffer_ptrs)
@@ -187,3 +189,182 @@ class FusedGather:
         ti = buf[: self.cap * NUM_INT * 8].view(torch.int64).view(self.cap, NUM_INT)[:total]
         tf = buf[off_f: off_f + self.cap * NUM_FLOAT * 8].view(torch.float64).view(self.cap, NUM_FLOAT)[:total]
         return ti, tf
+
+
+class SharedHostTable:
+    """The whole job's measurement table in ONE block of host memory shared by the ranks of a
+    node: every rank copies its OWN rows (device -> host, 400 B per instance) to its row offset
+    of a POSIX shared-memory segment that all ranks map and register with the CUDA driver
+    (``cudaHostRegister``), so the table is complete on the host without any rank reading the
+    other ranks' rows over PCIe and without a device-side collective: the host is the sink.
+
+    Replaces, for the end-to-end path, "all-gather on the devices, then rank 0 copies the whole
+    table" (8 ranks: 205 MB device->host through one root port per step, next to 1.6 GB of
+    host->device mask traffic).  ``SETS`` tables are used in turn.  Completion is signalled by the
+    copy engine itself: behind its rows every rank copies an 8-byte sequence number into a flag
+    word of the segment (copies of one stream land in order), which the destination rank polls;
+    a set is written again only after the reader of its previous table has let go of it
+    (``HostLease`` on the returned arrays).  Construction / growth is a collective."""
+
+    SETS = 4
+    HEADER = 4096
+
+    def __init__(self, device: torch.device, group=None):
+        self.device = device
+        self.group = group if group is not None else dist.group.WORLD
+        self.world = dist.get_world_size(self.group)
+        self.rank = dist.get_rank(self.group)
+        self.cap = 0
+        self.seq = 0
+        self.mm = None
+        self.buf = None
+        self.gen = 0
+        self.own_released = [0] * self.SETS
+        self.flag_dev = torch.zeros(1, dtype=torch.int64, device=device)
+
+    # -- layout ---------------------------------------------------------------------------
+    def _set_bytes(self, cap: int):
+        from .schema import NUM_FLOAT, NUM_INT
+        bi = (cap * NUM_INT * 8 + 4095) // 4096 * 4096
+        bf = (cap * NUM_FLOAT * 8 + 4095) // 4096 * 4096
+        return bi, bf
+
+    def ensure(self, total_rows: int) -> None:
+        import mmap
+        import os
+        if total_rows <= self.cap:
+            return
+        torch.cuda.synchronize(self.device)
+        self._close()
+        cap = max(int(total_rows * 1.1) + 64, 1024)
+        bi, bf = self._set_bytes(cap)
+        nbytes = self.HEADER + self.SETS * (bi + bf)
+        self.gen += 1
+        name = [f"/dev/shm/uwcv_table_{os.getuid()}_{os.getpid()}_{self.gen}"]
+        dist.broadcast_object_list(name, src=dist.get_global_rank(self.group, 0), group=self.group)
+        path = name[0]
+        if self.rank == 0:
+            fd = os.open(path, os.O_CREAT | os.O_RDWR | os.O_EXCL, 0o600)
+            os.ftruncate(fd, nbytes)
+        dist.barrier(self.group)
+        if self.rank != 0:
+            fd = os.open(path, os.O_RDWR)
+        self.mm = mmap.mmap(fd, nbytes)
+        os.close(fd)
+        dist.barrier(self.group)
+        if self.rank == 0:
+            os.unlink(path)                       # the mappings keep the segment alive
+        self.buf = torch.frombuffer(self.mm, dtype=torch.uint8)
+        rc = int(torch.cuda.cudart().cudaHostRegister(self.buf.data_ptr(), nbytes, 1))   # portable
+        self.registered = rc == 0
+        ok = torch.tensor([1 if rc == 0 else 0], dtype=torch.int32, device=self.device)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.group)      # all ranks or none
+        if int(ok.item()) == 0:
+            self._close()
+            raise RuntimeError(f"cudaHostRegister of the shared table failed on some rank (here: {rc})")
+        self.cap = cap
+        self.hdr = self.buf[: self.HEADER].view(torch.int64)
+        self.hdr_np = self.hdr.numpy()
+        if self.rank == 0:
+            self.hdr_np[:] = 0
+        self.own_released = [0] * self.SETS
+        self.seq = 0
+        dist.barrier(self.group)
+
+    def _close(self):
+        if self.buf is not None and getattr(self, "registered", False):
+            try:
+                torch.cuda.cudart().cudaHostUnregister(self.buf.data_ptr())
+            except Exception:                      # noqa: BLE001
+                pass
+        self.registered = False
+        self.buf = None
+        self.hdr = self.hdr_np = None
+        self.mm = None                             # (unmapped when the last view dies)
+        self.cap = 0
+
+    def _views(self, k: int):
+        from .schema import NUM_FLOAT, NUM_INT
+        bi, bf = self._set_bytes(self.cap)
+        o = self.HEADER + k * (bi + bf)
+        ti = self.buf[o: o + self.cap * NUM_INT * 8].view(torch.int64).view(self.cap, NUM_INT)
+        tf = self.buf[o + bi: o + bi + self.cap * NUM_FLOAT * 8].view(torch.float64).view(self.cap, NUM_FLOAT)
+        return ti, tf, o, o + bi
+
+    def _done_index(self, k: int, r: int) -> int:
+        return k * self.world + r
+
+    def _released_index(self, k: int) -> int:
+        return 256 + k
+
+    # -- one call --------------------------------------------------------------------------
+    def begin(self, counts, timeout_s: float = 120.0):
+        """-> (set, seq, first row of this rank, total rows).  Blocks (host) until the readers of
+        the table that last used this set have released it."""
+        import time
+        counts = [int(c) for c in counts]
+        total = sum(counts)
+        self.ensure(total)
+        seq = self.seq
+        self.seq += 1
+        k = seq % self.SETS
+        need = seq + 1 - self.SETS                 # tables are numbered seq + 1 (0: never)
+        t0 = time.time()
+        while int(self.hdr_np[self._released_index(k)]) < need or self.own_released[k] < need:
+            time.sleep(0)
+            if time.time() - t0 > timeout_s:
+                raise RuntimeError(
+                    "uwcv: a MeasurementTable of an earlier host-gathered call is still referenced "
+                    f"(set {k}); copy or drop such tables within {self.SETS - 2} calls")
+        return k, seq, sum(counts[: self.rank]), total
+
+    def copy_rows(self, k: int, seq: int, base: int, rows_i: torch.Tensor, rows_f: torch.Tensor):
+        """On the current stream: this rank's rows -> its slice of set k, then the flag."""
+        ti, tf, _, _ = self._views(k)
+        n = int(rows_i.shape[0])
+        if n:
+            ti[base: base + n].copy_(rows_i, non_blocking=True)
+            tf[base: base + n].copy_(rows_f, non_blocking=True)
+        self.flag_dev.fill_(seq + 1)
+        j = self._done_index(k, self.rank)
+        self.hdr[j: j + 1].copy_(self.flag_dev, non_blocking=True)
+
+    def wait_all(self, k: int, seq: int, timeout_s: float = 120.0) -> None:
+        """(Host.)  Every rank's rows of table ``seq`` have landed in set k."""
+        import time
+        t0 = time.time()
+        lo = self._done_index(k, 0)
+        while int(self.hdr_np[lo: lo + self.world].min()) < seq + 1:
+            time.sleep(0)
+            if time.time() - t0 > timeout_s:
+                raise RuntimeError("uwcv: timed out waiting for the other ranks' rows")
+
+    def arrays(self, k: int, seq: int, lo: int, hi: int, whole: bool):
+        """numpy views of rows [lo, hi) of set k hanging off a lease; when the last view dies the
+        set is released (``whole``: in the shared header, for every rank; else for this rank)."""
+        from .api import HostLease
+        from .schema import NUM_FLOAT, NUM_INT
+        hdr_np, idx, own = self.hdr_np, self._released_index(k), self.own_released
+
+        def release():
+            own[k] = max(own[k], seq + 1)
+            if whole:
+                hdr_np[idx] = max(int(hdr_np[idx]), seq + 1)
+
+        _, _, oi, of = self._views(k)
+        base = self.buf.data_ptr()
+        lease = HostLease(base, self.buf.numel() // 8, release, keep=(self.buf, self.mm))
+        arr = lease.array()
+        r = hi - lo
+        a = oi // 8 + lo * NUM_INT
+        b = of // 8 + lo * NUM_FLOAT
+        n_i = arr[a: a + r * NUM_INT].reshape(r, NUM_INT)
+        n_f = arr[b: b + r * NUM_FLOAT].view("float64").reshape(r, NUM_FLOAT)
+        return n_i, n_f
+
+    def release_unread(self, k: int, seq: int, whole: bool) -> None:
+        """A rank that hands out no view of set k for this call releases its part at once."""
+        self.own_released[k] = max(self.own_released[k], seq + 1)
+        if whole:
+            i = self._released_index(k)
+            self.hdr_np[i] = max(int(self.hdr_np[i]), seq + 1)
