@@ -515,6 +515,9 @@ def run_ours(args):
             db.planes = None
             del planes_main
             wb = batch[:IMAGES_PER_GPU]
+            if len(wb) < IMAGES_PER_GPU:             # N = 8: the rank's shard holds only 32 images
+                wb = wb + synth.blob_batch(IMAGES_PER_GPU - len(wb), n_inst, H, W, seed=1234,
+                                           first_image=rank + len(wb) * world, stride=world)
             wdb = DeviceBatch(eng, wb, rank, world, dev)
             wc = torch.tensor([wdb.n], dtype=torch.int64, device=dev)
             wcs = torch.empty(world, dtype=torch.int64, device=dev)
@@ -649,6 +652,7 @@ def run_ours(args):
                     "call": "uwcv.MeasurementStream(depth=2).map (pinned host Instances in, "
                             "host MeasurementTable out, every step)",
                     "sync_call_ms_per_step": sync_s / e2e_steps * 1e3,
+                    "h2d_gbs_whole_job": h2d * world / (e2e_s / e2e_steps) / 1e9,
                     "device_resident_inputs_ms_per_step": dres_s / e2e_steps * 1e3,
                     "device_resident_inputs_value": e2e_steps * total_instances / dres_s},
             "gpu_launches": launches,

@@ -791,3 +791,4 @@ def test_device_resident_inputs_take_the_sync_free_path_and_fall_back():
     got = uwcv.measure_instances(to_dev(bad), (H, W), device=dev)
     assert len(want) == sum(len(b) for b in batch) - 1
     assert np.array_equal(got.ints, want.ints) and np.array_equal(got.floats, want.floats, equal_nan=True)
+

@@ -418,6 +418,9 @@ paste_measure_kernel(const float* __restrict__ masks, const float* __restrict__ 
     unsigned long long st_iters = 0, st_ff = 0, st_idle = 0;
 #endif
     for (;;) {
+#ifdef UWCV_TUNING
+      ++st_iters;                                      // (slots taken)
+#endif
       int ticket = 0;
       if (lane == 0) ticket = (int)atomicAdd(&s_qticket, 1u);
       ticket = __shfl_sync(kFull, ticket, 0);
@@ -438,57 +441,7 @@ paste_measure_kernel(const float* __restrict__ masks, const float* __restrict__ 
       TileView tv;
       tv.M = base; tv.V = base + words; tv.G = base + 2 * words; tv.tw = e.tw; tv.th = e.th;
       uint32_t* ext = base + 3 * words;
-      if (lane == 0) T.begin(tv, ext, ext + 2 * e.th, e.th, e.ylo, e.yhi);
-      for (;;) {
-        // -- parallel part of the scan: at a row start, find the next row with a real start pixel
-        int ffy = -1;
-        if (lane == 0 && T.state == LT::kScan && T.fresh && T.wi == 0 && T.y <= T.yhi) ffy = T.y;
-        ffy = __shfl_sync(kFull, ffy, 0);
-        if (ffy >= 0) {
-          __syncwarp();                                // lane 0's marks are visible to the warp
-          int found = e.yhi + 1;
-          for (int yb = ffy; yb <= e.yhi; yb += 32) {
-            const int yy = yb + lane;
-            bool hit = false;
-            if (yy <= e.yhi) {
-              const uint32_t* mrow = tv.M + yy * e.tw;
-              const uint32_t* vrow = tv.V + yy * e.tw;
-              const uint32_t* grow = tv.G + yy * e.tw;
-              uint32_t carry = 0;
-              int last_sign = 0;                       // sign of the last marked pixel in the words before
-              for (int w = 0; w < e.tw && !hit; ++w) {
-                const uint32_t m = SharedMem::ld(mrow + w);
-                const uint32_t v = SharedMem::ld(vrow + w);
-                uint32_t cand = m & ~((m << 1) | carry) & ~v;
-                carry = m >> 31;
-                uint32_t g = 0;
-                if (cand || v) g = SharedMem::ld(grow + w);
-                while (cand) {
-                  const int bpos = __ffs(cand) - 1;
-                  cand &= cand - 1;
-                  const uint32_t below = v & ((1u << bpos) - 1u);
-                  int sgn = last_sign;
-                  if (below) sgn = ((g >> (31 - __clz(below))) & 1u) ? -1 : +1;
-                  if (sgn <= 0) { hit = true; break; }
-                }
-                if (v) last_sign = ((g >> (31 - __clz(v))) & 1u) ? -1 : +1;
-              }
-            }
-            const unsigned bm = __ballot_sync(kFull, hit);
-            if (bm) { found = yb + __ffs(bm) - 1; break; }
-          }
-          if (lane == 0 && found != ffy) {
-            T.y = found;                               // (carry = 0, wi = 0 at a row start)
-            T.m_next = (found <= T.yhi) ? T.load_pair_m(found, 0) : 0ull;
-          }
-        }
-#ifdef UWCV_TUNING
-        ++st_iters; st_ff += ffy >= 0;
-#endif
-        // -- serial part: one scan step (inside a row that holds a start) or one border step
-        if (lane == 0 && !T.done()) T.step();
-        if (__shfl_sync(kFull, T.done() ? 1 : 0, 0)) break;
-      }
+      warp_trace<SharedMem>(tv, ext, ext + 2 * e.th, e.th, e.ylo, e.yhi, T, lane);
       // completion: extremes of the best contour -> workspace (whole warp), record, slot freed
       if (lane == 0) __threadfence_block();            // its red.shared marks / extremes are performed
       __syncwarp();
