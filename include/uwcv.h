@@ -287,7 +287,8 @@ int uwcv_tiles_to_masks(const void* paste_workspace, size_t ws_bytes, int64_t N,
                         uint8_t* out, void* stream);
 
 /* Bytes of workspace for uwcv_nms_filter; image_off is a HOST array [B + 1];
- * num_classes <= 0 means 128. */
+ * num_classes <= 0 means 128.  Linear in the candidate count (about 40 bytes per candidate + 12 per
+ * image and class): no suppression matrix is stored, the IoUs are evaluated on the fly. */
 size_t uwcv_nms_workspace_bytes(const int64_t* image_off, int B, int num_classes);
 
 /*
@@ -301,7 +302,9 @@ size_t uwcv_nms_workspace_bytes(const int64_t* image_off, int B, int num_classes
  *              image_off[b] .. image_off[b+1]-1
  *   scores     [R] float32,  classes [R] int64 in [0, num_classes) (others are dropped)
  *   image_off  HOST pointer, [B + 1] int64, image_off[0] = 0, non-decreasing; at most
- *              262144 candidates per image
+ *              262144 candidates per image.  Only read DURING the call (the offsets travel as
+ *              kernel arguments): it may be pageable and may be freed on return; the call never
+ *              synchronises and can be captured in a CUDA graph
  *   num_classes  K of the box head (<= 8192; <= 0 means 128): the serial part of NMS runs
  *              once per (image, class) in parallel
  *   score_thr  keep candidates with score > score_thr (float32 compare)

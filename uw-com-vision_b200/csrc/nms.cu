@@ -11,12 +11,15 @@
 // Within a class candidates are visited in (score descending, index ascending) order.
 //
 // Launches for the whole batch:
-//   A  per image: key = (class, ~orderable(score), index), bitonic sort (shared-memory
-//      passes for strides < 4096), gather sorted boxes, class segment table
-//   B  2-D grid of 64x64 IoU blocks over the sorted list (blocks without a common class are
-//      skipped) -> upper-triangular suppression bit matrix
-//   C  per (image, class): greedy sweep over the class segment, 64 candidates per step --
-//      the serial part of NMS runs once per class in parallel
+//   A  per image: candidates above the score threshold are COMPACTED first (the cost of every
+//      later step follows the survivors, as upstream's "scores > thresh" before batched_nms
+//      does), key = (class, ~orderable(score), index), bitonic sort of the survivors (shared-
+//      memory passes for strides < 4096), gather sorted boxes, class segment table
+//   C  per (image, class): greedy sweep over the class segment, 64 candidates per step: the
+//      64 x 64 IoU bits of the step are computed in place, the step's keepers resolved by one
+//      thread in registers, and every later candidate of the segment is tested against those
+//      keepers on the fly (early exit at the first hit).  No suppression matrix is stored:
+//      the workspace is O(R), not O(R^2 / 64) (r01: 800 MB per image at R = 1000 x 80 classes)
 //   D  per image: merge the per-class keep lists by score (rank = own rank + lower bounds
 //      in the other classes' lists), top-k
 #include "uwcv_common.cuh"
@@ -37,8 +40,6 @@ struct NmsWorkspace {
   int32_t* seg;        // [B][C][2] class segments (lo, hi) in sorted positions
   int32_t* ckeep;      // [R] per-class keep lists (sorted positions), stored at the segment start
   int32_t* ccount;     // [B][C]
-  int64_t* mask_off;   // [B + 1] offsets into mask (u64 words)
-  uint64_t* mask;      // [sum n_b * ceil(n_b / 64)]
 };
 
 __host__ __device__ inline size_t nms_fixed_bytes(int64_t R, int B, int C) {
@@ -51,7 +52,6 @@ __host__ __device__ inline size_t nms_fixed_bytes(int64_t R, int B, int C) {
   s += align_up((size_t)B * C * 8, 256);
   s += align_up((size_t)R * 4, 256);
   s += align_up((size_t)B * C * 4, 256);
-  s += align_up((size_t)(B + 1) * 8, 256);
   return s;
 }
 
@@ -65,9 +65,7 @@ inline NmsWorkspace nms_carve(void* ws, int64_t R, int B, int C) {
   w.scls = (int32_t*)p;     p += align_up((size_t)R * 4, 256);
   w.seg = (int32_t*)p;      p += align_up((size_t)B * C * 8, 256);
   w.ckeep = (int32_t*)p;    p += align_up((size_t)R * 4, 256);
-  w.ccount = (int32_t*)p;   p += align_up((size_t)B * C * 4, 256);
-  w.mask_off = (int64_t*)p; p += align_up((size_t)(B + 1) * 8, 256);
-  w.mask = (uint64_t*)p;
+  w.ccount = (int32_t*)p;
   return w;
 }
 
@@ -98,8 +96,6 @@ nms_sort_kernel(const float* __restrict__ boxes, const float* __restrict__ score
   const int b = blockIdx.x, tid = threadIdx.x;
   const int64_t lo = w.off[b];
   const int n = (int)(w.off[b + 1] - lo);
-  int P = 1;
-  while (P < n) P <<= 1;
   uint64_t* keys = w.keys + 2 * lo + b;
   if (tid == 0) s_count = 0;
   for (int k = tid; k < C; k += kNmsThreads) {
@@ -108,9 +104,12 @@ nms_sort_kernel(const float* __restrict__ boxes, const float* __restrict__ score
     w.ccount[(int64_t)b * C + k] = 0;
   }
   __syncthreads();
-  int local = 0;
-  for (int i = tid; i < P; i += kNmsThreads) {
+  // score filter first: the survivors are appended (warp-aggregated) to keys[0, nv); the order
+  // of the appends does not matter, the sort below fixes it
+  for (int i0 = 0; i0 < n; i0 += kNmsThreads) {
+    const int i = i0 + tid;
     uint64_t k = ~0ull;
+    bool ok = false;
     if (i < n) {
       const float s = scores[lo + i];
       const float4 bx = reinterpret_cast<const float4*>(boxes)[lo + i];
@@ -119,12 +118,20 @@ nms_sort_kernel(const float* __restrict__ boxes, const float* __restrict__ score
                        isfinite(s);
       if (fin && s > score_thr && c >= 0 && c < C) {
         k = ((uint64_t)c << kClsShift) | ((uint64_t)(~orderable(s)) << kIdxBits) | (uint32_t)i;
-        ++local;
+        ok = true;
       }
     }
-    keys[i] = k;
+    const unsigned m = __ballot_sync(0xffffffffu, ok);
+    int base = 0;
+    if ((tid & 31) == 0 && m) base = atomicAdd(&s_count, __popc(m));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (ok) keys[base + __popc(m & ((1u << (tid & 31)) - 1u))] = k;
   }
-  if (local) atomicAdd(&s_count, local);
+  __syncthreads();
+  const int nvalid_ = s_count;
+  int P = 1;
+  while (P < nvalid_) P <<= 1;
+  for (int i = nvalid_ + tid; i < P; i += kNmsThreads) keys[i] = ~0ull;      // padding sorts last
   __syncthreads();
   // stages k <= chunk: every chunk is sorted entirely in shared memory
   const int chunk = P < kSortChunk ? P : kSortChunk;
@@ -173,78 +180,71 @@ nms_sort_kernel(const float* __restrict__ boxes, const float* __restrict__ score
   }
 }
 
-// ---- B: suppression bit matrix ------------------------------------------------------
-__global__ void __launch_bounds__(64)
-nms_mask_kernel(double iou_thr, NmsWorkspace w) {
-  const int b = blockIdx.z;
-  const int nv = w.nvalid[b];
-  const int rb = blockIdx.y, cb = blockIdx.x;
-  if (rb * 64 >= nv || cb * 64 >= nv || cb < rb) return;
-  const int64_t lo = w.off[b];
-  // the list is sorted by class: no pair to test when the column block starts in a later class
-  // than the row block ends
-  if (w.scls[lo + cb * 64] > w.scls[lo + min(rb * 64 + 63, nv - 1)]) return;
-  const int nblk = (nv + 63) >> 6;
-  __shared__ float4 s_box[64];
-  __shared__ int s_cls[64];
-  const int t = threadIdx.x;
-  const int ncol = min(64, nv - cb * 64);
-  if (t < ncol) {
-    s_box[t] = w.sbox[lo + cb * 64 + t];
-    s_cls[t] = w.scls[lo + cb * 64 + t];
-  }
-  __syncthreads();
-  const int i = rb * 64 + t;
-  if (i >= nv) return;
-  const float4 bi = w.sbox[lo + i];
-  const int ci = w.scls[lo + i];
-  const float area_i = __fmul_rn(__fsub_rn(bi.z, bi.x), __fsub_rn(bi.w, bi.y));
-  uint64_t bits = 0;
-  const int jstart = (rb == cb) ? t + 1 : 0;
-  for (int j = jstart; j < ncol; ++j) {
-    if (s_cls[j] != ci) continue;
-    const float4 bj = s_box[j];
-    const float area_j = __fmul_rn(__fsub_rn(bj.z, bj.x), __fsub_rn(bj.w, bj.y));
-    const float ww = fmaxf(0.f, __fsub_rn(fminf(bi.z, bj.z), fmaxf(bi.x, bj.x)));
-    const float hh = fmaxf(0.f, __fsub_rn(fminf(bi.w, bj.w), fmaxf(bi.y, bj.y)));
-    const float inter = __fmul_rn(ww, hh);
-    const float iou = __fdiv_rn(inter, __fsub_rn(__fadd_rn(area_i, area_j), inter));
-    if ((double)iou > iou_thr) bits |= 1ull << j;
-  }
-  w.mask[w.mask_off[b] + (int64_t)i * nblk + cb] = bits;
+// ---- C: greedy sweep of one class segment, IoUs computed on the fly -------------------------
+constexpr int kMaxBlocks = 4096;     // 262144 candidates per image
+constexpr int kSweepThreads = 1024;
+constexpr int kSweepSmemBoxes = 8192;            // class segments up to this size are staged in shared memory
+
+// suppress iff iou > thr, with torchvision's float32 arithmetic; boxes that do not intersect are
+// decided without the division (inter == 0 -> iou == 0 or NaN, never above a threshold >= 0)
+__device__ __forceinline__ bool iou_above(const float4& bi, float area_i, const float4& bj,
+                                          double iou_thr) {
+  const float ww = fmaxf(0.f, __fsub_rn(fminf(bi.z, bj.z), fmaxf(bi.x, bj.x)));
+  const float hh = fmaxf(0.f, __fsub_rn(fminf(bi.w, bj.w), fmaxf(bi.y, bj.y)));
+  const float inter = __fmul_rn(ww, hh);
+  if (!(inter > 0.f) && iou_thr >= 0.0) return false;
+  const float area_j = __fmul_rn(__fsub_rn(bj.z, bj.x), __fsub_rn(bj.w, bj.y));
+  const float iou = __fdiv_rn(inter, __fsub_rn(__fadd_rn(area_i, area_j), inter));
+  return (double)iou > iou_thr;
 }
 
-// ---- C: greedy sweep of one class segment -------------------------------------------------
-constexpr int kMaxBlocks = 4096;     // 262144 candidates per image
-constexpr int kSweepThreads = 256;
-
 __global__ void __launch_bounds__(kSweepThreads)
-nms_sweep_kernel(int topk, int C, NmsWorkspace w) {
+nms_sweep_kernel(int topk, int C, double iou_thr, NmsWorkspace w) {
+  extern __shared__ float4 s_seg[];          // the segment's boxes (when it fits)
   const int b = blockIdx.y, cls = blockIdx.x, tid = threadIdx.x;
   const int s = w.seg[((int64_t)b * C + cls) * 2], e = w.seg[((int64_t)b * C + cls) * 2 + 1];
   if (e <= s) return;
-  const int nv = w.nvalid[b];
   const int64_t lo = w.off[b];
-  const int nblk = (nv + 63) >> 6;
   const int c_first = s >> 6, c_last = (e - 1) >> 6;
-  const uint64_t* mask = w.mask + w.mask_off[b];
   __shared__ uint64_t s_removed[kMaxBlocks];
   __shared__ uint64_t s_diag[64];
+  __shared__ float4 s_kbox[64];              // boxes kept in the current step
   __shared__ uint64_t s_keepbits;
   __shared__ int s_kept;
-  __shared__ int s_rows[64];
+  const bool staged = (e - s) <= kSweepSmemBoxes;
+  if (staged)
+    for (int k = s + tid; k < e; k += kSweepThreads) s_seg[k - s] = w.sbox[lo + k];
+  // box at sorted position p of this image (p in [s, e))
+  const float4* bx = staged ? (s_seg - s) : (w.sbox + lo);
   for (int k = c_first + tid; k <= c_last; k += kSweepThreads) s_removed[k] = 0ull;
   if (tid == 0) s_kept = 0;
   __syncthreads();
   for (int c = c_first; c <= c_last; ++c) {
-    const int nin = min(64, e - c * 64);     // positions >= e belong to the next class
+    const int ifirst = c == c_first ? (s & 63) : 0;          // positions < s: previous class
+    const int nin = min(64, e - c * 64);                     // positions >= e belong to the next class
     const int kept_before = s_kept;          // stable: last written before the previous barrier
-    if (tid < nin) s_diag[tid] = mask[(int64_t)(c * 64 + tid) * nblk + c];
+    // the step's 64 x 64 suppression bits, upper triangle: 16 threads per row i, each testing
+    // four of the candidates j > i (rows of candidates already removed are never consulted)
+    if (tid < 64) s_diag[tid] = 0ull;
+    __syncthreads();
+    {
+      const int i = tid >> 4, j0 = (tid & 15) * 4;
+      if (i >= ifirst && i < nin && !((s_removed[c] >> i) & 1ull)) {
+        const float4 bi = bx[c * 64 + i];
+        const float area_i = __fmul_rn(__fsub_rn(bi.z, bi.x), __fsub_rn(bi.w, bi.y));
+        uint64_t bits = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int j = j0 + k;
+          if (j > i && j < nin && iou_above(bi, area_i, bx[c * 64 + j], iou_thr)) bits |= 1ull << j;
+        }
+        if (bits) atomicOr((unsigned long long*)&s_diag[i], (unsigned long long)bits);
+      }
+    }
     __syncthreads();
     if (tid == 0) {
       uint64_t cur = s_removed[c], kb = 0;
       int kept = kept_before;
-      const int ifirst = c == c_first ? (s & 63) : 0;          // positions < s: previous class
       for (int i = ifirst; i < nin && kept < topk; ++i) {
         if (!((cur >> i) & 1ull)) { kb |= 1ull << i; ++kept; cur |= s_diag[i]; }
       }
@@ -257,18 +257,24 @@ nms_sweep_kernel(int topk, int C, NmsWorkspace w) {
     if (tid < 64 && ((kb >> tid) & 1ull)) {
       const int rank = __popcll(kb & ((1ull << tid) - 1ull));
       w.ckeep[lo + s + kept_before + rank] = c * 64 + tid;      // sorted position of a kept box
-      s_rows[rank] = c * 64 + tid;
+      s_kbox[rank] = bx[c * 64 + tid];
     }
     if (s_kept >= topk) break;
     __syncthreads();
-    // OR the suppression rows of the boxes kept in this step into the words to the right:
-    // (kept rows) x (remaining words of the segment) independent loads
-    const int rem = c_last - c;
-    const int items = nkept * rem;
-    for (int it = tid; it < items; it += kSweepThreads) {
-      const int r = it / rem, wd = c + 1 + (it - r * rem);
-      const uint64_t m = mask[(int64_t)s_rows[r] * nblk + wd];
-      if (m) atomicOr((unsigned long long*)&s_removed[wd], (unsigned long long)m);
+    // every later candidate of the segment that is still alive against this step's keepers
+    // (score order: a keeper always precedes the candidates it suppresses; torchvision
+    // evaluates iou(keeper, candidate) with the keeper first: same operand order here)
+    if (nkept) {
+      for (int j = (c + 1) * 64 + tid; j < e; j += kSweepThreads) {
+        if ((s_removed[j >> 6] >> (j & 63)) & 1ull) continue;
+        const float4 bj = bx[j];
+        bool hit = false;
+        for (int r = 0; r < nkept && !hit; ++r) {
+          const float4 bi = s_kbox[r];
+          hit = iou_above(bi, __fmul_rn(__fsub_rn(bi.z, bi.x), __fsub_rn(bi.w, bi.y)), bj, iou_thr);
+        }
+        if (hit) atomicOr((unsigned long long*)&s_removed[j >> 6], 1ull << (j & 63));
+      }
     }
     __syncthreads();
   }
@@ -317,28 +323,17 @@ nms_merge_kernel(int topk, int C, NmsWorkspace w, int64_t* __restrict__ keep,
   }
 }
 
-// mask_off[b] = sum_{b' < b} n_b' * ceil(n_b' / 64)  (upper bound using all candidates)
-__global__ void nms_offsets_kernel(int B, NmsWorkspace w) {
-  if (threadIdx.x == 0 && blockIdx.x == 0) {
-    int64_t acc = 0;
-    for (int b = 0; b < B; ++b) {
-      w.mask_off[b] = acc;
-      const int64_t n = w.off[b + 1] - w.off[b];
-      acc += n * ((n + 63) >> 6);
-    }
-    w.mask_off[B] = acc;
-  }
+// The per-image candidate offsets reach the device as KERNEL ARGUMENTS (32 per launch): the host
+// array is only read during the call, nothing is copied asynchronously from pageable memory, the
+// call never synchronises and can be captured in a CUDA graph.
+struct OffsetChunk { int64_t v[32]; };
+__global__ void nms_set_offsets_kernel(int64_t* __restrict__ off, int first, int count, OffsetChunk c) {
+  const int t = threadIdx.x;
+  if (t < count) off[first + t] = c.v[t];
 }
 
 size_t nms_workspace_bytes_host(const int64_t* image_off_host, int B, int C) {
-  const int64_t R = image_off_host[B];
-  size_t s = nms_fixed_bytes(R, B, C);
-  size_t m = 0;
-  for (int b = 0; b < B; ++b) {
-    const int64_t n = image_off_host[b + 1] - image_off_host[b];
-    m += (size_t)n * ((n + 63) >> 6);
-  }
-  return s + m * 8 + 256;
+  return nms_fixed_bytes(image_off_host[B], B, C) + 256;
 }
 
 cudaError_t launch_nms(const float* boxes, const float* scores, const int64_t* cls,
@@ -347,22 +342,26 @@ cudaError_t launch_nms(const float* boxes, const float* scores, const int64_t* c
                        cudaStream_t stream) {
   const int64_t R = image_off_host[B];
   NmsWorkspace w = nms_carve(ws, R, B, C);
-  cudaError_t e = cudaMemcpyAsync(w.off, image_off_host, (size_t)(B + 1) * 8,
-                                  cudaMemcpyHostToDevice, stream);
-  if (e != cudaSuccess) return e;
-  int64_t maxn = 0;
-  for (int b = 0; b < B; ++b) {
-    const int64_t n = image_off_host[b + 1] - image_off_host[b];
-    if (n > maxn) maxn = n;
+  for (int f = 0; f <= B; f += 32) {
+    OffsetChunk c;
+    const int cnt = (B + 1 - f) < 32 ? (B + 1 - f) : 32;
+    for (int k = 0; k < 32; ++k) c.v[k] = k < cnt ? image_off_host[f + k] : 0;
+    nms_set_offsets_kernel<<<1, 32, 0, stream>>>(w.off, f, cnt, c);
   }
-  nms_offsets_kernel<<<1, 32, 0, stream>>>(B, w);
   nms_sort_kernel<<<B, kNmsThreads, 0, stream>>>(boxes, scores, cls, score_thr, C, w);
-  if (maxn > 0) {
-    const unsigned nb = (unsigned)((maxn + 63) / 64);
-    dim3 grid(nb, nb, (unsigned)B);
-    nms_mask_kernel<<<grid, 64, 0, stream>>>(iou_thr, w);
+  if (R > 0) {
     dim3 sgrid((unsigned)C, (unsigned)B);
-    nms_sweep_kernel<<<sgrid, kSweepThreads, 0, stream>>>(topk, C, w);
+    int64_t maxn = 0;
+    for (int b = 0; b < B; ++b) {
+      const int64_t nb = image_off_host[b + 1] - image_off_host[b];
+      if (nb > maxn) maxn = nb;
+    }
+    // room for the largest class segment that can occur, capped at kSweepSmemBoxes boxes
+    const size_t dyn = (size_t)(maxn < kSweepSmemBoxes ? maxn : kSweepSmemBoxes) * sizeof(float4);
+    if (dyn > 12 * 1024)                               // (per device and context: set on every call)
+      cudaFuncSetAttribute(nms_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           kSweepSmemBoxes * (int)sizeof(float4));
+    nms_sweep_kernel<<<sgrid, kSweepThreads, dyn, stream>>>(topk, C, iou_thr, w);
   }
   nms_merge_kernel<<<B, kNmsThreads, 0, stream>>>(topk, C, w, keep, keep_count);
   return cudaPeekAtLastError();

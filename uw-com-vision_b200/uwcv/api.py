@@ -466,15 +466,16 @@ class Engine:
         keep = torch.empty(max(R, 1), dtype=torch.int64, device=dev)
         cnt = torch.zeros(max(B, 1), dtype=torch.int32, device=dev)
         nbytes = self.L.uwcv_nms_workspace_bytes(off, B, int(num_classes))
-        ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        ws = getattr(self, "_nms_ws", None)           # O(R) bytes, cached across calls
+        if ws is None or ws.numel() < nbytes:
+            ws = self._nms_ws = torch.empty(int(nbytes * 1.25) + 256, dtype=torch.uint8, device=dev)
         with torch.cuda.device(dev):
             rc = self.L.uwcv_nms_filter(_ptr(boxes), _ptr(scores), _ptr(classes), off, B,
                                         int(num_classes), float(score_thresh), float(nms_thresh), int(topk),
                                         _ptr(keep), _ptr(cnt), _ptr(ws), ws.numel(),
                                         _stream_ptr(dev))
         _lib.check(rc, "uwcv_nms_filter")
-        self.launches += 5 if R > 0 else 3
-        self._nms_ws = ws           # keep alive until the stream has consumed it
+        self.launches += (B + 32) // 32 + (3 if R > 0 else 2)    # offsets, sort, sweep, merge
         return keep, cnt
 
 
