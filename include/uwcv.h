@@ -40,7 +40,8 @@ extern "C" {
 #define UWCV_E_WORKSPACE  -5  /* workspace smaller than uwcv_workspace_bytes(N,0) */
 #define UWCV_E_LAUNCH     -6  /* CUDA reported a launch error                     */
 #define UWCV_E_CAPACITY   -7  /* (device status) tile words exceed the workspace  */
-#define UWCV_E_TOO_LARGE  -8  /* image side > 32768 or candidate count too large  */
+#define UWCV_E_TOO_LARGE  -8  /* image side > 32768 or candidate count too large; as a device
+                                 status: a tile whose raw moments could exceed int64          */
 
 /* Library version, major * 10000 + minor * 100 + patch. */
 int uwcv_version(void);
@@ -83,8 +84,10 @@ size_t uwcv_workspace_bytes(int64_t N, int64_t tile_words);
  *   rows_i     [N, UWCV_NUM_INT] int64 out     (column order: SURVEY.md 8(b))
  *   rows_f     [N, UWCV_NUM_FLOAT] float64 out
  *   workspace / ws_bytes   >= uwcv_workspace_bytes(N, tile_words)
- *   status     [4] int64 out (device): [0] 0 or UWCV_E_CAPACITY, [1] tile words needed,
- *              [2] tile rows needed, [3] number of tiles above the one-instance-per-warp limit.  On E_CAPACITY no row is written.
+ *   status     [4] int64 out (device): [0] 0, UWCV_E_CAPACITY or UWCV_E_TOO_LARGE (a tile so large
+ *              that m30 / m03 of an all-set mask would pass 2^63: raw moments are exact int64
+ *              sums, so full-frame masks are limited to about 6 000 pixels a side), [1] tile words needed,
+ *              [2] tile rows needed, [3] number of tiles above the one-instance-per-warp limit.  On a non-zero status no row is written.
  */
 int uwcv_paste_measure(const float* masks, const float* boxes, const int32_t* image_idx,
                        const int32_t* inst_idx, const int64_t* classes, const float* scores,
@@ -198,8 +201,9 @@ int uwcv_ingest(const void* src_host_mapped, void* dst, size_t bytes, void* stre
  * EVERY external contour of that union is measured (touching instances merge).
  *
  * Call order: uwcv_paste_measure_stages(stages = 3, bitplanes = NULL) on the selected
- * instances, then group them on the host (instances of one image whose 1-pixel-dilated pixel
- * boxes, rows_i columns bbox_*, overlap belong to one group), then uwcv_union_measure.
+ * instances, then group them (instances of one image whose 1-pixel-dilated pixel boxes, rows_i
+ * columns bbox_*, overlap belong to one group: uwcv_union_group does it on the device, or the
+ * caller on the host), then uwcv_union_measure[_grouped].
  *
  *   paste_workspace / paste_ws_bytes / N   exactly as passed to uwcv_paste_measure_stages
  *   member_group   [N] int32: group of every instance, -1 = not part of any group (empty mask)
@@ -237,6 +241,34 @@ int uwcv_union_measure(const void* paste_workspace, size_t paste_ws_bytes, int64
                        int64_t* rows_i, double* rows_f, int64_t* counters, void* stream);
 
 /*
+ * Grouping on the device, so that a union-mode call needs no host round trip between the paste
+ * and the contour kernels:
+ *   uwcv_union_group: paste_rows_i = the int64 rows [N, UWCV_NUM_INT] written by
+ *     uwcv_paste_measure_stages(stages = 3); the instances of an image must be consecutive and the
+ *     image indices (column 0) must be image_base, image_base + 1, ... (B images).  One CTA per
+ *     image forms the groups (minimum-label propagation over the box-overlap graph in shared
+ *     memory) and their tiles; outputs member_group [N], group_desc [N] (the first G are used),
+ *     group_image [N] and group_counters [4] int64 (device): [0] G, [1] words of all group tiles
+ *     (a multiple of 4), [3] 0 or UWCV_E_CAPACITY when [1] > group_words_cap.
+ *   uwcv_union_measure_grouped: uwcv_union_measure with G and the plane size read from
+ *     group_counters on the device; group_planes holds 3 * group_words_cap words.  On
+ *     group_counters[3] != 0 nothing is measured and counters[1] = UWCV_E_CAPACITY: repeat both
+ *     calls with group_words_cap >= group_counters[1].
+ */
+size_t uwcv_union_group_workspace_bytes(int64_t N, int B);
+int uwcv_union_group(const int64_t* paste_rows_i, int64_t N, int B, int64_t image_base,
+                     void* group_workspace, size_t group_ws_bytes, int32_t* member_group,
+                     uwcv_tile* group_desc, int32_t* group_image, int64_t group_words_cap,
+                     int64_t* group_counters, void* stream);
+int uwcv_union_measure_grouped(const void* paste_workspace, size_t paste_ws_bytes, int64_t N,
+                               const int32_t* member_group, const uwcv_tile* group_desc,
+                               const int32_t* group_image, const int64_t* group_counters,
+                               uint32_t* group_planes, int64_t group_words_cap, void* rec_workspace,
+                               size_t rec_ws_bytes, int64_t rec_cap, int64_t ext_rows_cap,
+                               double pixels_per_metric, int64_t* rows_i, double* rows_f,
+                               int64_t* counters, void* stream);
+
+/*
  * Mask clean-up + RLE export -- stands in for postprocess_masks
  * (nn_inference.py:265-306) and rle_encoding (:253-263) of the reference's export loop (:319-336).
  *
@@ -269,6 +301,19 @@ int uwcv_clean_masks(void* paste_workspace, size_t ws_bytes, int64_t N, int H, i
                      int32_t* flags, int64_t* area, int64_t* run_counts, void* stream);
 int uwcv_rle_write(const void* paste_workspace, size_t ws_bytes, int64_t N, int H, int W,
                    const int64_t* run_offsets, int64_t* runs, void* stream);
+/*
+ * The EncodedPixels text -- conv = ' '.join(map(str, rle_encoding(mask))) (nn_inference.py:317) --
+ * written on the device.  runs [total_runs, 2] as uwcv_rle_write left them, run_instance
+ * [total_runs] int32 = the instance of every run.  uwcv_rle_text_prep: chars [total_runs] int64 =
+ * characters run k contributes ("start length " with the runs that continue it across a column
+ * boundary merged into its length; 0 for such a continuation).  The caller takes the exclusive
+ * prefix sum (text_offsets) and calls uwcv_rle_text_write, which prints the decimal digits; the
+ * text of instance i is bytes [text_offsets[run_offsets[i]], text_offsets[run_offsets[i + 1]] - 1).
+ */
+int uwcv_rle_text_prep(int64_t total_runs, const int64_t* runs, const int32_t* run_instance,
+                       int64_t* chars, void* stream);
+int uwcv_rle_text_write(int64_t total_runs, const int64_t* runs, const int32_t* run_instance,
+                        const int64_t* text_offsets, uint8_t* text, void* stream);
 
 /*
  * Literal postprocess_masks(ori_mask, ...) entry (nn_inference.py:265, called at :325-327 with

@@ -792,3 +792,25 @@ def test_device_resident_inputs_take_the_sync_free_path_and_fall_back():
     assert len(want) == sum(len(b) for b in batch) - 1
     assert np.array_equal(got.ints, want.ints) and np.array_equal(got.floats, want.floats, equal_nan=True)
 
+
+def test_moment_overflow_is_refused_not_wrapped():
+    """m30 = sum x^3 of a near-full-frame mask passes int64 above ~6 000 px a side; such a
+    tile is refused with the device status UWCV_E_TOO_LARGE instead of wrapping silently, while an
+    8192-pixel frame with ordinary boxes is still measured."""
+    from uwcv import _lib
+    dev = torch.device("cuda", 0)
+    eng = uwcv.Engine.get(dev)
+    H = W = 8192
+    m = torch.ones((2, 28, 28), device=dev)
+    ok_boxes = torch.tensor([[100., 100., 400., 300.], [7000., 7800., 8192., 8192.]], device=dev)
+    ri, rf, st = eng.run(m, ok_boxes, H, W)
+    eng.check_status()
+    want = [int(d2.paste_one_cropped(m[k].cpu(), ok_boxes[k].cpu(), H, W, 0.5)[0].sum()) for k in range(2)]
+    assert ri[:, IC["area_px"]].tolist() == want and min(want) > 50000
+    huge = torch.tensor([[0., 0., 8192., 8192.], [10., 10., 50., 50.]], device=dev)
+    eng.run(m, huge, H, W)
+    with pytest.raises(_lib.UwcvError) as ei:
+        eng.check_status()
+    assert ei.value.code == -8
+    eng.run(m, ok_boxes, H, W)                       # the engine is usable afterwards
+    eng.check_status()

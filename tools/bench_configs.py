@@ -74,13 +74,20 @@ out["config4_4096_dense"] = {"candidates": len(cb), "instances": k, "nms_ms": ms
                              "full_frame_gbs": k * bpi / (ms * 1e-3) / 1e9,
                              "instances_per_s_full_frame": k / ms * 1e3}
 # ---- union mode on one config-2 image -----------------------------------------------------------
-t0 = time.perf_counter(); ut = uwcv.measure_union(batch[0], (2048, 2048), classes_of_interest=[3]); t1 = time.perf_counter()
-t0 = time.perf_counter(); ut = uwcv.measure_union(batch[:8], (2048, 2048), classes_of_interest=[3]); t1 = time.perf_counter()
-out["union_mode_8_images_class3"] = {"rows": len(ut), "wall_ms": (t1 - t0) * 1e3}
+def wall(fn, reps=5, warm=2):
+    for _ in range(warm):
+        r = fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(reps):
+        t0 = time.perf_counter(); r = fn(); ts.append((time.perf_counter() - t0) * 1e3)
+    return r, sorted(ts)[len(ts) // 2]
+
+
+ut, ms_u = wall(lambda: uwcv.measure_union(batch[:8], (2048, 2048), classes_of_interest=[3]))
+out["union_mode_8_images_class3"] = {"rows": len(ut), "wall_ms": ms_u}
 # ---- f2: mask clean-up + RLE export on 8 config-2 images ------------------------------------------
-uwcv.export_rle(batch[:2], (2048, 2048))
-torch.cuda.synchronize()
-t0 = time.perf_counter(); ex = uwcv.export_rle(batch[:8], (2048, 2048)); t1 = time.perf_counter()
-out["rle_export_8_images"] = {"rows": len(ex), "wall_ms": (t1 - t0) * 1e3,
+ex, ms_x = wall(lambda: uwcv.export_rle(batch[:8], (2048, 2048)))
+out["rle_export_8_images"] = {"rows": len(ex), "wall_ms": ms_x,
                               "emptied_multi_piece": int(ex.multi_piece.sum())}
 print(json.dumps(out, indent=1))

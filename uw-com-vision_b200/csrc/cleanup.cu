@@ -343,6 +343,55 @@ rle_write_kernel(int64_t n, int H, int W, Workspace ws, const int64_t* __restric
   }
 }
 
+// ---- phase D: the EncodedPixels text on the device --------------------------------------------------
+// conv = ' '.join(map(str, rle_encoding(mask)))  (nn_inference.py:317, :253-263).  A run that ends on
+// the last image row and the next one starting on row 0 of the following column are consecutive
+// flat indices, i.e. ONE run for the reference: run k is a continuation when it starts where run
+// k - 1 of the same instance ended.  prep: characters each run contributes ("start length " for a
+// head, nothing for a continuation); the caller scans them; write: decimal digits at those offsets.
+__device__ __forceinline__ int dec_digits(long long v) {
+  int d = 1;
+  while (v >= 10) { v /= 10; ++d; }
+  return d;
+}
+__device__ __forceinline__ bool rle_is_cont(const int64_t* runs, const int32_t* run_inst, int64_t k) {
+  return k > 0 && run_inst[k] == run_inst[k - 1] && runs[2 * k] == runs[2 * (k - 1)] + runs[2 * (k - 1) + 1];
+}
+__device__ __forceinline__ long long rle_merged_len(const int64_t* runs, const int32_t* run_inst,
+                                                    int64_t k, int64_t total) {
+  long long len = runs[2 * k + 1];
+  for (int64_t j = k + 1; j < total && rle_is_cont(runs, run_inst, j); ++j) len += runs[2 * j + 1];
+  return len;
+}
+
+__global__ void __launch_bounds__(256)
+rle_text_prep_kernel(int64_t total, const int64_t* __restrict__ runs, const int32_t* __restrict__ run_inst,
+                     int64_t* __restrict__ chars) {
+  const int64_t k = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (k >= total) return;
+  long long c = 0;
+  if (!rle_is_cont(runs, run_inst, k))
+    c = dec_digits(runs[2 * k]) + 1 + dec_digits(rle_merged_len(runs, run_inst, k, total)) + 1;
+  chars[k] = c;
+}
+
+__global__ void __launch_bounds__(256)
+rle_text_write_kernel(int64_t total, const int64_t* __restrict__ runs, const int32_t* __restrict__ run_inst,
+                      const int64_t* __restrict__ text_off, uint8_t* __restrict__ text) {
+  const int64_t k = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (k >= total || rle_is_cont(runs, run_inst, k)) return;
+  uint8_t* o = text + text_off[k];
+  long long v[2] = {runs[2 * k], rle_merged_len(runs, run_inst, k, total)};
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {
+    const int nd = dec_digits(v[q]);
+    long long x = v[q];
+    for (int p = nd - 1; p >= 0; --p) { o[p] = (uint8_t)('0' + (int)(x % 10)); x /= 10; }
+    o[nd] = ' ';
+    o += nd + 1;
+  }
+}
+
 // ---- launchers -----------------------------------------------------------------------------------
 static inline unsigned warps_grid(int64_t n) {
   return (unsigned)((n * 32 + kCleanThreads - 1) / kCleanThreads);
@@ -370,6 +419,19 @@ cudaError_t launch_rle_write(int64_t n, int H, int W, const Workspace& ws, const
                              int64_t* runs, cudaStream_t stream) {
   if (n == 0) return cudaSuccess;
   rle_write_kernel<<<warps_grid(n), kCleanThreads, 0, stream>>>(n, H, W, ws, run_off, runs);
+  return cudaPeekAtLastError();
+}
+
+cudaError_t launch_rle_text_prep(int64_t total, const int64_t* runs, const int32_t* run_inst,
+                                 int64_t* chars, cudaStream_t stream) {
+  if (total == 0) return cudaSuccess;
+  rle_text_prep_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(total, runs, run_inst, chars);
+  return cudaPeekAtLastError();
+}
+cudaError_t launch_rle_text_write(int64_t total, const int64_t* runs, const int32_t* run_inst,
+                                  const int64_t* text_off, uint8_t* text, cudaStream_t stream) {
+  if (total == 0) return cudaSuccess;
+  rle_text_write_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(total, runs, run_inst, text_off, text);
   return cudaPeekAtLastError();
 }
 

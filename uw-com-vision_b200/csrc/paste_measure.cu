@@ -97,6 +97,14 @@ layout_local_kernel(const float* __restrict__ boxes, int64_t n, int H, int W,
     block_sums[2 * blockIdx.x] = tw_total;
     block_sums[2 * blockIdx.x + 1] = tr_total;
   }
+  // the raw moments are exact int64 sums: a tile whose worst case (every pixel set) could pass
+  // 2^63 in m30 / m03 is refused instead of wrapping silently (full-frame masks above ~6 000 px)
+  if (i < n && th > 0) {
+    const double px = (double)tw * 32.0 * (double)th;
+    const double xm = (double)(wx0 + tw) * 32.0, ym = (double)(y0 + th);
+    const double worst = px * fmax(xm * xm * xm, ym * ym * ym);
+    if (worst >= 9.0e18) atomicOr(reinterpret_cast<unsigned long long*>(block_sums + 2 * gridDim.x), 1ull);
+  }
   // tiles too large for the one-instance-per-warp kernel of the rows-only contract
   const int big = __syncthreads_count(i < n && (int64_t)tw * th > kBigTileWords);
   if (threadIdx.x == 0 && big) atomicAdd(reinterpret_cast<unsigned long long*>(big_tiles),
@@ -126,7 +134,8 @@ layout_rebase_kernel(int64_t n, int nblk, TileDesc* __restrict__ desc,
     if (t == 0) {
       status[1] = base_w;
       status[2] = base_r;
-      status[0] = (base_w > cap_words) ? (int64_t)E_CAPACITY : 0;
+      status[0] = block_sums[2 * nblk] ? (int64_t)E_TOO_LARGE
+                                       : ((base_w > cap_words) ? (int64_t)E_CAPACITY : 0);
       for (int k = 0; k < 8; ++k) sched[k] = 0u;
     }
     return;                                              // offsets of CTA 0 need no rebase
@@ -788,6 +797,8 @@ cudaError_t launch_layout(const float* boxes, int64_t n, int H, int W, const Wor
                           int64_t* status, int num_sms, cudaStream_t stream) {
   const int nblk = (int)layout_blocks(n);
   if (cudaMemsetAsync(status + 3, 0, sizeof(int64_t), stream) != cudaSuccess) return cudaGetLastError();
+  if (cudaMemsetAsync(ws.block_sums + 2 * nblk, 0, sizeof(int64_t), stream) != cudaSuccess)   // moment-overflow flag
+    return cudaGetLastError();
   layout_local_kernel<<<nblk, kLayoutThreads, 0, stream>>>(boxes, n, H, W, ws.desc, ws.rec,
                                                            ws.block_sums, status + 3);
   layout_rebase_kernel<<<nblk, kLayoutThreads, 0, stream>>>(n, nblk, ws.desc, ws.block_sums,

@@ -53,7 +53,8 @@ inline UnionRecords union_carve(void* ws, int64_t cap, int64_t ext_rows_cap) {
 __global__ void __launch_bounds__(256)
 union_or_kernel(int64_t n, const TileDesc* __restrict__ desc, const uint32_t* __restrict__ M,
                 const int32_t* __restrict__ member_group, const TileDesc* __restrict__ gdesc,
-                uint32_t* __restrict__ gM) {
+                uint32_t* __restrict__ gM, const int64_t* __restrict__ gcount) {
+  if (gcount && gcount[3] != 0) return;                  // group planes too small: the caller retries
   const int lane = threadIdx.x & 31;
   const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -76,9 +77,14 @@ union_or_kernel(int64_t n, const TileDesc* __restrict__ desc, const uint32_t* __
 
 // ---- 2. trace every external contour of every group -------------------------------------------
 __global__ void __launch_bounds__(kUnionThreads)
-union_trace_kernel(int64_t G, int lanes, const TileDesc* __restrict__ gdesc,
+union_trace_kernel(int64_t G, const int64_t* __restrict__ gcount, int lanes,
+                   const TileDesc* __restrict__ gdesc,
                    const uint32_t* __restrict__ gM, uint32_t* __restrict__ gV,
                    uint32_t* __restrict__ gG, UnionRecords R, int64_t* __restrict__ counters) {
+  if (gcount) {                                          // groups were formed on the device
+    if (gcount[3] != 0) { if (blockIdx.x == 0 && threadIdx.x == 0) counters[1] = E_CAPACITY; return; }
+    G = gcount[0];
+  }
   const int lane = threadIdx.x & 31;
   const int64_t warp = ((int64_t)blockIdx.x * kUnionThreads + threadIdx.x) >> 5;
   const int64_t g = warp * lanes + lane;
@@ -258,11 +264,202 @@ union_describe_kernel(int lanes, const TileDesc* __restrict__ gdesc,
   ri[9] = 1;
 }
 
+// ---- 0. groups of instances on the device --------------------------------------------------------
+// Instances of one image whose 1-pixel-dilated pixel boxes overlap (transitively) form a group.
+// One CTA per image: minimum-label propagation over the overlap graph (every instance looks at
+// every other instance of its image: N^2 / 1024 box tests per thread and round, boxes in shared
+// memory) with pointer jumping, until no label changes; the roots become the groups, numbered
+// image-major in instance order (deterministic), each with the union of its members' boxes as
+// its tile.  A single-CTA scan turns the per-image counts into global group ids / word offsets.
+constexpr int kGroupThreads = 1024;
+constexpr int kGroupSmemBoxes = 6144;                  // boxes (16 B) + labels (4 B) per image in shared memory
+
+struct GroupScratch {
+  int32_t* label;       // [N]   propagation labels of images too large for shared memory
+  int32_t* local_gid;   // [N]   group of the instance inside its image (-1: none)
+  TileDesc* tmp;        // [N]   per image: tiles of its groups, local word offsets
+  int64_t* per_image;   // [B][4] groups, words, first instance, -
+};
+
+__host__ __device__ inline size_t group_scratch_bytes(int64_t n, int B) {
+  return 2 * align_up((size_t)n * 4, 256) + align_up((size_t)n * sizeof(TileDesc), 256) +
+         align_up((size_t)B * 32, 256) + 256;
+}
+inline GroupScratch group_carve(void* ws, int64_t n, int B) {
+  GroupScratch g;
+  char* p = (char*)ws;
+  g.label = (int32_t*)p;      p += align_up((size_t)n * 4, 256);
+  g.local_gid = (int32_t*)p;  p += align_up((size_t)n * 4, 256);
+  g.tmp = (TileDesc*)p;       p += align_up((size_t)n * sizeof(TileDesc), 256);
+  g.per_image = (int64_t*)p;
+  return g;
+}
+
+__global__ void __launch_bounds__(kGroupThreads)
+union_group_kernel(const int64_t* __restrict__ rows_i, int64_t n, int64_t image_base,
+                   GroupScratch gs) {
+  extern __shared__ int4 s_box[];                        // dilated pixel boxes (x0-1, y0-1, x1+1, y1+1)
+  __shared__ int s_scan[kGroupThreads];
+  const int b = blockIdx.x, tid = threadIdx.x;
+  // instances of image b are consecutive: first row with image index >= base + b (binary search)
+  auto lower = [&](int64_t img) {
+    int64_t a = 0, z = n;
+    while (a < z) { const int64_t m = (a + z) >> 1; if (rows_i[m * kNumInt + I_IMAGE] < img) a = m + 1; else z = m; }
+    return a;
+  };
+  const int64_t lo = lower(image_base + b), hi = lower(image_base + b + 1);
+  const int nb = (int)(hi - lo);
+  int* s_label = reinterpret_cast<int*>(s_box + (nb <= kGroupSmemBoxes ? nb : 0));
+  const bool staged = nb <= kGroupSmemBoxes;
+  auto box_of = [&](int i) -> int4 {
+    const int64_t* r = rows_i + (lo + i) * kNumInt;
+    if (r[I_VALID] != 1) return make_int4(1, 1, -1, -1);          // empty: overlaps nothing
+    return make_int4((int)r[I_BX0] - 1, (int)r[I_BY0] - 1, (int)r[I_BX1] + 1, (int)r[I_BY1] + 1);
+  };
+  int32_t* g_label = gs.label + lo;                      // labels live here when the image is too big
+  for (int i = tid; i < nb; i += kGroupThreads) {
+    const int4 bx = box_of(i);
+    if (staged) { s_box[i] = bx; s_label[i] = bx.z >= bx.x ? i : -1; }
+    else g_label[i] = bx.z >= bx.x ? i : -1;
+  }
+  __syncthreads();
+  volatile int* label = staged ? (volatile int*)s_label : (volatile int*)g_label;
+  for (;;) {
+    int changed = 0;
+    for (int i = tid; i < nb; i += kGroupThreads) {
+      int m = label[i];
+      if (m < 0) continue;
+      const int4 a = staged ? s_box[i] : box_of(i);
+      for (int j = 0; j < nb; ++j) {
+        const int4 c = staged ? s_box[j] : box_of(j);
+        // [x0-1, x1+1] x [y0-1, y1+1] intersect  <=>  8-adjacent or overlapping pixel boxes
+        if (a.x <= c.z && c.x <= a.z && a.y <= c.w && c.y <= a.w && c.z >= c.x) {
+          const int lj = label[j];
+          if (lj < m) m = lj;
+        }
+      }
+      // pointer jumping: follow the labels down to a root
+      for (int k = 0; k < 8; ++k) { const int up = label[m]; if (up >= m) break; m = up; }
+      if (m < label[i]) { label[i] = m; changed = 1; }
+    }
+    if (!__syncthreads_or(changed)) break;
+  }
+  // At the fixed point every label is the smallest instance index of its group, and that
+  // instance (the root) carries its own index.  Roots -> dense local group ids in instance
+  // order (block scan of the root flags); the group's box starts empty.
+  int base = 0;
+  for (int i0 = 0; i0 < nb; i0 += kGroupThreads) {
+    const int i = i0 + tid;
+    const int is_root = (i < nb && label[i] == i) ? 1 : 0;
+    s_scan[tid] = is_root;
+    __syncthreads();
+    for (int off = 1; off < kGroupThreads; off <<= 1) {
+      int v = 0;
+      if (tid >= off) v = s_scan[tid - off];
+      __syncthreads();
+      s_scan[tid] += v;
+      __syncthreads();
+    }
+    if (is_root) {
+      const int gid = base + s_scan[tid] - 1;
+      TileDesc d;                                        // pixel extents first, words further down
+      d.wx0 = 0x7fffffff; d.y0 = 0x7fffffff; d.tw = -1; d.th = -1; d.word_off = 0; d.row_off = 0;
+      gs.tmp[lo + gid] = d;
+      gs.local_gid[lo + i] = gid;
+    }
+    base += s_scan[kGroupThreads - 1];
+    __syncthreads();
+  }
+  const int ngroups = base;
+  // members take their root's id; the group box is the union of the members' pixel boxes
+  for (int i = tid; i < nb; i += kGroupThreads) {
+    const int root = label[i];
+    if (root < 0) { gs.local_gid[lo + i] = -1; continue; }
+    const int gid = gs.local_gid[lo + root];             // (roots were written before the barrier)
+    if (root != i) gs.local_gid[lo + i] = gid;
+    const int64_t* r = rows_i + (lo + i) * kNumInt;
+    TileDesc* d = gs.tmp + lo + gid;
+    atomicMin(&d->wx0, (int)r[I_BX0]);
+    atomicMin(&d->y0, (int)r[I_BY0]);
+    atomicMax(&d->tw, (int)r[I_BX1]);
+    atomicMax(&d->th, (int)r[I_BY1]);
+  }
+  __syncthreads();
+  // tiles in words + local word offsets (serial over the image's groups: a few hundred)
+  __syncthreads();
+  if (tid == 0) {
+    int64_t words = 0;
+    for (int g = 0; g < ngroups; ++g) {
+      TileDesc d = gs.tmp[lo + g];
+      const int x0 = d.wx0, y0 = d.y0, x1 = d.tw, y1 = d.th;
+      d.wx0 = x0 >> 5; d.tw = (x1 >> 5) - d.wx0 + 1; d.y0 = y0; d.th = y1 - y0 + 1;
+      d.word_off = words; d.row_off = 0;
+      words += (int64_t)d.tw * d.th;
+      gs.tmp[lo + g] = d;
+    }
+    gs.per_image[b * 4 + 0] = ngroups;
+    gs.per_image[b * 4 + 1] = words;
+    gs.per_image[b * 4 + 2] = lo;
+    gs.per_image[b * 4 + 3] = nb;
+  }
+}
+
+// global group ids / word offsets: exclusive scan over the images (single thread: B is small),
+// then every image's groups and members are written at their final places
+__global__ void __launch_bounds__(1024)
+union_group_finish_kernel(int B, int64_t image_base, GroupScratch gs, int32_t* __restrict__ member_group,
+                          TileDesc* __restrict__ gdesc, int32_t* __restrict__ group_image,
+                          int64_t group_words_cap, int64_t* __restrict__ gcount) {
+  __shared__ int64_t s_gbase, s_wbase;
+  const int tid = threadIdx.x;
+  int64_t gbase = 0, wbase = 0;
+  for (int b = 0; b < B; ++b) {
+    const int64_t ng = gs.per_image[b * 4 + 0], words = gs.per_image[b * 4 + 1];
+    const int64_t lo = gs.per_image[b * 4 + 2], nb = gs.per_image[b * 4 + 3];
+    for (int64_t g = tid; g < ng; g += blockDim.x) {
+      TileDesc d = gs.tmp[lo + g];
+      d.word_off += wbase;
+      gdesc[gbase + g] = d;
+      group_image[gbase + g] = (int32_t)(image_base + b);
+    }
+    for (int64_t i = tid; i < nb; i += blockDim.x) {
+      const int l = gs.local_gid[lo + i];
+      member_group[lo + i] = l < 0 ? -1 : (int32_t)(gbase + l);
+    }
+    gbase += ng; wbase += words;
+  }
+  if (tid == 0) {
+    s_gbase = gbase; s_wbase = wbase;
+    gcount[0] = gbase;
+    gcount[1] = (wbase + 3) & ~(int64_t)3;
+    gcount[2] = 0;
+    gcount[3] = (((wbase + 3) & ~(int64_t)3) > group_words_cap) ? (int64_t)E_CAPACITY : 0;
+  }
+}
+
+size_t union_group_workspace_bytes_host(int64_t n, int B) { return group_scratch_bytes(n, B); }
+
+cudaError_t launch_union_group(const int64_t* rows_i, int64_t n, int B, int64_t image_base, void* scratch,
+                               int32_t* member_group, TileDesc* gdesc, int32_t* group_image,
+                               int64_t group_words_cap, int64_t* gcount, cudaStream_t stream) {
+  if (n == 0 || B == 0) return cudaMemsetAsync(gcount, 0, 4 * sizeof(int64_t), stream);
+  GroupScratch gs = group_carve(scratch, n, B);
+  const size_t dyn = (size_t)kGroupSmemBoxes * 20;
+  cudaFuncSetAttribute(union_group_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+  union_group_kernel<<<B, kGroupThreads, dyn, stream>>>(rows_i, n, image_base, gs);
+  union_group_finish_kernel<<<1, 1024, 0, stream>>>(B, image_base, gs, member_group, gdesc, group_image,
+                                                     group_words_cap, gcount);
+  return cudaPeekAtLastError();
+}
+
+// gcount != NULL: the groups were formed on the device (launch_union_group); G is then the
+// CAPACITY the grids are sized for (at most N groups) and gwords the capacity of the planes
 cudaError_t launch_union(int64_t n, const Workspace& ws, const int32_t* member_group,
                          const TileDesc* gdesc, const int32_t* group_image, int64_t G,
                          uint32_t* gplanes, int64_t gwords, void* rec_ws, int64_t rec_cap,
                          int64_t ext_rows_cap, double ppm, int64_t* rows_i, double* rows_f,
-                         int64_t* counters, int num_sms, cudaStream_t stream) {
+                         int64_t* counters, int num_sms, cudaStream_t stream,
+                         const int64_t* gcount) {
   cudaError_t e = cudaMemsetAsync(counters, 0, 4 * sizeof(int64_t), stream);
   if (e != cudaSuccess) return e;
   if (G == 0 || n == 0) return cudaSuccess;
@@ -276,7 +473,7 @@ cudaError_t launch_union(int64_t n, const Workspace& ws, const int32_t* member_g
     int64_t blocks = (n * 32 + 255) / 256;
     const int64_t cap = (int64_t)num_sms * 16;
     if (blocks > cap) blocks = cap;
-    union_or_kernel<<<(unsigned)blocks, 256, 0, stream>>>(n, ws.desc, ws.M, member_group, gdesc, gM);
+    union_or_kernel<<<(unsigned)blocks, 256, 0, stream>>>(n, ws.desc, ws.M, member_group, gdesc, gM, gcount);
   }
   auto lanes_for = [&](int64_t items) {
     const int64_t resident = (int64_t)num_sms * 10 * (kUnionThreads / 32);
@@ -287,7 +484,7 @@ cudaError_t launch_union(int64_t n, const Workspace& ws, const int32_t* member_g
     const int lanes = lanes_for(G);
     const int64_t warps = (G + lanes - 1) / lanes;
     const unsigned grid = (unsigned)((warps * 32 + kUnionThreads - 1) / kUnionThreads);
-    union_trace_kernel<<<grid, kUnionThreads, 0, stream>>>(G, lanes, gdesc, gM, gV, gG, R, counters);
+    union_trace_kernel<<<grid, kUnionThreads, 0, stream>>>(G, gcount, lanes, gdesc, gM, gV, gG, R, counters);
   }
   union_scan_kernel<<<1, 1024, 0, stream>>>(R, counters);
   {

@@ -18,7 +18,10 @@ size_t nms_workspace_bytes_host(const int64_t*, int, int);
 size_t union_workspace_bytes_host(int64_t, int64_t);
 cudaError_t launch_union(int64_t, const Workspace&, const int32_t*, const TileDesc*, const int32_t*,
                          int64_t, uint32_t*, int64_t, void*, int64_t, int64_t, double, int64_t*,
-                         double*, int64_t*, int, cudaStream_t);
+                         double*, int64_t*, int, cudaStream_t, const int64_t*);
+size_t union_group_workspace_bytes_host(int64_t, int);
+cudaError_t launch_union_group(const int64_t*, int64_t, int, int64_t, void*, int32_t*, TileDesc*, int32_t*,
+                               int64_t, int64_t*, cudaStream_t);
 cudaError_t launch_nms(const float*, const float*, const int64_t*, const int64_t*, int, int, float,
                        double, int, int64_t*, int32_t*, void*, cudaStream_t);
 cudaError_t launch_column_totals(int64_t, int, const Workspace&, const int32_t*, int32_t*,
@@ -27,6 +30,8 @@ cudaError_t launch_clean(int64_t, int, int, const Workspace&, const int32_t*, co
                          const int32_t*, int32_t*, int64_t*, int64_t*, cudaStream_t);
 cudaError_t launch_rle_write(int64_t, int, int, const Workspace&, const int64_t*, int64_t*,
                              cudaStream_t);
+cudaError_t launch_rle_text_prep(int64_t, const int64_t*, const int32_t*, int64_t*, cudaStream_t);
+cudaError_t launch_rle_text_write(int64_t, const int64_t*, const int32_t*, const int64_t*, uint8_t*, cudaStream_t);
 cudaError_t launch_pixel_boxes(const uint8_t*, int64_t, int, int, float*, cudaStream_t);
 cudaError_t launch_pack_tiles(const uint8_t*, int64_t, int, int, const Workspace&, cudaStream_t);
 cudaError_t launch_tiles_to_masks(int64_t, int, int, const Workspace&, uint8_t*, cudaStream_t);
@@ -231,6 +236,26 @@ int uwcv_rle_write(const void* paste_workspace, size_t ws_bytes, int64_t N, int 
              ? UWCV_OK : UWCV_E_LAUNCH;
 }
 
+int uwcv_rle_text_prep(int64_t total_runs, const int64_t* runs, const int32_t* run_instance,
+                       int64_t* chars, void* stream) {
+  if (total_runs < 0) return UWCV_E_SHAPE;
+  if (total_runs == 0) return UWCV_OK;
+  if (!runs || !run_instance || !chars) return UWCV_E_NULL;
+  return uwcv::launch_rle_text_prep(total_runs, runs, run_instance, chars,
+                                    reinterpret_cast<cudaStream_t>(stream)) == cudaSuccess
+             ? UWCV_OK : UWCV_E_LAUNCH;
+}
+
+int uwcv_rle_text_write(int64_t total_runs, const int64_t* runs, const int32_t* run_instance,
+                        const int64_t* text_offsets, uint8_t* text, void* stream) {
+  if (total_runs < 0) return UWCV_E_SHAPE;
+  if (total_runs == 0) return UWCV_OK;
+  if (!runs || !run_instance || !text_offsets || !text) return UWCV_E_NULL;
+  return uwcv::launch_rle_text_write(total_runs, runs, run_instance, text_offsets, text,
+                                     reinterpret_cast<cudaStream_t>(stream)) == cudaSuccess
+             ? UWCV_OK : UWCV_E_LAUNCH;
+}
+
 int uwcv_ingest(const void* src_host_mapped, void* dst, size_t bytes, void* stream) {
   if (bytes == 0) return UWCV_OK;
   if (!src_host_mapped || !dst) return UWCV_E_NULL;
@@ -283,12 +308,13 @@ size_t uwcv_union_workspace_bytes(int64_t rec_cap, int64_t ext_rows_cap) {
   return uwcv::union_workspace_bytes_host(rec_cap, ext_rows_cap);
 }
 
-int uwcv_union_measure(const void* paste_workspace, size_t paste_ws_bytes, int64_t N,
-                       const int32_t* member_group, const uwcv_tile* group_desc,
-                       const int32_t* group_image, int64_t G, uint32_t* group_planes,
-                       int64_t group_words, void* rec_workspace, size_t rec_ws_bytes,
-                       int64_t rec_cap, int64_t ext_rows_cap, double pixels_per_metric,
-                       int64_t* rows_i, double* rows_f, int64_t* counters, void* stream) {
+static int union_measure_impl(const void* paste_workspace, size_t paste_ws_bytes, int64_t N,
+                              const int32_t* member_group, const uwcv_tile* group_desc,
+                              const int32_t* group_image, int64_t G, uint32_t* group_planes,
+                              int64_t group_words, void* rec_workspace, size_t rec_ws_bytes,
+                              int64_t rec_cap, int64_t ext_rows_cap, double pixels_per_metric,
+                              int64_t* rows_i, double* rows_f, int64_t* counters, void* stream,
+                              const int64_t* group_counters) {
   static_assert(sizeof(uwcv_tile) == sizeof(uwcv::TileDesc), "uwcv_tile mirrors TileDesc");
   if (N < 0 || G < 0 || group_words < 0 || rec_cap < 0 || ext_rows_cap < 0) return UWCV_E_SHAPE;
   if (!(pixels_per_metric > 0.0)) return UWCV_E_SHAPE;
@@ -309,8 +335,54 @@ int uwcv_union_measure(const void* paste_workspace, size_t paste_ws_bytes, int64
                             reinterpret_cast<const uwcv::TileDesc*>(group_desc), group_image, G,
                             group_planes, group_words, rec_workspace, rec_cap, ext_rows_cap,
                             pixels_per_metric, rows_i, rows_f, counters, num_sms(),
-                            reinterpret_cast<cudaStream_t>(stream)) == cudaSuccess
+                            reinterpret_cast<cudaStream_t>(stream), group_counters) == cudaSuccess
              ? UWCV_OK : UWCV_E_LAUNCH;
+}
+
+int uwcv_union_measure(const void* paste_workspace, size_t paste_ws_bytes, int64_t N,
+                       const int32_t* member_group, const uwcv_tile* group_desc,
+                       const int32_t* group_image, int64_t G, uint32_t* group_planes,
+                       int64_t group_words, void* rec_workspace, size_t rec_ws_bytes,
+                       int64_t rec_cap, int64_t ext_rows_cap, double pixels_per_metric,
+                       int64_t* rows_i, double* rows_f, int64_t* counters, void* stream) {
+  return union_measure_impl(paste_workspace, paste_ws_bytes, N, member_group, group_desc, group_image, G,
+                            group_planes, group_words, rec_workspace, rec_ws_bytes, rec_cap, ext_rows_cap,
+                            pixels_per_metric, rows_i, rows_f, counters, stream, nullptr);
+}
+
+size_t uwcv_union_group_workspace_bytes(int64_t N, int B) {
+  return uwcv::union_group_workspace_bytes_host(N < 0 ? 0 : N, B < 0 ? 0 : B);
+}
+
+int uwcv_union_group(const int64_t* paste_rows_i, int64_t N, int B, int64_t image_base, void* group_workspace,
+                     size_t group_ws_bytes, int32_t* member_group, uwcv_tile* group_desc,
+                     int32_t* group_image, int64_t group_words_cap, int64_t* group_counters, void* stream) {
+  if (N < 0 || B < 0 || group_words_cap < 0) return UWCV_E_SHAPE;
+  if (!group_counters) return UWCV_E_NULL;
+  if (N > 0 && B > 0) {
+    if (!paste_rows_i || !group_workspace || !member_group || !group_desc || !group_image) return UWCV_E_NULL;
+    if (misaligned(paste_rows_i) || misaligned(group_workspace) || misaligned(group_desc)) return UWCV_E_ALIGN;
+    if (B > 65535) return UWCV_E_TOO_LARGE;
+    if (group_ws_bytes < uwcv::union_group_workspace_bytes_host(N, B)) return UWCV_E_WORKSPACE;
+  }
+  return uwcv::launch_union_group(paste_rows_i, N, B, image_base, group_workspace, member_group,
+                                  reinterpret_cast<uwcv::TileDesc*>(group_desc), group_image, group_words_cap,
+                                  group_counters, reinterpret_cast<cudaStream_t>(stream)) == cudaSuccess
+             ? UWCV_OK : UWCV_E_LAUNCH;
+}
+
+int uwcv_union_measure_grouped(const void* paste_workspace, size_t paste_ws_bytes, int64_t N,
+                               const int32_t* member_group, const uwcv_tile* group_desc,
+                               const int32_t* group_image, const int64_t* group_counters,
+                               uint32_t* group_planes, int64_t group_words_cap, void* rec_workspace,
+                               size_t rec_ws_bytes, int64_t rec_cap, int64_t ext_rows_cap,
+                               double pixels_per_metric, int64_t* rows_i, double* rows_f,
+                               int64_t* counters, void* stream) {
+  if (!group_counters) return UWCV_E_NULL;
+  return union_measure_impl(paste_workspace, paste_ws_bytes, N, member_group, group_desc, group_image,
+                            /*G capacity*/ N, group_planes, group_words_cap, rec_workspace, rec_ws_bytes,
+                            rec_cap, ext_rows_cap, pixels_per_metric, rows_i, rows_f, counters, stream,
+                            group_counters);
 }
 
 size_t uwcv_nms_workspace_bytes(const int64_t* image_off, int B, int num_classes) {

@@ -73,6 +73,10 @@ def lib() -> C.CDLL:
     L.uwcv_clean_masks.argtypes = [vp, sz, i64, i32, i32, vp, vp, vp, vp, vp, vp, vp]
     L.uwcv_rle_write.restype = C.c_int
     L.uwcv_rle_write.argtypes = [vp, sz, i64, i32, i32, vp, vp, vp]
+    L.uwcv_rle_text_prep.restype = C.c_int
+    L.uwcv_rle_text_prep.argtypes = [i64, vp, vp, vp, vp]
+    L.uwcv_rle_text_write.restype = C.c_int
+    L.uwcv_rle_text_write.argtypes = [i64, vp, vp, vp, vp, vp]
     L.uwcv_ingest.restype = C.c_int
     L.uwcv_ingest.argtypes = [vp, vp, sz, vp]
     L.uwcv_mask_pixel_boxes.restype = C.c_int
@@ -88,6 +92,13 @@ def lib() -> C.CDLL:
     L.uwcv_union_measure.restype = C.c_int
     L.uwcv_union_measure.argtypes = [vp, sz, i64, vp, vp, vp, i64, vp, i64, vp, sz, i64, i64, f64,
                                      vp, vp, vp, vp]
+    L.uwcv_union_group_workspace_bytes.restype = sz
+    L.uwcv_union_group_workspace_bytes.argtypes = [i64, i32]
+    L.uwcv_union_group.restype = C.c_int
+    L.uwcv_union_group.argtypes = [vp, i64, i32, i64, vp, sz, vp, vp, vp, i64, vp, vp]
+    L.uwcv_union_measure_grouped.restype = C.c_int
+    L.uwcv_union_measure_grouped.argtypes = [vp, sz, i64, vp, vp, vp, vp, vp, i64, vp, sz, i64, i64, f64,
+                                             vp, vp, vp, vp]
     L.uwcv_nms_workspace_bytes.restype = sz
     L.uwcv_nms_workspace_bytes.argtypes = [C.POINTER(C.c_int64), i32, i32]
     L.uwcv_nms_filter.restype = C.c_int
@@ -100,8 +111,10 @@ def lib() -> C.CDLL:
 EXPORTS = ("uwcv_version", "uwcv_strerror", "uwcv_plane_row_words", "uwcv_workspace_bytes",
            "uwcv_paste_measure", "uwcv_paste_measure_stages", "uwcv_paste_measure_range", "uwcv_paste_measure_heads", "uwcv_paste_measure_gather",
            "uwcv_unpack_planes", "uwcv_ingest", "uwcv_mask_column_totals", "uwcv_clean_masks", "uwcv_rle_write",
+           "uwcv_rle_text_prep", "uwcv_rle_text_write",
            "uwcv_mask_pixel_boxes", "uwcv_pack_mask_tiles", "uwcv_tiles_to_masks",
-           "uwcv_union_workspace_bytes", "uwcv_union_measure", "uwcv_nms_workspace_bytes",
+           "uwcv_union_workspace_bytes", "uwcv_union_measure", "uwcv_union_group_workspace_bytes",
+           "uwcv_union_group", "uwcv_union_measure_grouped", "uwcv_nms_workspace_bytes",
            "uwcv_nms_filter")
 
 

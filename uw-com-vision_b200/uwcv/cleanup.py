@@ -7,7 +7,8 @@ and the ``R50_flip_.csv`` it writes (``ImageId, EncodedPixels``).
 
 ``export_rle`` takes the RAW predictor output (as ``measure_instances`` does), pastes the masks
 into bit tiles on the GPU and runs the clean-up and the run extraction there
-(``csrc/cleanup.cu``); the host only formats the runs as text.  The reference's quirks are kept
+(``csrc/cleanup.cu``), the ``EncodedPixels`` text included (digits printed by a kernel); the host
+only slices the text per instance.  The reference's quirks are kept
 (the image is skipped when a score is exactly zero; the instance list is truncated to the number
 of image columns holding more than ``min_crys_size`` mask pixels when that number is smaller
 than the instance count): see oracle/cleanup.py for the line-by-line reading.
@@ -191,30 +192,26 @@ def export_rle(instances, output_size: Optional[Tuple[int, int]] = None,
         _lib.check(L.uwcv_rle_write(_ptr(ws), ws.numel(), n, H, W, _ptr(run_off), _ptr(runs), st),
                    "uwcv_rle_write")
         eng.launches += 1
-        h_runs = runs[:total].cpu().numpy()
-        h_off = run_off.cpu().numpy()
+        # the text on the device: characters per (merged) run -> offsets -> digits
+        run_inst = torch.repeat_interleave(torch.arange(n, dtype=torch.int32, device=dev), nruns,
+                                           output_size=total)
+        chars = torch.empty(max(total, 1), dtype=torch.int64, device=dev)
+        _lib.check(L.uwcv_rle_text_prep(total, _ptr(runs), _ptr(run_inst), _ptr(chars), st),
+                   "uwcv_rle_text_prep")
+        toff = torch.zeros(total + 1, dtype=torch.int64, device=dev)
+        if total:
+            torch.cumsum(chars[:total], 0, out=toff[1:])
+        inst_text = toff[run_off]                              # [n + 1] first character of every instance
+        nchar = int(toff[-1].item())
+        text = torch.empty(max(nchar, 1), dtype=torch.uint8, device=dev)
+        _lib.check(L.uwcv_rle_text_write(total, _ptr(runs), _ptr(run_inst), _ptr(toff), _ptr(text), st),
+                   "uwcv_rle_text_write")
+        eng.launches += 3
+        h_text = text[:nchar].cpu().numpy().tobytes()
+        h_bounds = inst_text.cpu().tolist()
         h_flags = flags.cpu().numpy()
         h_area = area.cpu().numpy()
         h_limit = d_limit.cpu().numpy()
-    # a run ending on the last row and the next starting on row 0 of the following column are
-    # consecutive flat indices: one run for the reference
-    inst_of_run = np.repeat(np.arange(n), np.diff(h_off))
-    if total:
-        s, l = h_runs[:, 0], h_runs[:, 1]
-        cont = np.zeros(total, dtype=bool)
-        cont[1:] = (s[1:] == s[:-1] + l[:-1]) & (inst_of_run[1:] == inst_of_run[:-1])
-        head = np.flatnonzero(~cont)
-        m_start = s[head]
-        m_len = np.add.reduceat(l, head)
-        m_inst = inst_of_run[head]
-    else:
-        m_start = m_len = m_inst = np.zeros(0, np.int64)
-    bounds = np.searchsorted(m_inst, np.arange(n + 1)).tolist()
-    # text of every number once (start, length interleaved), joined per instance below
-    inter = np.empty(2 * len(m_start), dtype=np.int64)
-    inter[0::2] = m_start
-    inter[1::2] = m_len
-    words = list(map(str, inter.tolist()))
     slot = torch.cat(slot_l).numpy()
     idx = torch.cat(inst_l).numpy()
     out = RleExport([], [], None, None, None, None)
@@ -222,7 +219,8 @@ def export_rle(instances, output_size: Optional[Tuple[int, int]] = None,
     ids = [nm.replace('.tif', '') for nm in names]
     for i, b in zip(kr.tolist(), slot[kr].tolist()):
         out.image_id.append(ids[b])
-        out.encoded_pixels.append(' '.join(words[2 * bounds[i]: 2 * bounds[i + 1]]))
+        lo_c, hi_c = h_bounds[i], h_bounds[i + 1]
+        out.encoded_pixels.append(h_text[lo_c: hi_c - 1].decode("ascii") if hi_c > lo_c else "")
     out.image_idx = slot[kr].astype(np.int64)
     out.inst_idx = idx[kr].astype(np.int64)
     out.area = h_area[kr]

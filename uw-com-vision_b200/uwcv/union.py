@@ -3,8 +3,9 @@
 nn_inference.py:394-459 ORs the masks of the class of interest into ONE image and measures
 every external contour of that union (contourArea >= 100), left to right: touching instances
 merge and an instance with several blobs yields several rows.  ``measure_union`` reproduces
-those rows; the pixel work (paste, OR, border following, descriptors) runs in libuwcv.so, the
-host only groups instances by box overlap (N x 4 integers) and orders the small row table.
+those rows; everything between the predictor output and the row table runs in libuwcv.so --
+paste, grouping of the instances by box overlap (``uwcv_union_group``), OR, border following,
+descriptors -- with ONE synchronising read at the end; the host orders the small row table.
 """
 from __future__ import annotations
 
@@ -45,32 +46,6 @@ class UnionTable:
         return self.floats[ok][:, 7:16]
 
 
-def _group_by_overlap(img: np.ndarray, bbox: np.ndarray, valid: np.ndarray):
-    """Connected groups of instances (per image) whose 1-pixel-dilated pixel boxes overlap.
-    Returns (member_group [N] int32, list of (image, x0, y0, x1, y1) per group)."""
-    from scipy.sparse import coo_matrix
-    from scipy.sparse.csgraph import connected_components
-    n = len(img)
-    member = np.full(n, -1, dtype=np.int32)
-    groups = []
-    for b in np.unique(img[valid]):
-        idx = np.flatnonzero(valid & (img == b))
-        x0, y0, x1, y1 = (bbox[idx, k].astype(np.int64) for k in range(4))
-        # boxes [x0-1, x1+1] x [y0-1, y1+1] intersect  <=>  8-adjacent or overlapping pixel boxes
-        ov = (x0[:, None] - 1 <= x1[None, :] + 1) & (x0[None, :] - 1 <= x1[:, None] + 1) & \
-             (y0[:, None] - 1 <= y1[None, :] + 1) & (y0[None, :] - 1 <= y1[:, None] + 1)
-        r, c = np.nonzero(ov)
-        ncomp, lab = connected_components(coo_matrix((np.ones(len(r), np.int8), (r, c)),
-                                                     shape=(len(idx), len(idx))), directed=False)
-        base = len(groups)
-        member[idx] = base + lab
-        for g in range(ncomp):
-            m = lab == g
-            groups.append((int(b), int(x0[m].min()), int(y0[m].min()), int(x1[m].max()),
-                           int(y1[m].max())))
-    return member, groups
-
-
 def measure_union(instances, output_size: Optional[Tuple[int, int]] = None,
                   classes_of_interest: Optional[Sequence[int]] = None, *,
                   mask_threshold: float = 0.5, pixels_per_metric: float = 0.85,
@@ -100,6 +75,8 @@ def measure_union(instances, output_size: Optional[Tuple[int, int]] = None,
     if n == 0:
         return empty
     L = eng.L
+    B = len(batch)
+    st = _stream_ptr(dev)
     with torch.cuda.device(dev):
         d_boxes = boxes.contiguous().to(dev)
         d_masks = torch.cat(ml).contiguous().to(dev)
@@ -107,57 +84,64 @@ def measure_union(instances, output_size: Optional[Tuple[int, int]] = None,
         rows_i = torch.empty((n, NUM_INT), dtype=torch.int64, device=dev)
         rows_f = torch.empty((n, NUM_FLOAT), dtype=torch.float64, device=dev)
         # layout + paste (cropped: no full-frame planes), no per-instance contour pass
+        member_words = tile_words(boxes, H, W)
         eng.run(d_masks, d_boxes, H, W, image_idx=d_img, threshold=mask_threshold,
                 pixels_per_metric=pixels_per_metric, rows_i=rows_i, rows_f=rows_f, stages=3,
-                n_tile_words=tile_words(boxes, H, W))
-        hi = rows_i.cpu().numpy()
-        eng.check_status()
-        valid = hi[:, ICOL["valid"]] == 1
-        if not valid.any():
-            return empty
-        bbox = hi[:, [ICOL["bbox_x0"], ICOL["bbox_y0"], ICOL["bbox_x1"], ICOL["bbox_y1"]]]
-        member, groups = _group_by_overlap(hi[:, ICOL["image_idx"]], bbox, valid)
-        G = len(groups)
-        gdesc = np.zeros(G, dtype=np.dtype([("wx0", "<i4"), ("y0", "<i4"), ("tw", "<i4"),
-                                            ("th", "<i4"), ("word_off", "<i8"), ("res", "<i8")]))
-        gimg = np.zeros(G, dtype=np.int32)
-        off = 0
-        for g, (b, x0, y0, x1, y1) in enumerate(groups):
-            wx0 = x0 >> 5
-            tw = (x1 >> 5) - wx0 + 1
-            th = y1 - y0 + 1
-            gdesc[g] = (wx0, y0, tw, th, off, 0)
-            gimg[g] = b
-            off += tw * th
-        gwords = (off + 3) & ~3
-        d_member = torch.from_numpy(member).to(dev)
-        d_gdesc = torch.from_numpy(gdesc.view(np.uint8).copy()).to(dev)
-        d_gimg = torch.from_numpy(gimg).to(dev)
-        gplanes = torch.empty(3 * gwords, dtype=torch.int32, device=dev)
-        counters = torch.zeros(4, dtype=torch.int64, device=dev)
-        rec_cap = 2 * int(valid.sum()) + 256
-        ext_cap = 4 * int(gdesc["th"].sum()) + 1024
+                n_tile_words=member_words)
         ws = eng._ws
+        # groups on the device (no host round trip between the paste and the contour kernels)
+        gws = torch.empty(L.uwcv_union_group_workspace_bytes(n, B), dtype=torch.uint8, device=dev)
+        d_member = torch.empty(n, dtype=torch.int32, device=dev)
+        d_gdesc = torch.empty(n * 32, dtype=torch.uint8, device=dev)
+        d_gimg = torch.empty(n, dtype=torch.int32, device=dev)
+        gcount = torch.zeros(4, dtype=torch.int64, device=dev)
+        counters = torch.zeros(4, dtype=torch.int64, device=dev)
+        # capacities: a group tile can exceed the sum of its members' tiles (a diagonal chain of
+        # boxes), a contour count / extreme-row count is data dependent: generous first guesses,
+        # exact sizes reported by the device when one of them is too small
+        gwords_cap = 4 * int(member_words) + 4096
+        rec_cap = 2 * n + 256
+        ext_cap = 8 * int(boxes[:, 3].sub(boxes[:, 1]).clamp(min=0).sum().item()) + 16 * n + 1024
         for _attempt in range(3):
+            gwords_cap = (gwords_cap + 3) & ~3
+            gplanes = torch.empty(3 * gwords_cap, dtype=torch.int32, device=dev)
             rec_ws = torch.empty(L.uwcv_union_workspace_bytes(rec_cap, ext_cap), dtype=torch.uint8,
                                  device=dev)
             u_i = torch.zeros((rec_cap, 10), dtype=torch.int64, device=dev)
             u_f = torch.zeros((rec_cap, 16), dtype=torch.float64, device=dev)
-            rc = L.uwcv_union_measure(_ptr(ws), ws.numel(), n, _ptr(d_member), _ptr(d_gdesc),
-                                      _ptr(d_gimg), G, _ptr(gplanes), gwords, _ptr(rec_ws),
-                                      rec_ws.numel(), rec_cap, ext_cap, float(pixels_per_metric),
-                                      _ptr(u_i), _ptr(u_f), _ptr(counters), _stream_ptr(dev))
-            _lib.check(rc, "uwcv_union_measure")
-            eng.launches += 4
-            c = counters.cpu().tolist()
-            if c[1] == 0:
+            _lib.check(L.uwcv_union_group(_ptr(rows_i), n, B, int(image_idx_offset), _ptr(gws), gws.numel(),
+                                          _ptr(d_member), _ptr(d_gdesc), _ptr(d_gimg), gwords_cap,
+                                          _ptr(gcount), st), "uwcv_union_group")
+            _lib.check(L.uwcv_union_measure_grouped(_ptr(ws), ws.numel(), n, _ptr(d_member), _ptr(d_gdesc),
+                                                    _ptr(d_gimg), _ptr(gcount), _ptr(gplanes), gwords_cap,
+                                                    _ptr(rec_ws), rec_ws.numel(), rec_cap, ext_cap,
+                                                    float(pixels_per_metric), _ptr(u_i), _ptr(u_f),
+                                                    _ptr(counters), st), "uwcv_union_measure_grouped")
+            eng.launches += 6
+            # ONE synchronising read for the whole call: status, counters and the rows together
+            pin = torch.empty(12, dtype=torch.int64).pin_memory()
+            pin[0:4].copy_(eng.status, non_blocking=True)
+            pin[4:8].copy_(gcount, non_blocking=True)
+            pin[8:12].copy_(counters, non_blocking=True)
+            h_i = torch.empty((rec_cap, 10), dtype=torch.int64).pin_memory()
+            h_f = torch.empty((rec_cap, 16), dtype=torch.float64).pin_memory()
+            h_i.copy_(u_i, non_blocking=True)
+            h_f.copy_(u_f, non_blocking=True)
+            torch.cuda.current_stream(dev).synchronize()
+            c = pin.tolist()
+            if c[0] != 0:
+                raise _lib.UwcvError(int(c[0]), f"uwcv_paste_measure (needs {int(c[1])} tile words)")
+            if c[7] == 0 and c[9] == 0:
                 break
-            rec_cap = max(rec_cap, int(c[0]) + 64)          # exact needs reported by the device
-            ext_cap = max(ext_cap, int(c[2]) + 64)
+            gwords_cap = max(gwords_cap, int(c[5]) + 64)     # exact needs reported by the device
+            rec_cap = max(rec_cap, int(c[8]) + 64)
+            ext_cap = max(ext_cap, int(c[10]) + 64)
         else:
             raise _lib.UwcvError(_lib.E_CAPACITY, "uwcv_union_measure")
-        k = int(c[0])
-        ui, uf = u_i[:k].cpu().numpy(), u_f[:k].cpu().numpy()
+        k = int(c[8])
+        if k == 0:
+            return empty
+        ui, uf = h_i[:k].numpy().copy(), h_f[:k].numpy().copy()
     # reference order: cv2 returns contours in reverse raster order of their start pixel and
     # imutils sorts them (stable) by boundingRect x; rows of different images stay image-major
     order = np.lexsort((-ui[:, 2], -ui[:, 3]))              # (start_y, start_x) descending
