@@ -9,6 +9,13 @@ for p in (ROOT, os.path.join(ROOT, "uw-com-vision_b200")):
         sys.path.insert(0, p)
 
 
+# UWCV_TEST_VARIANT=check runs the whole suite against lib/libuwcv_check.so (device-side bounds
+# traps, the memory-safety run kept in profiles/); test infrastructure, not a product knob
+if os.environ.get("UWCV_TEST_VARIANT"):
+    from uwcv import _lib as _uwcv_lib
+    _uwcv_lib.use_library_variant(os.environ["UWCV_TEST_VARIANT"])
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
 

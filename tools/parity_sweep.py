@@ -5,6 +5,9 @@ import json, os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "uw-com-vision_b200")); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np, torch
+from uwcv import _lib as _uwcv_lib
+if os.environ.get('UWCV_TEST_VARIANT'):
+    _uwcv_lib.use_library_variant(os.environ['UWCV_TEST_VARIANT'])
 import uwcv
 from uwcv import synth, schema
 from oracle import d2, pipeline as P, cleanup as OC

@@ -105,6 +105,10 @@ contour_measure_kernel(int64_t first, int64_t n, int lanes, const float* __restr
   t.tw = d.tw; t.th = d.th;
   // two sets of per-row extremes (left | right): the contour being traced and the best so far
   uint32_t* ext0 = ws.scratch + 4 * d.row_off;
+  if (live) {
+    UWCV_BOUND(d.word_off + (int64_t)d.tw * d.th, ws.cap_words + 1);
+    UWCV_BOUND(4 * (d.row_off + d.th), 4 * ws.cap_words + 1);     // extremes: 4 words per tile row
+  }
   LaneTracer<GlobalMem> T;
   T.idle();
   // rows outside the pixel bbox cannot hold a start pixel

@@ -118,6 +118,7 @@ __device__ __forceinline__ void trace_begin(const TileView& t, Trace& c, int x0,
   c.area2 = 0; c.perim = 0.0; c.npts = 0; c.ymax = y0;
   c.x0 = x0; c.y0 = y0; c.x3 = x0; c.y3 = y0;
   c.fvx = c.fvy = c.lvx = c.lvy = 0;
+  UWCV_BOUND(y0, t.th); UWCV_BOUND(x0, 32 * t.tw);
   c.w.template load<Mem>(t, x0, y0);
   c.nb = c.w.neighbours(x0);
   if (kExt) { Mem::st(ext_l + y0, (uint32_t)x0); Mem::st(ext_r + y0, (uint32_t)x0); }
@@ -151,6 +152,7 @@ __device__ __forceinline__ void trace_step(const TileView& t, Trace& c, uint32_t
   const uint32_t rot = ((c.nb | (c.nb << 8)) >> ((s_end + 1) & 7)) & 0xFFu;
   const int s = (s_end + __ffs(rot)) & 7;     // s_end + 1 + (ffs - 1)
   const int x3 = c.x3, y3 = c.y3;
+  UWCV_BOUND(y3, t.th); UWCV_BOUND(x3, 32 * t.tw);
   if (kMark) {
     const int o = y3 * t.tw + (x3 >> 5);
     const uint32_t b = 1u << (x3 & 31);
@@ -179,6 +181,7 @@ __device__ __forceinline__ void trace_step(const TileView& t, Trace& c, uint32_t
     return;
   }
   c.x3 = x4; c.y3 = y4;
+  UWCV_BOUND(y4, t.th); UWCV_BOUND(x4, 32 * t.tw);     // the walk never leaves the tile (zero frame)
   if (y4 > c.ymax) {                          // rows are first reached in increasing order
     c.ymax = y4;
     if (kExt) { Mem::st(ext_l + y4, (uint32_t)x4); Mem::st(ext_r + y4, (uint32_t)x4); }
@@ -194,6 +197,7 @@ __device__ __forceinline__ void trace_step(const TileView& t, Trace& c, uint32_t
 // sign of the last marked pixel in words [0, wi) of row y: 0 none, +1 positive, -1 negative
 template <class Mem = GlobalMem>
 static __device__ int last_mark_before(const TileView& t, int wi, int y) {
+  UWCV_BOUND(y, t.th); UWCV_BOUND(wi, t.tw + 1);
   const int row = y * t.tw;
   for (--wi; wi >= 0; --wi) {
     const uint32_t v = Mem::ld(t.V + row + wi);
@@ -226,12 +230,14 @@ struct LaneTracer {
   Trace tr;
 
   __device__ __forceinline__ uint64_t load_pair(const uint32_t* plane, int yy, int w0) const {
+    UWCV_BOUND(yy, t.th); UWCV_BOUND(w0, t.tw);
     const uint32_t* row = plane + yy * t.tw;
     const uint32_t lo = Mem::ld(row + w0);
     const uint32_t hi = (w0 + 1 < t.tw) ? Mem::ld(row + w0 + 1) : 0u;
     return (uint64_t)lo | ((uint64_t)hi << 32);
   }
   __device__ __forceinline__ uint64_t load_pair_m(int yy, int w0) const {
+    UWCV_BOUND(yy, t.th); UWCV_BOUND(w0, t.tw);
     const uint32_t* row = t.M + yy * t.tw;
     const uint32_t lo = Mem::ldm(row + w0);
     const uint32_t hi = (w0 + 1 < t.tw) ? Mem::ldm(row + w0 + 1) : 0u;
@@ -629,6 +635,7 @@ static __device__ void describe_contour(bool have, uint32_t* ext_l, uint32_t* ex
     bool need = true;
     while (__any_sync(kFull, yy <= ylast)) {
       if (yy <= ylast) {
+        UWCV_BOUND(yy - y0, ymax - y0 + 1); UWCV_BOUND(nr, ymax - y0 + 1);
         if (need) { p = pk((int)ext_r[yy], yy); need = false; }
         if (nr >= 2 && cross3(a, b, p) <= 0) {
           --nr; b = a;
@@ -648,6 +655,7 @@ static __device__ void describe_contour(bool have, uint32_t* ext_l, uint32_t* ex
     bool need = true;
     while (__any_sync(kFull, yy <= ylast)) {
       if (yy <= ylast) {
+        UWCV_BOUND(yy - y0, ymax - y0 + 1); UWCV_BOUND(nl, ymax - y0 + 1);
         if (need) { p = pk((int)ext_l[yy], yy); need = false; }
         if (nl >= 2 && cross3(a, b, p) >= 0) {
           --nl; b = a;

@@ -247,6 +247,8 @@ __device__ __forceinline__ void paste_rows(const TileDesc& d, int rbase, const f
     // lane r holds the word of row rbase + r
     if (lane < nrows) {
       const int64_t o = (int64_t)(rbase + lane) * d.tw + strip;
+      UWCV_BOUND(o, (int64_t)d.tw * d.th);
+      UWCV_BOUND(d.y0 + rbase + lane, 32768); UWCV_BOUND(d.wx0 + strip, wpr);
       tM[o] = myword;
       if (sM) sM[o] = myword;                          // shared-memory copy for the tracer warp
       if (kPlanes) plane[(int64_t)(d.y0 + rbase + lane) * wpr + d.wx0 + strip] = myword;
@@ -398,6 +400,7 @@ paste_measure_kernel(const float* __restrict__ masks, const float* __restrict__ 
           for (int64_t o = seg_lo[sgi]; o < seg_hi[sgi]; o += zero_bytes) {
             const int64_t rem = seg_hi[sgi] - o;
             const uint32_t nbytes = (uint32_t)(rem < zero_bytes ? rem : zero_bytes);
+            UWCV_BOUND(o + nbytes, plane_words * 4 + 1); UWCV_BOUND(inst, n);
             if (fill_mode == 2) bulk_store_zero_hint(base + o, zero_smem, nbytes, policy);
             else bulk_store_zero(base + o, zero_smem, nbytes);
             if (rot_mul > 0) {                       // bounded number of bulk stores in flight
@@ -564,6 +567,9 @@ paste_measure_kernel(const float* __restrict__ masks, const float* __restrict__ 
     compute_barrier();
 
     // ---- the tile: each warp takes groups of 32 rows --------------------------------
+    UWCV_BOUND(d.word_off + (int64_t)d.tw * d.th, ws.cap_words + 1);
+    UWCV_BOUND(d.y0 + d.th, H + 1); UWCV_BOUND(d.wx0 + d.tw, wpr + 1);
+    if (band_tma) UWCV_BOUND((int64_t)d.th * wpr * 4, (int64_t)band_bytes_cap + 1);
     uint32_t* tM = ws.M + d.word_off;
     uint32_t* sM = nullptr;                            // the slot: mask bits | visited | sign | extremes
     if (kFused && s_slot >= 0) {
@@ -641,6 +647,7 @@ paste_measure_kernel(const float* __restrict__ masks, const float* __restrict__ 
       compute_barrier();
       for (int k = tid; k < d.th * d.tw; k += kComputeThreads) {     // back to all zeros
         const int r = k / d.tw, c = k - r * d.tw;
+        UWCV_BOUND((r * wpr + d.wx0 + c) * 4, band_bytes_cap);
         s_band[r * wpr + d.wx0 + c] = 0u;
       }
       fence_proxy_async_smem();

@@ -410,7 +410,6 @@ __global__ void __launch_bounds__(1024)
 union_group_finish_kernel(int B, int64_t image_base, GroupScratch gs, int32_t* __restrict__ member_group,
                           TileDesc* __restrict__ gdesc, int32_t* __restrict__ group_image,
                           int64_t group_words_cap, int64_t* __restrict__ gcount) {
-  __shared__ int64_t s_gbase, s_wbase;
   const int tid = threadIdx.x;
   int64_t gbase = 0, wbase = 0;
   for (int b = 0; b < B; ++b) {
@@ -429,7 +428,6 @@ union_group_finish_kernel(int B, int64_t image_base, GroupScratch gs, int32_t* _
     gbase += ng; wbase += words;
   }
   if (tid == 0) {
-    s_gbase = gbase; s_wbase = wbase;
     gcount[0] = gbase;
     gcount[1] = (wbase + 3) & ~(int64_t)3;
     gcount[2] = 0;

@@ -7,6 +7,24 @@
 #include <cstdint>
 #include <cuda_runtime.h>
 
+// -DUWCV_CHECK (lib/libuwcv_check.so): device-side bounds traps on every tile / plane / band /
+// extremes / mark index the kernels compute -- the memory-safety substitute for compute-sanitizer
+// (closed on the GPU pool).  The GPU test set and tools/parity_sweep.py are run against it
+// (UWCV_TEST_VARIANT=check); a violated bound prints its source line and traps the kernel.
+#ifdef UWCV_CHECK
+#include <cstdio>
+#define UWCV_BOUND(idx, limit)                                                                   \
+  do {                                                                                           \
+    if (!((long long)(idx) >= 0 && (long long)(idx) < (long long)(limit))) {                     \
+      printf("UWCV_CHECK %s:%d: index %lld outside [0, %lld)\n", __FILE__, __LINE__,             \
+             (long long)(idx), (long long)(limit));                                              \
+      __trap();                                                                                  \
+    }                                                                                            \
+  } while (0)
+#else
+#define UWCV_BOUND(idx, limit) do { } while (0)
+#endif
+
 namespace uwcv {
 
 constexpr int kMaskSide = 28;              // Detectron2 / torchvision mask head output side
