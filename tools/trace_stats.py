@@ -47,4 +47,7 @@ lanes = 22
 w = tot[: n // lanes * lanes].reshape(-1, lanes)
 out["warp_max_mean"] = float(w.max(1).mean())
 out["warp_sum_over_max"] = float((w.sum(1) / np.maximum(w.max(1), 1)).mean())
+words_each = api.tile_words_each(boxes, H, W).numpy()
+np.savez_compressed(os.path.join(ROOT, "gpurun_out", "trace_stats_arrays.npz"), stats=s, words=words_each,
+                    area=hi[:, 5], bbox=hi[:, 6:10], boxes=boxes.numpy())
 print(json.dumps(out))
