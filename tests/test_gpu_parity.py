@@ -814,3 +814,66 @@ def test_moment_overflow_is_refused_not_wrapped():
     assert ei.value.code == -8
     eng.run(m, ok_boxes, H, W)                       # the engine is usable afterwards
     eng.check_status()
+
+
+def _shared_table_worker(q):
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for p in (root, os.path.join(root, "uw-com-vision_b200")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    import gc
+    import torch.distributed as dist
+    from uwcv.dist import SharedHostTable
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(29700 + os.getpid() % 1000)
+    torch.cuda.set_device(0)
+    dev = torch.device("cuda", 0)
+    dist.init_process_group("nccl", rank=0, world_size=1, device_id=dev)
+    try:
+        ht = SharedHostTable(dev)
+        kept, ok = [], True
+        for call in range(2 * ht.SETS + 1):                    # every set is reused at least once
+            n = 50 + call
+            ri = torch.arange(n * 20, dtype=torch.int64, device=dev).view(n, 20) + 1000 * call
+            rf = (torch.arange(n * 30, dtype=torch.float64, device=dev).view(n, 30) + 0.5) * (call + 1)
+            k, seq, base, total = ht.begin([n])
+            assert (base, total) == (0, n) and seq == call and k == call % ht.SETS
+            ht.copy_rows(k, seq, base, ri, rf)
+            torch.cuda.current_stream().synchronize()
+            ht.wait_all(k, seq)                                 # the flag word landed behind the rows
+            a_i, a_f = ht.arrays(k, seq, 0, total, whole=True)
+            ok &= bool(np.array_equal(a_i, ri.cpu().numpy()) and np.array_equal(a_f, rf.cpu().numpy()))
+            kept.append((a_i[:, 3], a_f))                       # a slice keeps the set leased ...
+            if len(kept) > ht.SETS - 2:
+                kept.pop(0)                                     # ... until it is dropped
+                gc.collect()
+        # a table that is never dropped blocks the reuse of its set with a clear error
+        kept.clear()
+        del a_i, a_f
+        gc.collect()
+        hold = [ht.arrays(*(ht.begin([10])[:2]), 0, 10, whole=True) for _ in range(ht.SETS)]
+        try:
+            ht.begin([10], timeout_s=0.3)
+            blocked = False
+        except RuntimeError as e:
+            blocked = "still referenced" in str(e)
+        q.put((ok, blocked))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_shared_host_table_on_one_gpu():
+    """uwcv.dist.SharedHostTable (the host-sink of the e2e gather) with a one-rank group: rows and
+    the completion flag land in the registered shared segment, sets are reused only after their
+    views are dropped, and a table held forever is reported instead of being overwritten."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    p = ctx.Process(target=_shared_table_worker, args=(q,))
+    p.start()
+    ok, blocked = q.get(timeout=180)
+    p.join(timeout=60)
+    assert p.exitcode == 0
+    assert ok, "rows read back from the shared table differ"
+    assert blocked, "reusing a set whose table is still referenced must raise"

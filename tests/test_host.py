@@ -273,3 +273,27 @@ def test_release_library_reads_no_environment_knobs():
         assert knob not in blob, knob
     assert "uwcv_tuning_" not in subprocess.run(["nm", "-D", "--defined-only", LIB_PATH],
                                                 capture_output=True, text=True).stdout
+
+
+def test_host_lease_releases_when_the_last_view_dies():
+    """Explicit ownership of returned host buffers (no sys.getrefcount): the numpy
+    arrays handed out hang off a HostLease; the release callback runs once, when the table AND every
+    slice taken from it are gone."""
+    import gc
+    from uwcv.api import HostLease
+    buf = torch.arange(100, dtype=torch.int64)
+    fired = []
+    arr = HostLease(buf.data_ptr(), 100, lambda: fired.append(1), keep=buf).array()
+    rows = arr[10:30].reshape(2, 10)
+    col = rows[:, 3]
+    as_f = arr[40:50].view(np.float64)
+    assert rows[1, 2] == 22
+    del arr, rows
+    gc.collect()
+    assert not fired                      # two views are still alive
+    del col
+    gc.collect()
+    assert not fired
+    del as_f
+    gc.collect()
+    assert fired == [1]

@@ -38,7 +38,11 @@ __device__ int32_t* g_trace_stats = nullptr;
 static_assert((kNumInt * 8) % 16 == 0 && (kNumFloat * 8) % 16 == 0, "rows are copied as 16-byte words");
 static_assert(F_CHORDS - F_CAREA == 15, "describe_contour writes 16 contiguous float columns");
 
+#ifdef UWCV_CONTOUR_MINBLOCKS                               // (tuning sweep: register cap vs co-residency)
+__global__ void __launch_bounds__(kContourThreads, UWCV_CONTOUR_MINBLOCKS)
+#else
 __global__ void __launch_bounds__(kContourThreads)
+#endif
 contour_measure_kernel(int64_t first, int64_t n, int lanes, const float* __restrict__ scores,
                        double pixels_per_metric, int64_t* __restrict__ rows_i,
                        double* __restrict__ rows_f, Workspace ws,

@@ -799,29 +799,125 @@ class MeasurementStream:
             yield inflight.pop(0).result()
 
 
-def submit_measure_instances(instances, output_size=None, classes_of_interest=None, *,
-                             mask_threshold: float = 0.5, pixels_per_metric: float = 0.85,
-                             image_idx_offset: int = 0, return_planes: bool = False,
-                             write_planes: bool = False, gather: bool = False,
-                             gather_counts: Optional[Sequence[int]] = None,
-                             gather_dst: Optional[int] = None, gather_sink: str = "auto",
-                             mask_channel_offset: int = 0,
-                             pipeline_chunks: int = 4, device=None, _exact_words: bool = False,
-                             _slot: int = 0, _no_fast: bool = False) -> PendingTable:
-    """Enqueue one ``measure_instances`` call (same arguments) and return its handle."""
-    single = not isinstance(instances, (list, tuple))
-    batch: List[object] = [instances] if single else list(instances)
-    dev = _require_cuda(device)
-    eng = Engine.get(dev)
-    empty = (MeasurementTable.empty(), None) if return_planes else MeasurementTable.empty()
-    if not batch:
-        return PendingTable.ready(MeasurementTable.empty())
-    H, W = (int(output_size[0]), int(output_size[1])) if output_size is not None else \
-        tuple(int(v) for v in batch[0].image_size)
-    slot = eng.slot(_slot)
-    if slot.pending is not None:            # the slot's previous call has not been collected
-        slot.pending.result()
+def _rank_counts(gather_counts, n: int, world: int, dev) -> List[int]:
+    """Rows per rank of a gathered call: as given, else exchanged (one synchronising read)."""
+    if gather_counts is not None:
+        return [int(c) for c in gather_counts]
+    import torch.distributed as dist
+    c_l = torch.tensor([n], dtype=torch.int64, device=dev)
+    c_all = torch.empty(world, dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(c_all, c_l)
+    return c_all.cpu().tolist()
 
+
+def _copy_status(eng, slot, pend, status, d_ok):
+    """(On the d2h stream.)  Status word and the validity flag of the device-input path."""
+    hp_s = slot.pinned("status", (4,), torch.int64)
+    hp_s.copy_(status, non_blocking=True)
+    if d_ok is not None:
+        pend.hp_ok = slot.pinned("ok", (1,), torch.int64)
+        pend.hp_ok.copy_(d_ok, non_blocking=True)
+        d_ok.record_stream(eng.d2h_stream)
+    return hp_s
+
+
+def _read_back_to_shared_table(eng, slot, pend, ht, call, dst: int, rows_done, rows_i, rows_f,
+                               status, d_ok, n: int) -> "PendingTable":
+    """The host is the sink of the gather: this rank's rows go to its offset of the node-shared
+    host table; the destination rank returns the whole table, the others their own rows."""
+    import torch.distributed as dist
+    hk, hseq, hbase, htotal = call
+    is_dst = dist.get_rank() == dst
+    with torch.cuda.stream(eng.d2h_stream):
+        eng.d2h_stream.wait_event(rows_done)
+        ht.copy_rows(hk, hseq, hbase, rows_i, rows_f)
+        hp_s = _copy_status(eng, slot, pend, status, d_ok)
+        done = torch.cuda.Event()
+        done.record(eng.d2h_stream)
+    lo, hi = (0, htotal) if is_dst else (hbase, hbase + n)
+    pend.np_i, pend.np_f = ht.arrays(hk, hseq, lo, hi, whole=is_dst)
+    if is_dst:
+        pend._after_sync = lambda: ht.wait_all(hk, hseq)
+    pend.n = hi - lo
+    pend.hp_i = pend.hp_f = None
+    pend.hp_s = hp_s
+    pend._done = done
+    slot.pending = pend
+    return pend
+
+
+def _stage_small_arrays(eng, slot, dev, main, n, boxes, sl, cl, il, jl):
+    """The five small per-instance arrays (boxes, scores, classes, image / instance index) in ONE
+    packed device buffer of the slot.  Returns their device views."""
+    nb = dict(non_blocking=True)
+    small_parts = (("boxes", [boxes], torch.float32, 4), ("scores", sl, torch.float32, 1),
+                   ("classes", cl, torch.int64, 1), ("img", il, torch.int32, 1),
+                   ("inst", jl, torch.int32, 1))
+    on_device = any(p_.is_cuda for _, parts, _, _ in small_parts for p_ in parts)
+    # one packed buffer for the five small arrays (every segment 256-byte aligned)
+    offs, total_b = {}, 0
+    for name, _parts, dt, width in small_parts:
+        offs[name] = total_b
+        total_b += (n * width * dt.itemsize + 255) // 256 * 256
+    d_small = slot.device("small", (total_b,), torch.uint8)
+
+    def seg(buf, name, dt, width):
+        v = buf[offs[name]: offs[name] + n * width * dt.itemsize].view(dt)
+        return v.view(n, width) if width > 1 else v
+
+    d_boxes, d_scores, d_classes, d_img, d_inst = (seg(d_small, nm, dt, w)
+                                                   for nm, _p, dt, w in small_parts)
+    if on_device:
+        # device-resident inputs: plain device copies behind their producer
+        eng.small_stream.wait_stream(main)
+        with torch.cuda.stream(eng.small_stream):
+            for (name, parts, dt, w), dst in zip(small_parts, (d_boxes, d_scores, d_classes,
+                                                               d_img, d_inst)):
+                src = parts[0] if len(parts) == 1 else torch.cat([p_.to(dev) for p_ in parts])
+                dst.copy_(src.to(dt).reshape(dst.shape), **nb)
+            ev_small = torch.cuda.Event()
+            ev_small.record(eng.small_stream)
+        main.wait_event(ev_small)
+    else:
+        # host inputs: packed into pinned (device-mapped) memory and pulled in by ONE kernel on
+        # the main stream (uwcv_ingest).  The copy engine serves copies in issue order: 1 MB of
+        # boxes queued behind 200 MB of masks would hold the layout back for milliseconds
+        h_small = slot.pinned("small", (total_b,), torch.uint8)
+        for name, parts, dt, w in small_parts:
+            dst = seg(h_small, name, dt, w)
+            if len(parts) > 1:
+                torch.cat(parts, out=dst)
+            else:
+                dst.copy_(parts[0].reshape(dst.shape))
+        _lib.check(eng.L.uwcv_ingest(_ptr(h_small), _ptr(d_small), total_b, _stream_ptr(dev)),
+                   "uwcv_ingest")
+        eng.launches += 1
+    return d_boxes, d_scores, d_classes, d_img, d_inst
+
+
+@dataclass
+class _CallInputs:
+    """What one call feeds the kernels, still as per-image parts (host or device tensors)."""
+    boxes: list            # output-space boxes (scaled, clipped, empty ones dropped)
+    scores: list
+    classes: list
+    masks: list            # [n_k, channels * 784] float32
+    image_idx: list
+    inst_idx: list
+    counts: list           # instances per image
+    early: object          # mask copies already under way (_issue_mask_copies), or None
+    d_ok: object           # device flag of the optimistic device-input path, or None
+    logits: bool
+    channels: int
+
+
+def _collect_call_inputs(eng, slot, dev, batch, H, W, output_size, classes_of_interest,
+                         image_idx_offset, pipeline_chunks, no_fast) -> _CallInputs:
+    """detector_postprocess's box handling (scale, clip, drop empty) for every image of the call
+    and the per-instance index columns.  Three paths with the same result: host tensors with one
+    shared image size (one vectorised pass, the mask copies start first), device-resident
+    predictor output (no host synchronisation: validity is a device flag), and the general
+    per-image path (class filter, mixed sizes, ``orig_idx``)."""
     bl, sl, cl, ml, il, jl = [], [], [], [], [], []
     mfields = [_mask_field(inst) for inst in batch]
     logits = mfields[0][1]
@@ -864,7 +960,7 @@ def submit_measure_instances(instances, output_size=None, classes_of_interest=No
         else:
             early = None
     d_ok = None
-    if counts_fast is None and not _no_fast and len(sizes) == 1 and classes_of_interest is None and \
+    if counts_fast is None and not no_fast and len(sizes) == 1 and classes_of_interest is None and \
             all(_as_box_tensor(i.pred_boxes).is_cuda and _as_box_tensor(i.pred_boxes).device == dev
                 for i in batch) and not any(_has(i, "orig_idx") for i in batch):
         # device-resident predictor output (the single-forward path): nothing here may wait for
@@ -908,6 +1004,37 @@ def submit_measure_instances(instances, output_size=None, classes_of_interest=No
             jl.append(oi[keep.cpu()] if nk != keep.numel() else oi)
         else:
             jl.append(torch.arange(nk, dtype=torch.int32))
+    counts = counts_fast if counts_fast is not None else [int(b.shape[0]) for b in bl]
+    return _CallInputs(bl, sl, cl, ml, il, jl, counts, early, d_ok, logits, channels)
+
+
+def submit_measure_instances(instances, output_size=None, classes_of_interest=None, *,
+                             mask_threshold: float = 0.5, pixels_per_metric: float = 0.85,
+                             image_idx_offset: int = 0, return_planes: bool = False,
+                             write_planes: bool = False, gather: bool = False,
+                             gather_counts: Optional[Sequence[int]] = None,
+                             gather_dst: Optional[int] = None, gather_sink: str = "auto",
+                             mask_channel_offset: int = 0,
+                             pipeline_chunks: int = 4, device=None, _exact_words: bool = False,
+                             _slot: int = 0, _no_fast: bool = False) -> PendingTable:
+    """Enqueue one ``measure_instances`` call (same arguments) and return its handle."""
+    single = not isinstance(instances, (list, tuple))
+    batch: List[object] = [instances] if single else list(instances)
+    dev = _require_cuda(device)
+    eng = Engine.get(dev)
+    empty = (MeasurementTable.empty(), None) if return_planes else MeasurementTable.empty()
+    if not batch:
+        return PendingTable.ready(MeasurementTable.empty())
+    H, W = (int(output_size[0]), int(output_size[1])) if output_size is not None else \
+        tuple(int(v) for v in batch[0].image_size)
+    slot = eng.slot(_slot)
+    if slot.pending is not None:            # the slot's previous call has not been collected
+        slot.pending.result()
+
+    inp = _collect_call_inputs(eng, slot, dev, batch, H, W, output_size, classes_of_interest,
+                               image_idx_offset, pipeline_chunks, _no_fast)
+    bl, sl, cl, ml, il, jl = inp.boxes, inp.scores, inp.classes, inp.masks, inp.image_idx, inp.inst_idx
+    early, d_ok, logits, channels = inp.early, inp.d_ok, inp.logits, inp.channels
     boxes = torch.cat(bl)
     n = int(boxes.shape[0])
     gathered = gather and dist_is_multi()
@@ -923,7 +1050,7 @@ def submit_measure_instances(instances, output_size=None, classes_of_interest=No
         n_words = tile_words_bound(boxes)             # (device boxes: one synchronising read, first call only)
     else:
         n_words = eng._cap_words
-    counts = counts_fast if counts_fast is not None else [int(b.shape[0]) for b in bl]
+    counts = inp.counts
     main = torch.cuda.current_stream(dev)
     nb = dict(non_blocking=True)
 
@@ -964,48 +1091,8 @@ def submit_measure_instances(instances, output_size=None, classes_of_interest=No
         else:
             planes = None
         pend.planes = planes if return_planes else None
-        small_parts = (("boxes", [boxes], torch.float32, 4), ("scores", sl, torch.float32, 1),
-                       ("classes", cl, torch.int64, 1), ("img", il, torch.int32, 1),
-                       ("inst", jl, torch.int32, 1))
-        on_device = any(p_.is_cuda for _, parts, _, _ in small_parts for p_ in parts)
-        # one packed buffer for the five small arrays (every segment 256-byte aligned)
-        offs, total_b = {}, 0
-        for name, _parts, dt, width in small_parts:
-            offs[name] = total_b
-            total_b += (n * width * dt.itemsize + 255) // 256 * 256
-        d_small = slot.device("small", (total_b,), torch.uint8)
-
-        def seg(buf, name, dt, width):
-            v = buf[offs[name]: offs[name] + n * width * dt.itemsize].view(dt)
-            return v.view(n, width) if width > 1 else v
-
-        d_boxes, d_scores, d_classes, d_img, d_inst = (seg(d_small, nm, dt, w)
-                                                       for nm, _p, dt, w in small_parts)
-        if on_device:
-            # device-resident inputs: plain device copies behind their producer
-            eng.small_stream.wait_stream(main)
-            with torch.cuda.stream(eng.small_stream):
-                for (name, parts, dt, w), dst in zip(small_parts, (d_boxes, d_scores, d_classes,
-                                                                   d_img, d_inst)):
-                    src = parts[0] if len(parts) == 1 else torch.cat([p_.to(dev) for p_ in parts])
-                    dst.copy_(src.to(dt).reshape(dst.shape), **nb)
-                ev_small = torch.cuda.Event()
-                ev_small.record(eng.small_stream)
-            main.wait_event(ev_small)
-        else:
-            # host inputs: packed into pinned (device-mapped) memory and pulled in by ONE kernel on
-            # the main stream (uwcv_ingest).  The copy engine serves copies in issue order: 1 MB of
-            # boxes queued behind 200 MB of masks would hold the layout back for milliseconds
-            h_small = slot.pinned("small", (total_b,), torch.uint8)
-            for name, parts, dt, w in small_parts:
-                dst = seg(h_small, name, dt, w)
-                if len(parts) > 1:
-                    torch.cat(parts, out=dst)
-                else:
-                    dst.copy_(parts[0].reshape(dst.shape))
-            _lib.check(eng.L.uwcv_ingest(_ptr(h_small), _ptr(d_small), total_b, _stream_ptr(dev)),
-                       "uwcv_ingest")
-            eng.launches += 1
+        d_boxes, d_scores, d_classes, d_img, d_inst = _stage_small_arrays(
+            eng, slot, dev, main, n, boxes, sl, cl, il, jl)
         resume_mask_copies()
         ws = eng._workspace(n, n_words)
         common = dict(image_idx=d_img, inst_idx=d_inst, classes=d_classes, scores=d_scores,
@@ -1033,26 +1120,12 @@ def submit_measure_instances(instances, output_size=None, classes_of_interest=No
         fg = eng.fused_gather() if (gathered and ht is None) else None
         gstruct = gset = None
         if ht is not None:
-            cts = gather_counts
-            if cts is None:
-                import torch.distributed as dist
-                c_l = torch.tensor([n], dtype=torch.int64, device=dev)
-                c_all = torch.empty(ht.world, dtype=torch.int64, device=dev)
-                dist.all_gather_into_tensor(c_all, c_l)
-                cts = c_all.cpu().tolist()
-            hk, hseq, hbase, htotal = ht.begin(cts)
+            hk, hseq, hbase, htotal = ht.begin(_rank_counts(gather_counts, n, ht.world, dev))
         if fg is not None:
             # fused all-gather: the trace kernel stores the rows into every rank's table
             # (symmetric memory over NVLink), a signal barrier completes them -- no collective
             # kernel has to find SMs next to the following call's paste
-            cts = gather_counts
-            if cts is None:
-                import torch.distributed as dist
-                c_l = torch.tensor([n], dtype=torch.int64, device=dev)
-                c_all = torch.empty(fg.world, dtype=torch.int64, device=dev)
-                dist.all_gather_into_tensor(c_all, c_l)
-                cts = c_all.cpu().tolist()
-            gstruct, gset, g_total = fg.begin(cts, dst=gather_dst)
+            gstruct, gset, g_total = fg.begin(_rank_counts(gather_counts, n, fg.world, dev), dst=gather_dst)
         if n > 0:
             rows_done = eng.run_overlapped(
                 d_masks, d_boxes, H, W,
@@ -1082,29 +1155,8 @@ def submit_measure_instances(instances, output_size=None, classes_of_interest=No
             rows_done.record(main)
         out_i, out_f = (out["i"], out["f"]) if (gathered and ht is None) else (rows_i, rows_f)
         if ht is not None:
-            import torch.distributed as dist
-            is_dst = dist.get_rank() == int(gather_dst)
-            hp_s = slot.pinned("status", (4,), torch.int64)
-            with torch.cuda.stream(eng.d2h_stream):
-                eng.d2h_stream.wait_event(rows_done)
-                ht.copy_rows(hk, hseq, hbase, rows_i, rows_f)
-                hp_s.copy_(status, **nb)
-                if d_ok is not None:
-                    pend.hp_ok = slot.pinned("ok", (1,), torch.int64)
-                    pend.hp_ok.copy_(d_ok, **nb)
-                    d_ok.record_stream(eng.d2h_stream)
-                done = torch.cuda.Event()
-                done.record(eng.d2h_stream)
-            lo, hi = (0, htotal) if is_dst else (hbase, hbase + n)
-            pend.np_i, pend.np_f = ht.arrays(hk, hseq, lo, hi, whole=is_dst)
-            if is_dst:
-                pend._after_sync = lambda: ht.wait_all(hk, hseq)
-            pend.n = hi - lo
-            pend.hp_i = pend.hp_f = None
-            pend.hp_s = hp_s
-            pend._done = done
-            slot.pending = pend
-            return pend
+            return _read_back_to_shared_table(eng, slot, pend, ht, (hk, hseq, hbase, htotal), int(gather_dst),
+                                              rows_done, rows_i, rows_f, status, d_ok, n)
         if gathered and gather_dst is not None:
             import torch.distributed as dist
             if dist.get_rank() != int(gather_dst):
@@ -1113,16 +1165,11 @@ def submit_measure_instances(instances, output_size=None, classes_of_interest=No
         # the rows land in pinned memory that the returned table owns (no host copy); the
         # engine recycles the buffer when the table is gone
         hp_i, hp_f, pend.np_i, pend.np_f = eng.host_rows(r)
-        hp_s = slot.pinned("status", (4,), torch.int64)
         with torch.cuda.stream(eng.d2h_stream):
             eng.d2h_stream.wait_event(rows_done)
             hp_i.copy_(out_i, **nb)
             hp_f.copy_(out_f, **nb)
-            hp_s.copy_(status, **nb)
-            if d_ok is not None:
-                pend.hp_ok = slot.pinned("ok", (1,), torch.int64)
-                pend.hp_ok.copy_(d_ok, **nb)
-                d_ok.record_stream(eng.d2h_stream)
+            hp_s = _copy_status(eng, slot, pend, status, d_ok)
             done = torch.cuda.Event()
             done.record(eng.d2h_stream)
         if fg is not None:
