@@ -11,10 +11,11 @@
 // Within a class candidates are visited in (score descending, index ascending) order.
 //
 // Launches for the whole batch:
-//   A  per image: candidates above the score threshold are COMPACTED first (the cost of every
-//      later step follows the survivors, as upstream's "scores > thresh" before batched_nms
-//      does), key = (class, ~orderable(score), index), bitonic sort of the survivors (shared-
-//      memory passes for strides < 4096), gather sorted boxes, class segment table
+//   A  per image: the survivors of the score filter (the cost of every later step follows them,
+//      as upstream's "scores > thresh" before batched_nms does) are bucketed by class
+//      (shared-memory histogram, scan, scatter: the class segment table); per (image, class): the
+//      segment's keys (~orderable(score), index) are sorted by their own CTA, in shared memory
+//      up to 8 192 keys, and the boxes gathered in sorted order
 //   C  per (image, class): greedy sweep over the class segment, 64 candidates per step: the
 //      64 x 64 IoU bits of the step are computed in place, the step's keepers resolved by one
 //      thread in registers, and every later candidate of the segment is tested against those
@@ -29,7 +30,6 @@ namespace uwcv {
 constexpr int kNmsThreads = 1024;
 constexpr int kIdxBits = 18;            // <= 262144 candidates per image
 constexpr int kClsShift = 50;           // key = class << 50 | ~score << 18 | index
-constexpr int kSortChunk = 4096;        // keys per shared-memory sort chunk
 
 struct NmsWorkspace {
   int64_t* off;        // [B + 1] device copy of the per-image candidate offsets
@@ -74,109 +74,117 @@ __device__ __forceinline__ uint32_t orderable(float f) {
   return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
 }
 
-// one bitonic compare-exchange pass with stride j of the stage k on keys[0, count)
-// (global index of keys[0] is `base`; count and base are multiples of 2 j)
-__device__ __forceinline__ void bitonic_pass(uint64_t* keys, int count, int base, int k, int j,
-                                             int tid) {
-  for (int t = tid; t < count / 2; t += kNmsThreads) {
-    const int i = ((t / j) * 2 * j) + (t % j);          // lower element of the pair
-    const int p = i + j;
-    const uint64_t a = keys[i], c = keys[p];
-    const bool asc = ((base + i) & k) == 0;
-    if ((a > c) == asc) { keys[i] = c; keys[p] = a; }
-  }
+// ---- A: filter + class buckets (per image), then one sort per (image, class) ------------------
+// key of a candidate: class << 50 | ~orderable(score) << 18 | index.  The survivors of the score
+// filter are counted per class (shared-memory histogram), the class segments laid out by an
+// exclusive scan, and the keys scattered into their segment (unordered); every segment is then
+// sorted by its own CTA -- the serial depth of the sort follows the largest class, not the image,
+// and the sorts of all classes and images run side by side.
+constexpr int kMaxClasses = 8192;
+constexpr int kSegSortSmem = 8192;       // keys sorted entirely in shared memory (64 KB)
+
+__device__ __forceinline__ bool nms_key_of(const float* __restrict__ boxes, const float* __restrict__ scores,
+                                           const int64_t* __restrict__ cls, int64_t lo, int i, float score_thr,
+                                           int C, uint64_t& key, int& c_out) {
+  const float s = scores[lo + i];
+  const float4 bx = reinterpret_cast<const float4*>(boxes)[lo + i];
+  const long long c = cls[lo + i];
+  const bool fin = isfinite(bx.x) && isfinite(bx.y) && isfinite(bx.z) && isfinite(bx.w) && isfinite(s);
+  if (!(fin && s > score_thr && c >= 0 && c < C)) return false;
+  key = ((uint64_t)c << kClsShift) | ((uint64_t)(~orderable(s)) << kIdxBits) | (uint32_t)i;
+  c_out = (int)c;
+  return true;
 }
 
-// ---- A: filter + sort + class segments --------------------------------------------------
 __global__ void __launch_bounds__(kNmsThreads)
-nms_sort_kernel(const float* __restrict__ boxes, const float* __restrict__ scores,
-                const int64_t* __restrict__ cls, float score_thr, int C, NmsWorkspace w) {
-  __shared__ uint64_t s_keys[kSortChunk];
-  __shared__ int s_count;
+nms_bucket_kernel(const float* __restrict__ boxes, const float* __restrict__ scores,
+                  const int64_t* __restrict__ cls, float score_thr, int C, NmsWorkspace w) {
+  __shared__ int s_hist[kMaxClasses];      // count per class, then the scatter cursor
+  __shared__ int s_part[kNmsThreads];
   const int b = blockIdx.x, tid = threadIdx.x;
   const int64_t lo = w.off[b];
   const int n = (int)(w.off[b + 1] - lo);
   uint64_t* keys = w.keys + 2 * lo + b;
-  if (tid == 0) s_count = 0;
-  for (int k = tid; k < C; k += kNmsThreads) {
-    w.seg[((int64_t)b * C + k) * 2] = 0;
-    w.seg[((int64_t)b * C + k) * 2 + 1] = 0;
-    w.ccount[(int64_t)b * C + k] = 0;
+  for (int k = tid; k < C; k += kNmsThreads) { s_hist[k] = 0; w.ccount[(int64_t)b * C + k] = 0; }
+  __syncthreads();
+  for (int i = tid; i < n; i += kNmsThreads) {
+    uint64_t key; int c;
+    if (nms_key_of(boxes, scores, cls, lo, i, score_thr, C, key, c)) atomicAdd(&s_hist[c], 1);
   }
   __syncthreads();
-  // score filter first: the survivors are appended (warp-aggregated) to keys[0, nv); the order
-  // of the appends does not matter, the sort below fixes it
-  for (int i0 = 0; i0 < n; i0 += kNmsThreads) {
-    const int i = i0 + tid;
-    uint64_t k = ~0ull;
-    bool ok = false;
-    if (i < n) {
-      const float s = scores[lo + i];
-      const float4 bx = reinterpret_cast<const float4*>(boxes)[lo + i];
-      const long long c = cls[lo + i];
-      const bool fin = isfinite(bx.x) && isfinite(bx.y) && isfinite(bx.z) && isfinite(bx.w) &&
-                       isfinite(s);
-      if (fin && s > score_thr && c >= 0 && c < C) {
-        k = ((uint64_t)c << kClsShift) | ((uint64_t)(~orderable(s)) << kIdxBits) | (uint32_t)i;
-        ok = true;
-      }
-    }
-    const unsigned m = __ballot_sync(0xffffffffu, ok);
-    int base = 0;
-    if ((tid & 31) == 0 && m) base = atomicAdd(&s_count, __popc(m));
-    base = __shfl_sync(0xffffffffu, base, 0);
-    if (ok) keys[base + __popc(m & ((1u << (tid & 31)) - 1u))] = k;
-  }
+  // exclusive scan over the classes: thread t owns classes [t * per, (t + 1) * per)
+  const int per = (C + kNmsThreads - 1) / kNmsThreads;
+  int mine = 0;
+  for (int k = tid * per; k < min(C, (tid + 1) * per); ++k) mine += s_hist[k];
+  s_part[tid] = mine;
   __syncthreads();
-  const int nvalid_ = s_count;
+  for (int off = 1; off < kNmsThreads; off <<= 1) {
+    int v = 0;
+    if (tid >= off) v = s_part[tid - off];
+    __syncthreads();
+    s_part[tid] += v;
+    __syncthreads();
+  }
+  int run = s_part[tid] - mine;
+  for (int k = tid * per; k < min(C, (tid + 1) * per); ++k) {
+    const int cnt = s_hist[k];
+    w.seg[((int64_t)b * C + k) * 2] = cnt ? run : 0;
+    w.seg[((int64_t)b * C + k) * 2 + 1] = cnt ? run + cnt : 0;
+    s_hist[k] = run;                                   // from now on: the class's scatter cursor
+    run += cnt;
+  }
+  if (tid == kNmsThreads - 1) w.nvalid[b] = s_part[kNmsThreads - 1];
+  __syncthreads();
+  for (int i = tid; i < n; i += kNmsThreads) {
+    uint64_t key; int c;
+    if (nms_key_of(boxes, scores, cls, lo, i, score_thr, C, key, c)) keys[atomicAdd(&s_hist[c], 1)] = key;
+  }
+}
+
+// Bitonic network for ANY length m (no padding stored): the first pass of every stage pairs i with
+// i ^ (k - 1), the following ones with i ^ j, all comparisons ascending; partners >= m are skipped.
+__device__ __forceinline__ void bitonic_any(uint64_t* keys, int m, int tid, int nthreads) {
   int P = 1;
-  while (P < nvalid_) P <<= 1;
-  for (int i = nvalid_ + tid; i < P; i += kNmsThreads) keys[i] = ~0ull;      // padding sorts last
-  __syncthreads();
-  // stages k <= chunk: every chunk is sorted entirely in shared memory
-  const int chunk = P < kSortChunk ? P : kSortChunk;
-  if (chunk >= 2) {
-    for (int c0 = 0; c0 < P; c0 += chunk) {
-      for (int i = tid; i < chunk; i += kNmsThreads) s_keys[i] = keys[c0 + i];
-      __syncthreads();
-      for (int k = 2; k <= chunk; k <<= 1)
-        for (int j = k >> 1; j > 0; j >>= 1) {
-          bitonic_pass(s_keys, chunk, c0, k, j, tid);
-          __syncthreads();
+  while (P < m) P <<= 1;
+  for (int k = 2; k <= P; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      const bool first = j == (k >> 1);
+      for (int i = tid; i < m; i += nthreads) {
+        const int l = first ? (i ^ (k - 1)) : (i ^ j);
+        if (l > i && l < m) {
+          const uint64_t a = keys[i], c = keys[l];
+          if (a > c) { keys[i] = c; keys[l] = a; }
         }
-      for (int i = tid; i < chunk; i += kNmsThreads) keys[c0 + i] = s_keys[i];
+      }
       __syncthreads();
-    }
-    // stages k > chunk: strides >= chunk in global memory, the rest per chunk in shared memory
-    for (int k = 2 * chunk; k <= P; k <<= 1) {
-      for (int j = k >> 1; j >= chunk; j >>= 1) {
-        bitonic_pass(keys, P, 0, k, j, tid);
-        __syncthreads();
-      }
-      for (int c0 = 0; c0 < P; c0 += chunk) {
-        for (int i = tid; i < chunk; i += kNmsThreads) s_keys[i] = keys[c0 + i];
-        __syncthreads();
-        for (int j = chunk >> 1; j > 0; j >>= 1) {
-          bitonic_pass(s_keys, chunk, c0, k, j, tid);
-          __syncthreads();
-        }
-        for (int i = tid; i < chunk; i += kNmsThreads) keys[c0 + i] = s_keys[i];
-        __syncthreads();
-      }
     }
   }
-  const int nv = s_count;
-  if (tid == 0) w.nvalid[b] = nv;
-  for (int r = tid; r < nv; r += kNmsThreads) {
-    const uint64_t key = keys[r];
+}
+
+__global__ void __launch_bounds__(kNmsThreads)
+nms_segment_sort_kernel(const float* __restrict__ boxes, int C, NmsWorkspace w) {
+  extern __shared__ uint64_t s_sort[];
+  const int b = blockIdx.y, cls = blockIdx.x, tid = threadIdx.x;
+  const int s = w.seg[((int64_t)b * C + cls) * 2], e = w.seg[((int64_t)b * C + cls) * 2 + 1];
+  const int m = e - s;
+  if (m <= 0) return;
+  const int64_t lo = w.off[b];
+  uint64_t* keys = w.keys + 2 * lo + b + s;
+  if (m <= kSegSortSmem) {
+    for (int i = tid; i < m; i += kNmsThreads) s_sort[i] = keys[i];
+    __syncthreads();
+    bitonic_any(s_sort, m, tid, kNmsThreads);
+    for (int i = tid; i < m; i += kNmsThreads) keys[i] = s_sort[i];
+  } else {
+    __syncthreads();
+    bitonic_any(keys, m, tid, kNmsThreads);            // (a class with more than 8 192 survivors)
+  }
+  __syncthreads();
+  for (int r = tid; r < m; r += kNmsThreads) {
+    const uint64_t key = m <= kSegSortSmem ? s_sort[r] : keys[r];
     const int li = (int)(key & ((1u << kIdxBits) - 1u));
-    const int c = (int)(key >> kClsShift);
-    w.sbox[lo + r] = reinterpret_cast<const float4*>(boxes)[lo + li];
-    w.scls[lo + r] = c;
-    const int cp = r > 0 ? (int)(keys[r - 1] >> kClsShift) : -1;
-    const int cn = r + 1 < nv ? (int)(keys[r + 1] >> kClsShift) : -1;
-    if (cp != c) w.seg[((int64_t)b * C + c) * 2] = r;
-    if (cn != c) w.seg[((int64_t)b * C + c) * 2 + 1] = r + 1;
+    w.sbox[lo + s + r] = reinterpret_cast<const float4*>(boxes)[lo + li];
+    w.scls[lo + s + r] = cls;
   }
 }
 
@@ -283,22 +291,59 @@ nms_sweep_kernel(int topk, int C, double iou_thr, NmsWorkspace w) {
 }
 
 // ---- D: merge the per-class keep lists by score, top-k -------------------------------------
+// The non-empty classes of the image (count, first kept slot, prefix of the counts) are staged in
+// shared memory; one thread per kept box: its rank in the global score order is its rank in its own
+// class plus, for every other non-empty class, the number of that class's kept boxes that precede
+// it (binary search in the class's keep list, which is in score order).
+constexpr int kMergeClasses = 2048;      // non-empty classes staged in shared memory
+
 __global__ void __launch_bounds__(kNmsThreads)
 nms_merge_kernel(int topk, int C, NmsWorkspace w, int64_t* __restrict__ keep,
                  int32_t* __restrict__ keep_count) {
+  __shared__ int s_cnt[kMergeClasses], s_seg[kMergeClasses], s_pre[kMergeClasses + 1];
+  __shared__ int s_ne, s_total;
   const int b = blockIdx.x, tid = threadIdx.x;
   const int64_t lo = w.off[b];
   const uint64_t* keys = w.keys + 2 * lo + b;
   const uint64_t kScoreMask = (1ull << kClsShift) - 1ull;      // (~score, index): global order
-  __shared__ int s_total;
-  if (tid == 0) {
-    int t = 0;
-    for (int k = 0; k < C; ++k) t += w.ccount[(int64_t)b * C + k];
-    s_total = t;
-    keep_count[b] = t < topk ? t : topk;
+  if (tid == 0) {                                              // compact the non-empty classes
+    int ne = 0, tot = 0;
+    for (int k = 0; k < C; ++k) {
+      const int c = w.ccount[(int64_t)b * C + k];
+      if (!c) continue;
+      if (ne < kMergeClasses) { s_cnt[ne] = c; s_seg[ne] = w.seg[((int64_t)b * C + k) * 2]; s_pre[ne] = tot; }
+      ++ne; tot += c;
+    }
+    s_ne = ne; s_total = tot;
+    if (ne <= kMergeClasses) s_pre[ne] = tot;
+    keep_count[b] = tot < topk ? tot : topk;
   }
   __syncthreads();
-  if (s_total == 0) return;
+  const int ne = s_ne, total = s_total;
+  if (total == 0) return;
+  if (ne <= kMergeClasses) {
+    for (int q = tid; q < total; q += kNmsThreads) {
+      int a = 0, z = ne;                                       // class slot of kept box q: s_pre[e] <= q
+      while (z - a > 1) { const int m = (a + z) >> 1; if (s_pre[m] <= q) a = m; else z = m; }
+      const int e = a, j = q - s_pre[e];
+      const uint64_t key = keys[w.ckeep[lo + s_seg[e] + j]];
+      const uint64_t mine = key & kScoreMask;
+      int rank = j;
+      for (int e2 = 0; e2 < ne; ++e2) {
+        if (e2 == e) continue;
+        const int s2 = s_seg[e2];
+        int x = 0, y = s_cnt[e2];                              // lower bound of `mine` in class e2
+        while (x < y) {
+          const int mid = (x + y) >> 1;
+          if ((keys[w.ckeep[lo + s2 + mid]] & kScoreMask) < mine) x = mid + 1; else y = mid;
+        }
+        rank += x;
+      }
+      if (rank < topk) keep[lo + rank] = lo + (int64_t)(key & ((1u << kIdxBits) - 1u));
+    }
+    return;
+  }
+  // more non-empty classes than the staging area holds: the same ranking straight from global memory
   for (int k = 0; k < C; ++k) {
     const int cnt = w.ccount[(int64_t)b * C + k];
     const int s = w.seg[((int64_t)b * C + k) * 2];
@@ -311,7 +356,7 @@ nms_merge_kernel(int topk, int C, NmsWorkspace w, int64_t* __restrict__ keep,
         const int cnt2 = w.ccount[(int64_t)b * C + k2];
         if (!cnt2) continue;
         const int s2 = w.seg[((int64_t)b * C + k2) * 2];
-        int a = 0, z = cnt2;                               // lower bound of `mine` in class k2
+        int a = 0, z = cnt2;
         while (a < z) {
           const int mid = (a + z) >> 1;
           if ((keys[w.ckeep[lo + s2 + mid]] & kScoreMask) < mine) a = mid + 1; else z = mid;
@@ -348,9 +393,12 @@ cudaError_t launch_nms(const float* boxes, const float* scores, const int64_t* c
     for (int k = 0; k < 32; ++k) c.v[k] = k < cnt ? image_off_host[f + k] : 0;
     nms_set_offsets_kernel<<<1, 32, 0, stream>>>(w.off, f, cnt, c);
   }
-  nms_sort_kernel<<<B, kNmsThreads, 0, stream>>>(boxes, scores, cls, score_thr, C, w);
+  nms_bucket_kernel<<<B, kNmsThreads, 0, stream>>>(boxes, scores, cls, score_thr, C, w);
   if (R > 0) {
     dim3 sgrid((unsigned)C, (unsigned)B);
+    cudaFuncSetAttribute(nms_segment_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         kSegSortSmem * (int)sizeof(uint64_t));
+    nms_segment_sort_kernel<<<sgrid, kNmsThreads, kSegSortSmem * sizeof(uint64_t), stream>>>(boxes, C, w);
     int64_t maxn = 0;
     for (int b = 0; b < B; ++b) {
       const int64_t nb = image_off_host[b + 1] - image_off_host[b];

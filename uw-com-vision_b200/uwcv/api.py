@@ -475,7 +475,7 @@ class Engine:
                                         _ptr(keep), _ptr(cnt), _ptr(ws), ws.numel(),
                                         _stream_ptr(dev))
         _lib.check(rc, "uwcv_nms_filter")
-        self.launches += (B + 32) // 32 + (3 if R > 0 else 2)    # offsets, sort, sweep, merge
+        self.launches += (B + 32) // 32 + (4 if R > 0 else 2)    # offsets, buckets, segment sorts, sweep, merge
         return keep, cnt
 
 

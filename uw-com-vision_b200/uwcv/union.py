@@ -66,7 +66,8 @@ def measure_union(instances, output_size: Optional[Tuple[int, int]] = None,
     for k, inst in enumerate(batch):
         boxes, _scores, _classes, masks = _gather_fields(inst, classes_of_interest)
         b, keep = scale_clip_boxes(boxes, inst.image_size, (H, W))
-        b, masks = b[keep], masks[keep]
+        if not bool(keep.all()):                       # (dropping nothing: no copy of the masks)
+            b, masks = b[keep], masks[keep]
         bl.append(b.cpu())
         ml.append(masks.to(torch.float32).reshape(-1, MASK_SIDE, MASK_SIDE).cpu())
         il.append(torch.full((int(b.shape[0]),), image_idx_offset + k, dtype=torch.int32))
@@ -79,7 +80,14 @@ def measure_union(instances, output_size: Optional[Tuple[int, int]] = None,
     st = _stream_ptr(dev)
     with torch.cuda.device(dev):
         d_boxes = boxes.contiguous().to(dev)
-        d_masks = torch.cat(ml).contiguous().to(dev)
+        # the masks are concatenated straight into pinned memory (one host copy) and DMA'd from there
+        slot = eng.slot(0)
+        if slot.pending is not None:
+            slot.pending.result()
+        h_masks = slot.pinned("masks", (n, MASK_SIDE, MASK_SIDE), torch.float32)
+        torch.cat(ml, out=h_masks)
+        d_masks = slot.device("masks", (n, MASK_SIDE, MASK_SIDE), torch.float32)
+        d_masks.copy_(h_masks, non_blocking=True)
         d_img = torch.cat(il).to(dev)
         rows_i = torch.empty((n, NUM_INT), dtype=torch.int64, device=dev)
         rows_f = torch.empty((n, NUM_FLOAT), dtype=torch.float64, device=dev)
