@@ -191,6 +191,10 @@ class FusedGather:
         return ti, tf
 
 
+class SharedTableUnavailable(RuntimeError):
+    """Raised on EVERY rank together when the node-shared table cannot be created or grown."""
+
+
 class SharedHostTable:
     """The whole job's measurement table in ONE block of host memory shared by the ranks of a
     node: every rank copies its OWN rows (device -> host, 400 B per instance) to its row offset
@@ -243,6 +247,17 @@ class SharedHostTable:
         name = [f"/dev/shm/uwcv_table_{os.getuid()}_{os.getpid()}_{self.gen}"]
         dist.broadcast_object_list(name, src=dist.get_global_rank(self.group, 0), group=self.group)
         path = name[0]
+        # a segment that does not fit into /dev/shm would only fail when its pages are touched
+        # (SIGBUS): every rank checks the free space first and all ranks give up together
+        try:
+            st = os.statvfs("/dev/shm")
+            room = st.f_bavail * st.f_frsize >= nbytes + (64 << 20)
+        except OSError:
+            room = False
+        ok = torch.tensor([1 if room else 0], dtype=torch.int32, device=self.device)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.group)
+        if int(ok.item()) == 0:
+            raise SharedTableUnavailable(f"/dev/shm has no room for a {nbytes >> 20} MiB shared table")
         if self.rank == 0:
             fd = os.open(path, os.O_CREAT | os.O_RDWR | os.O_EXCL, 0o600)
             os.ftruncate(fd, nbytes)
@@ -261,7 +276,7 @@ class SharedHostTable:
         dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.group)      # all ranks or none
         if int(ok.item()) == 0:
             self._close()
-            raise RuntimeError(f"cudaHostRegister of the shared table failed on some rank (here: {rc})")
+            raise SharedTableUnavailable(f"cudaHostRegister of the shared table failed on some rank (here: {rc})")
         self.cap = cap
         self.hdr = self.buf[: self.HEADER].view(torch.int64)
         self.hdr_np = self.hdr.numpy()
