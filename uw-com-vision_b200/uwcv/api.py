@@ -1117,10 +1117,19 @@ def submit_measure_instances(instances, output_size=None, classes_of_interest=No
             ht = eng.host_table()
             if ht is None and gather_sink == "host":
                 raise RuntimeError("uwcv: the shared host table is not available for this group")
+        if ht is not None:
+            from .dist import SharedTableUnavailable
+            try:
+                hk, hseq, hbase, htotal = ht.begin(_rank_counts(gather_counts, n, ht.world, dev))
+            except SharedTableUnavailable as e:       # (raised by all ranks together)
+                if gather_sink == "host":
+                    raise
+                import warnings
+                warnings.warn(f"uwcv: {e}; gathering on the devices")
+                eng._host_table = False
+                ht = None
         fg = eng.fused_gather() if (gathered and ht is None) else None
         gstruct = gset = None
-        if ht is not None:
-            hk, hseq, hbase, htotal = ht.begin(_rank_counts(gather_counts, n, ht.world, dev))
         if fg is not None:
             # fused all-gather: the trace kernel stores the rows into every rank's table
             # (symmetric memory over NVLink), a signal barrier completes them -- no collective
