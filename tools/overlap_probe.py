@@ -1,10 +1,14 @@
 """Probe: border trace of step i on a second stream under the paste kernel of step i + 1
 (double-buffered workspace and row tables) vs the serial step.  Env knobs: UWCV_FILL=2 (evict-first
-zero rows), UWCV_PASTE_CTAS."""
+zero rows), UWCV_PASTE_CTAS -- read by the tuning library only: python tools/overlap_probe.py tuning."""
 import os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "uw-com-vision_b200"))
-import torch, uwcv
+import torch
+from uwcv import _lib
+if len(sys.argv) > 1:
+    _lib.use_library_variant(sys.argv[1])
+import uwcv
 from uwcv import api, synth
 H = W = 2048
 dev = torch.device("cuda", 0)
