@@ -101,6 +101,14 @@ int uwcv_paste_measure(const float* masks, const float* boxes, const int32_t* im
  * 2 = paste + threshold + bit-pack + raw moments, 4 = border trace + descriptors.
  * Stages must be issued in that order on one stream with identical arguments;
  * uwcv_paste_measure is stages = 7.
+ *
+ * Split pipeline: with bit 16 set stage 2 writes the tiles and the integer rows only (as with
+ * bitplanes == NULL) and stage 8 writes the full-frame bit-planes FROM THE TILES with a kernel
+ * that only moves data (96 threads, ~30 registers per CTA; csrc/plane_fill.cu).  Stages 8 and 4
+ * both depend on stage 2 only, so a caller may issue 1 | 2 | 16 on one stream and, behind an
+ * event, 8 and 4 on two others: the HBM-bound plane fill then shares the SMs with the border
+ * trace of the same call and the tile arithmetic of the next one.  Same planes, same rows
+ * (Detectron2 paste_masks_in_image, reached from nn_inference.py:372).
  */
 int uwcv_paste_measure_stages(const float* masks, const float* boxes, const int32_t* image_idx,
                               const int32_t* inst_idx, const int64_t* classes,

@@ -22,6 +22,8 @@ ap.add_argument("--instances", type=int, default=1000)
 ap.add_argument("--steps", type=int, default=10)
 ap.add_argument("--size", type=int, default=2048)
 ap.add_argument("--no-planes", action="store_true")
+ap.add_argument("--check-split", action="store_true", help="planes / rows of the split pipeline == fused kernel")
+ap.add_argument("--timeline", default="", help="write the CUPTI kernel timeline of 6 split steps to this file")
 a = ap.parse_args()
 from uwcv import _lib  # noqa: E402
 if a.variant:
@@ -70,25 +72,63 @@ assert int(eng.status.cpu()[0]) == 0
 for name, st in (("layout", 1), ("paste", 2), ("trace", 4), ("serial_step", 7)):
     res[name] = timed(lambda: eng.run(d_masks, d_boxes, H, W, rows_i=rows[0][0], rows_f=rows[0][1],
                                       stages=st, **kw), max(3, a.steps))
+if planes is not None:
+    for name, st in (("tile_rows_only", 2 | 16), ("plane_fill", 8 | 16), ("serial_split_step", 1 | 2 | 16 | 8 | 4)):
+        res[name] = timed(lambda: eng.run(d_masks, d_boxes, H, W, rows_i=rows[0][0], rows_f=rows[0][1],
+                                          stages=st, **kw), max(3, a.steps))
 tick = [0]
 
 
-def ostep():
+def ostep(split):
     k = tick[0] & 1
     tick[0] += 1
-    eng.run_overlapped(d_masks, d_boxes, H, W, rows_i=rows[k][0], rows_f=rows[k][1], status=stat[k], **kw)
+    eng.run_overlapped(d_masks, d_boxes, H, W, rows_i=rows[k][0], rows_f=rows[k][1], status=stat[k],
+                       split=split, **kw)
 
 
-for _ in range(3):
-    ostep()
-torch.cuda.synchronize()
-e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-e0.record()
-for _ in range(a.steps):
-    ostep()
-main.wait_stream(eng.trace_stream)
-e1.record(); e1.synchronize()
-res["overlapped_step"] = e0.elapsed_time(e1) / a.steps
+for split in ((False, True) if planes is not None else (False,)):
+    for _ in range(3):
+        ostep(split)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(a.steps):
+        ostep(split)
+    main.wait_stream(eng.trace_stream)
+    main.wait_stream(eng.fill_stream)
+    e1.record(); e1.synchronize()
+    res["overlapped_split_step" if split else "overlapped_step"] = e0.elapsed_time(e1) / a.steps
+    res["rows_checksum_split" if split else "rows_checksum_fused"] = [
+        int(rows[0][0].sum().item()), float(rows[0][1].nan_to_num().sum().item()),
+        int(rows[1][0].sum().item()), float(rows[1][1].nan_to_num().sum().item())]
+if a.check_split and planes is not None:
+    ref_i, ref_f = rows[0][0].clone(), rows[0][1].clone()
+    eng.run(d_masks, d_boxes, H, W, rows_i=ref_i, rows_f=ref_f, **kw)          # fused kernel
+    torch.cuda.synchronize()
+    ref_planes = planes.clone()
+    planes.fill_(-1)
+    ostep(True); ostep(True)
+    torch.cuda.synchronize()
+    res["split_planes_equal"] = bool(torch.equal(ref_planes, planes))
+    res["split_rows_equal"] = bool(torch.equal(ref_i, rows[0][0]) and torch.equal(ref_i, rows[1][0]) and
+                                   torch.equal(ref_f.nan_to_num(), rows[0][1].nan_to_num()) and
+                                   torch.equal(ref_f.nan_to_num(), rows[1][1].nan_to_num()))
+    del ref_planes
+if a.timeline and planes is not None:
+    from torch.profiler import profile, ProfilerActivity
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        for _ in range(6):
+            ostep(True)
+        torch.cuda.synchronize()
+    tmp = a.timeline + ".chrome.json"
+    prof.export_chrome_trace(tmp)
+    ev = [e for e in json.load(open(tmp))["traceEvents"] if e.get("cat") in ("kernel", "gpu_memset") and "ts" in e]
+    ev.sort(key=lambda e: e["ts"])
+    with open(a.timeline, "w") as f:
+        for e in ev:
+            f.write(f"{(e['ts'] - ev[0]['ts']) / 1e3:9.3f} ms  +{e['dur'] / 1e3:7.3f} ms  stream {e.get('args', {}).get('stream')}  "
+                    f"{e['name'].split('(')[0][-44:]}\n")
+    os.remove(tmp)
 if a.variant.startswith("tuning"):
     import ctypes as C
     L = _lib.lib()

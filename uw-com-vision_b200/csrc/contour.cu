@@ -179,13 +179,17 @@ contour_measure_kernel(int64_t first, int64_t n, int lanes, const float* __restr
 cudaError_t launch_contour_measure(int64_t first, int64_t count, const float* scores, double ppm,
                                    int64_t* rows_i, double* rows_f, const Workspace& ws,
                                    const int64_t* status, int num_sms, cudaStream_t stream,
-                                   const GatherDst& gather) {
+                                   const GatherDst& gather, int reserve_ctas) {
   if (count == 0) return cudaSuccess;
   const int64_t n = count;                               // sizing below is per launched range
   int per_sm = 0;
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, contour_measure_kernel,
                                                     kContourThreads, 0) != cudaSuccess || per_sm < 1)
     per_sm = 8;
+  // split pipeline: the plane-fill CTAs of the same call are resident beside this kernel; keep the
+  // trace grid within ONE wave of what is left (a second wave starts behind the shortest warps
+  // and ends a whole serial chain later)
+  if (reserve_ctas > 0 && per_sm > reserve_ctas + 1) per_sm -= reserve_ctas;
   // as many warps as can be resident at once, each carrying ceil(n / warps) instances
   const int64_t resident_warps = (int64_t)num_sms * per_sm * (kContourThreads / 32);
   int lanes = (int)((n + resident_warps - 1) / resident_warps);

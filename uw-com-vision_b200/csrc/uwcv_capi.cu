@@ -11,7 +11,9 @@ cudaError_t launch_paste_measure(const float*, const float*, const int32_t*, con
                                  const MaskSource&);
 cudaError_t launch_contour_measure(int64_t, int64_t, const float*, double, int64_t*, double*,
                                    const Workspace&, const int64_t*, int, cudaStream_t,
-                                   const GatherDst&);
+                                   const GatherDst&, int);
+cudaError_t launch_plane_fill(uint32_t*, int64_t, int64_t, int, int, const Workspace&, const int64_t*, int,
+                              cudaStream_t);
 cudaError_t launch_unpack(const uint32_t*, int64_t, int, int, uint8_t*, int, cudaStream_t);
 cudaError_t launch_ingest(const void*, void*, size_t, cudaStream_t);
 size_t nms_workspace_bytes_host(const int64_t*, int, int);
@@ -149,12 +151,21 @@ int uwcv_paste_measure_gather(const float* masks, int mask_channels, int channel
   src.logits = is_logits ? 1 : 0;
   if ((stages & 1) && uwcv::launch_layout(boxes, N, H, W, ws, status, num_sms(), st) != cudaSuccess)
     return UWCV_E_LAUNCH;
+  // split pipeline (stage bit 16): the paste writes tiles and integer rows only, the planes are
+  // written from the tiles by stage 8 (plane_fill.cu), which a caller may issue on another stream
+  const bool split = (stages & 16) != 0;
+  if ((stages & 8) && !bitplanes) return UWCV_E_NULL;
   if ((stages & 2) &&
       uwcv::launch_paste_measure(masks, boxes, image_idx, inst_idx, classes, first, count, H, W,
-                                 thr, bitplanes, rows_i, ws, status, num_sms(), st, src) != cudaSuccess)
+                                 thr, split ? nullptr : bitplanes, rows_i, ws, status, num_sms(), st,
+                                 src) != cudaSuccess)
+    return UWCV_E_LAUNCH;
+  if ((stages & 8) &&
+      uwcv::launch_plane_fill(bitplanes, first, count, H, W, ws, status, num_sms(), st) != cudaSuccess)
     return UWCV_E_LAUNCH;
   if ((stages & 4) && uwcv::launch_contour_measure(first, count, scores, pixels_per_metric, rows_i,
-                                                   rows_f, ws, status, num_sms(), st, gd) != cudaSuccess)
+                                                   rows_f, ws, status, num_sms(), st, gd,
+                                                   split ? 1 : 0) != cudaSuccess)
     return UWCV_E_LAUNCH;
   return UWCV_OK;
 }

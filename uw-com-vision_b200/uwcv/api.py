@@ -231,7 +231,15 @@ class Engine:
         # idle) tail overlaps the (HBM-bound) paste of call i + 1: two workspaces, used in turn
         self.trace_stream = torch.cuda.Stream(device, priority=-1)   # its CTAs go first when SMs free up
         self._trace_done = [None, None]
+        # split pipeline: the planes are written from the tiles by a data-movement kernel on its
+        # own stream (csrc/plane_fill.cu) beside the trace of the same call and the tile kernel of
+        # the next one; its CTAs are placed first when an SM has room
+        self.fill_stream = torch.cuda.Stream(device, priority=-2)
+        self._fill_done = [None, None]
+        self.planes_done = None      # event behind the last plane fill (split pipeline)
+        self.fill_events = None      # list: (start, end) timing events of every plane fill are appended
         self._parity = 0
+        self.split_default = True
         self._slots = {}
         self._host_pool = []
         self._fused = None
@@ -378,6 +386,9 @@ class Engine:
             # the layout is about to hand this workspace out again: after the trace that reads it
             torch.cuda.current_stream(dev).wait_event(self._trace_done[ws_slot])
             self._trace_done[ws_slot] = None
+        if (stages & 1) and self._fill_done[ws_slot] is not None:
+            torch.cuda.current_stream(dev).wait_event(self._fill_done[ws_slot])   # ... and the plane fill
+            self._fill_done[ws_slot] = None
         with torch.cuda.device(dev):
             rc = self.L.uwcv_paste_measure_gather(
                 _ptr(masks), int(mask_channels), int(channel_offset), int(bool(logits)), _ptr(boxes), _ptr(image_idx), _ptr(inst_idx), _ptr(classes),
@@ -387,16 +398,21 @@ class Engine:
                 int(n - first if count is None else count),
                 C.byref(gather) if (gather is not None and (stages & 4)) else None)
         _lib.check(rc, "uwcv_paste_measure")
-        if n > 0:        # layout = 3 kernels, paste = 1 (rows only: 2), contour = 1
-            self.launches += 3 * (stages & 1) + ((stages >> 1) & 1) * (1 if planes is not None else 2) \
-                + ((stages >> 2) & 1)
+        if n > 0:        # layout = 3 kernels, paste = 1 (rows only / split: 2), contour = 1, plane fill = 1
+            self.launches += 3 * (stages & 1) \
+                + ((stages >> 1) & 1) * (1 if (planes is not None and not (stages & 16)) else 2) \
+                + ((stages >> 2) & 1) + ((stages >> 3) & 1)
         return rows_i, rows_f, status
 
-    def run_overlapped(self, masks, boxes, H, W, *, paste_ranges=None, after=None, **kw):
+    def run_overlapped(self, masks, boxes, H, W, *, paste_ranges=None, after=None, split=None, **kw):
         """Layout + paste on the current stream, border trace on ``trace_stream``, alternating
         between the two workspaces.  ``paste_ranges``: [(first, count, event or None), ...] --
         the paste of a range waits for its event (chunks of a host->device copy in flight).
         ``after``: callable run on the trace stream behind the trace (collectives, D2H hand-off).
+        ``split`` (default: whenever planes are written): the paste writes tiles and integer rows
+        only (compute-bound) and the planes are written from the tiles on ``fill_stream`` by a
+        kernel that only moves data, so the HBM-bound fill shares the SMs with the trace of this
+        call and the tile kernel of the next; ``self.planes_done`` is the event behind the fill.
         Returns the event that marks the rows complete."""
         dev = self.device
         main = torch.cuda.current_stream(dev)
@@ -404,17 +420,39 @@ class Engine:
         self._parity ^= 1
         n = int(boxes.shape[0])
         kw = dict(kw, ws_slot=p)
+        if split is None:
+            split = self.split_default
+        split = bool(split) and kw.get("planes") is not None
+        sbit = 16 if split else 0
         self.run(masks, boxes, H, W, stages=1, **kw)
         for first, count, ev in (paste_ranges or [(0, n, None)]):
             if ev is not None:
                 main.wait_event(ev)
             if count > 0:
-                self.run(masks, boxes, H, W, stages=2, first=first, count=count, **kw)
+                self.run(masks, boxes, H, W, stages=2 | sbit, first=first, count=count, **kw)
+                if split:
+                    tiles = torch.cuda.Event()
+                    tiles.record(main)
+                    with torch.cuda.stream(self.fill_stream):
+                        self.fill_stream.wait_event(tiles)
+                        if self.fill_events is not None:       # (bench: live time of the fill inside the pipeline)
+                            t0 = torch.cuda.Event(enable_timing=True)
+                            t0.record(self.fill_stream)
+                        self.run(masks, boxes, H, W, stages=8 | sbit, first=first, count=count, **kw)
+                        if self.fill_events is not None:
+                            t1 = torch.cuda.Event(enable_timing=True)
+                            t1.record(self.fill_stream)
+                            self.fill_events.append((t0, t1))
         pasted = torch.cuda.Event()
         pasted.record(main)
+        if split:
+            fd = torch.cuda.Event()
+            fd.record(self.fill_stream)
+            self._fill_done[p] = fd
+            self.planes_done = fd
         with torch.cuda.stream(self.trace_stream):
             self.trace_stream.wait_event(pasted)
-            self.run(masks, boxes, H, W, stages=4, **kw)
+            self.run(masks, boxes, H, W, stages=4 | sbit, **kw)
             if after is not None:
                 after()
             done = torch.cuda.Event()
@@ -435,6 +473,8 @@ class Engine:
         need = n * H * wpr
         buf = getattr(self, "_planes", None)
         if buf is None or buf.numel() < need:
+            if buf is not None:
+                self.fill_stream.synchronize()        # a plane fill may still be writing the old buffer
             self._planes = None
             self._planes = buf = torch.empty(need, dtype=torch.int32, device=self.device)
         return buf[:need].view(n, H, wpr)
@@ -671,6 +711,7 @@ class PendingTable:
         self.n = 0
         self.planes = None
         self.return_planes = False
+        self._planes_done = None
         self.hp_i = self.hp_f = self.hp_s = self.np_i = self.np_f = None
 
     @staticmethod
@@ -683,6 +724,9 @@ class PendingTable:
         if self._value is not None:
             return self._value[0]
         self._done.synchronize()
+        if self._planes_done is not None:              # split pipeline: the fill has its own stream
+            self._planes_done.synchronize()
+            self._planes_done = None
         if self._after_sync is not None:
             self._after_sync()
             self._after_sync = None
@@ -1141,6 +1185,8 @@ def submit_measure_instances(instances, output_size=None, classes_of_interest=No
                 paste_ranges=[(lo, hi - lo, ev_in[c]) for c, (i0, i1, lo, hi) in enumerate(bounds)],
                 gather=gstruct, after=(lambda: fg.barrier(gset)) if fg is not None else None,
                 **common)
+            if planes is not None and eng.planes_done is not None:
+                pend._planes_done = eng.planes_done
         else:
             status.zero_()
             with torch.cuda.stream(eng.trace_stream):
