@@ -877,3 +877,59 @@ def test_shared_host_table_on_one_gpu():
     assert p.exitcode == 0
     assert ok, "rows read back from the shared table differ"
     assert blocked, "reusing a set whose table is still referenced must raise"
+
+
+def test_split_pipeline_equals_fused_kernel():
+    """Stage 8 (planes written from the tiles by plane_fill_kernel, on its own stream) against the
+    fused paste kernel of the single-stream call: identical planes and rows -- bands taller than the
+    shared-memory band image (chunked), frame-sized and empty tiles, W not a multiple of 32,
+    instance ranges, both workspaces of Engine.run_overlapped."""
+    dev = torch.device("cuda", 0)
+    eng = api.Engine.get(dev)
+    g = torch.Generator().manual_seed(77)
+    for (H, W, n) in ((300, 4000, 90), (144, 208, 300), (64, 33, 40)):
+        cx = torch.rand(n, generator=g) * (W + 20) - 10
+        cy = torch.rand(n, generator=g) * (H + 20) - 10
+        w = torch.exp(torch.rand(n, generator=g) * 8 - 2).clamp(max=2.0 * W)
+        h = torch.exp(torch.rand(n, generator=g) * 8 - 2).clamp(max=2.0 * H)
+        boxes = torch.stack([cx - w / 2, cy - h / 2, cx + w / 2, cy + h / 2], 1)
+        boxes[0] = torch.tensor([0., 0., float(W), float(H)])            # whole frame: the tallest band
+        boxes[1] = torch.tensor([5., 5., 5., 40.])                       # zero width: empty tile
+        boxes[2] = torch.tensor([W - 3.5, 0., float(W), float(H)])       # right edge, full height
+        boxes[:, 0::2] = boxes[:, 0::2].clamp(0, W)
+        boxes[:, 1::2] = boxes[:, 1::2].clamp(0, H)
+        masks = torch.rand(n, 28, 28, generator=g)
+        masks[0] = 1.0
+        masks[::6] = (masks[::6] > 0.5).float()
+        d_b, d_m = boxes.contiguous().to(dev), masks.contiguous().to(dev)
+        words = api.tile_words(boxes, H, W)
+        sc = torch.rand(n, generator=g).to(dev)
+
+        def fresh():
+            return (eng.alloc_planes(n, H, W).fill_(-1), torch.empty((n, 20), dtype=torch.int64, device=dev),
+                    torch.empty((n, 30), dtype=torch.float64, device=dev))
+
+        p0, i0, f0 = fresh()
+        eng.run(d_m, d_b, H, W, planes=p0, rows_i=i0, rows_f=f0, scores=sc, n_tile_words=words)   # fused, stages = 7
+        torch.cuda.synchronize()
+        assert int(eng.status.cpu()[0]) == 0
+        # (a) the split stages on one stream
+        p1, i1, f1 = fresh()
+        eng.run(d_m, d_b, H, W, planes=p1, rows_i=i1, rows_f=f1, scores=sc, n_tile_words=words,
+                stages=1 | 2 | 16 | 8 | 4)
+        torch.cuda.synchronize()
+        assert torch.equal(p1, p0) and torch.equal(i1, i0) and torch.equal(f1.nan_to_num(), f0.nan_to_num())
+        # (b) three streams, instance ranges, both workspaces in turn
+        third = n // 3
+        ranges = [(0, third, None), (third, third, None), (2 * third, n - 2 * third, None)]
+        for rep in range(2):
+            p2, i2, f2 = fresh()
+            eng.run_overlapped(d_m, d_b, H, W, planes=p2, rows_i=i2, rows_f=f2, scores=sc, n_tile_words=words,
+                               paste_ranges=ranges if rep else None, split=True)
+            assert eng.planes_done is not None
+            torch.cuda.synchronize()
+            assert torch.equal(p2, p0), (H, W, rep)
+            assert torch.equal(i2, i0) and torch.equal(f2.nan_to_num(), f0.nan_to_num())
+        # the planes are the Detectron2-literal masks
+        ref = d2.paste_masks_in_image(masks, boxes, (H, W))
+        assert torch.equal(eng.unpack(p2, H, W).cpu(), ref)
