@@ -214,11 +214,6 @@ static __device__ int last_mark_before(const TileView& t, int wi, int y) {
 // prefetched) or by one border step; the largest external contour (by |area|, the raster-first
 // one on ties) and its per-row extremes are kept.  Used lane-per-instance by the stand-alone
 // trace kernel (GlobalMem) and by the tracer warp of the paste kernel (SharedMem).
-#ifdef UWCV_NOEXT                       // (tuning probe: no per-row extremes -- wrong hulls, timing only)
-constexpr bool kTraceExt = false;
-#else
-constexpr bool kTraceExt = true;
-#endif
 template <class Mem>
 struct LaneTracer {
   enum { kScan = 0, kTrace = 1, kDone = 2 };
@@ -310,14 +305,14 @@ struct LaneTracer {
         }
         if (start) {
           sy = cy_;
-          trace_begin<true, kTraceExt, Mem>(t, tr, cwi * 32 + b, cy_, cur, cur + estride);
+          trace_begin<true, true, Mem>(t, tr, cwi * 32 + b, cy_, cur, cur + estride);
           if (tr.active) state = kTrace; else finished = true;
         } else {
           fresh = true;
         }
       }
     } else if (state == kTrace) {
-      trace_step<true, kTraceExt, Mem>(t, tr, cur, cur + estride);
+      trace_step<true, true, Mem>(t, tr, cur, cur + estride);
       if (!tr.active) { finished = true; state = kScan; }
     }
     if (finished) {
