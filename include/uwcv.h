@@ -32,6 +32,13 @@ extern "C" {
 #define UWCV_NUM_INT   20   /* int64 columns of a measurement row   */
 #define UWCV_NUM_FLOAT 30   /* float64 columns of a measurement row */
 
+/* stage bits of uwcv_paste_measure_stages / _range / _heads / _gather */
+#define UWCV_STAGE_LAYOUT  1   /* tile geometry + offsets, marks cleared                              */
+#define UWCV_STAGE_PASTE   2   /* paste + threshold + bit-pack + raw moments (+ planes, fused)        */
+#define UWCV_STAGE_TRACE   4   /* border trace + descriptors + float columns (+ fused gather)         */
+#define UWCV_STAGE_PLANES  8   /* full-frame planes written from the tiles (split pipeline)           */
+#define UWCV_STAGE_SPLIT  16   /* modifier: stage 2 leaves the planes to stage 8                      */
+
 #define UWCV_OK            0
 #define UWCV_E_NULL       -1  /* required pointer is NULL                         */
 #define UWCV_E_SHAPE      -2  /* negative / zero / inconsistent sizes             */

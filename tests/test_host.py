@@ -52,6 +52,10 @@ def test_argument_validation_without_gpu():
     assert _lib.strerror(-7).startswith("tile words")
     assert L.uwcv_unpack_planes(None, 1, 8, 8, None, None) == -1
     assert L.uwcv_unpack_planes(None, 0, 8, 8, None, None) == 0
+    # split pipeline: stage 8 (planes from the tiles) without a plane buffer is refused before any launch
+    fake = 4096                                          # non-NULL, 16-byte aligned, never dereferenced
+    assert L.uwcv_paste_measure_stages(fake, fake, None, None, None, None, 1, 8, 8, 0.5, 0.85, None, fake, fake,
+                                       fake, 1 << 20, C.addressof(st), None, 8 | 16) == -1
     off = (C.c_int64 * 2)(0, -5)
     assert L.uwcv_nms_filter(None, None, None, off, 1, 4, 0.5, 0.5, 10, None, C.addressof(st), None, 0, None) == -2
     off = (C.c_int64 * 2)(1, 5)

@@ -139,6 +139,7 @@ int uwcv_paste_measure_gather(const float* masks, int mask_channels, int channel
                                                                               : UWCV_E_LAUNCH;
   }
   if (!masks || !boxes || !rows_i || !rows_f || !workspace) return UWCV_E_NULL;
+  if ((stages & UWCV_STAGE_PLANES) && !bitplanes) return UWCV_E_NULL;     // nothing to write the planes into
   if (misaligned(masks) || misaligned(boxes) || misaligned(rows_i) || misaligned(rows_f) ||
       misaligned(workspace) || misaligned(status) || (bitplanes && misaligned(bitplanes)))
     return UWCV_E_ALIGN;
@@ -154,7 +155,6 @@ int uwcv_paste_measure_gather(const float* masks, int mask_channels, int channel
   // split pipeline (stage bit 16): the paste writes tiles and integer rows only, the planes are
   // written from the tiles by stage 8 (plane_fill.cu), which a caller may issue on another stream
   const bool split = (stages & 16) != 0;
-  if ((stages & 8) && !bitplanes) return UWCV_E_NULL;
   if ((stages & 2) &&
       uwcv::launch_paste_measure(masks, boxes, image_idx, inst_idx, classes, first, count, H, W,
                                  thr, split ? nullptr : bitplanes, rows_i, ws, status, num_sms(), st,
