@@ -129,15 +129,5 @@ if a.timeline and planes is not None:
             f.write(f"{(e['ts'] - ev[0]['ts']) / 1e3:9.3f} ms  +{e['dur'] / 1e3:7.3f} ms  stream {e.get('args', {}).get('stream')}  "
                     f"{e['name'].split('(')[0][-44:]}\n")
     os.remove(tmp)
-if a.variant.startswith("tuning"):
-    import ctypes as C
-    L = _lib.lib()
-    buf = (C.c_ulonglong * 4)()
-    L.uwcv_tuning_fused_stats(buf, 1)
-    eng.run(d_masks, d_boxes, H, W, rows_i=rows[0][0], rows_f=rows[0][1], **kw)
-    torch.cuda.synchronize()
-    L.uwcv_tuning_fused_stats(buf, 1)
-    res["fused_stats_one_step"] = dict(alloc_retries=buf[0], tracer_idle_polls=buf[1], tracer_warp_iters=buf[2],
-                                       tracer_lane_steps=buf[3])
 res["checksum"] = [int(rows[0][0].sum().item()), float(rows[0][1].nan_to_num().sum().item())]
 print(json.dumps(res))

@@ -96,14 +96,8 @@ contour_measure_kernel(int64_t first, int64_t n, int lanes, const float* __restr
   }
 
   // ---- raster scan + border following; keep the largest contour and its row extremes ---
-  // Instances whose tile was traced by the tracer warps of the paste kernel (from shared
-  // memory, under the HBM-bound plane fill) arrive with their result in ws.rec and their
-  // extremes in the first extremes set; everything else (rows-only contract, tiles too large
-  // for a shared-memory slot) is traced here, lane per instance: each iteration of the
-  // warp-uniform loop advances a lane by one 64-pixel scan step or one border step
-  // (LaneTracer), so no lane waits for another lane's contour.
-  const int pre_ncont = live ? ws.rec[inst].ncont : kNotTraced;
-  const bool pre = pre_ncont != kNotTraced;
+  // Lane per instance: each iteration of the warp-uniform loop advances a lane by one 64-pixel
+  // scan step or one border step (LaneTracer), so no lane waits for another lane's contour.
   TileView t;
   t.M = ws.M + d.word_off; t.V = ws.V + d.word_off; t.G = ws.G + d.word_off;
   t.tw = d.tw; t.th = d.th;
@@ -116,7 +110,7 @@ contour_measure_kernel(int64_t first, int64_t n, int lanes, const float* __restr
   LaneTracer<GlobalMem> T;
   T.idle();
   // rows outside the pixel bbox cannot hold a start pixel
-  if (work && !pre) T.begin(t, ext0, ext0 + 2 * d.th, d.th, (int)ri[I_BY0] - d.y0, (int)ri[I_BY1] - d.y0);
+  if (work) T.begin(t, ext0, ext0 + 2 * d.th, d.th, (int)ri[I_BY0] - d.y0, (int)ri[I_BY1] - d.y0);
 #ifdef UWCV_TUNING
   int st_scan = 0, st_trace = 0, st_iter = 0, st_end = 0;
 #endif
@@ -129,17 +123,11 @@ contour_measure_kernel(int64_t first, int64_t n, int lanes, const float* __restr
 #endif
     if (!T.done()) T.step();
   }
-  int ncont = T.ncont, best_npts = T.best_npts, best_y = T.best_y, best_ymax = T.best_ymax;
-  long long best_a2 = T.best_a2;
-  double best_perim = T.best_perim;
+  const int ncont = T.ncont, best_npts = T.best_npts, best_y = T.best_y, best_ymax = T.best_ymax;
+  const long long best_a2 = T.best_a2;
+  const double best_perim = T.best_perim;
   uint32_t* best = T.best;
-  if (pre) {
-    const TraceRec rec = ws.rec[inst];
-    ncont = rec.ncont; best_npts = rec.npts; best_y = rec.best_y; best_ymax = rec.best_ymax;
-    best_a2 = rec.a2; best_perim = rec.perim; best = ext0;
-  } else if (work) {
-    ri[I_NCONT] = ncont; ri[I_NPTS] = best_npts;
-  }
+  if (work) { ri[I_NCONT] = ncont; ri[I_NPTS] = best_npts; }
   const bool have = work && ncont > 0;
 #ifdef UWCV_TUNING
   if (g_trace_stats && live) {

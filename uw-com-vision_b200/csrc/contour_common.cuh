@@ -14,10 +14,9 @@ struct TileView {
   int tw, th;
 };
 
-// Where a tile (mask bits, marks, per-row extremes) lives.  GlobalMem: the tile workspace in HBM /
-// L2 (stand-alone trace kernel, union mode).  SharedMem: a slot of the paste kernel's shared-memory
-// arena, owned by ONE tracer lane (fused trace): plain ld.shared, result-less red.shared -- the
-// serial chain of a border walk then waits ~30 cycles per load instead of an L2 / DRAM round trip.
+// Where a tile (mask bits, marks, per-row extremes) lives, as a policy of the trace code.  GlobalMem:
+// the tile workspace in HBM / L2.  (Round 2 also ran the walk on a shared-memory arena inside the
+// paste kernel through a second policy; it lost -- profiles/r02_fused_trace_sweep.txt -- and is gone.)
 struct GlobalMem {
   static __device__ __forceinline__ uint32_t ldm(const uint32_t* p) { return __ldg(p); }   // mask bits: read-only
   static __device__ __forceinline__ uint32_t ld(const uint32_t* p) { return *p; }
@@ -28,29 +27,6 @@ struct GlobalMem {
   static __device__ __forceinline__ void min_(uint32_t* p, uint32_t v) { atomicMin(p, v); }
   static __device__ __forceinline__ void max_(uint32_t* p, uint32_t v) { atomicMax(p, v); }
 };
-struct SharedMem {
-  static __device__ __forceinline__ uint32_t sa(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-  static __device__ __forceinline__ uint32_t ldm(const uint32_t* p) { return ld(p); }
-  static __device__ __forceinline__ uint32_t ldc(const uint32_t* p) { return ld(p); }
-  static __device__ __forceinline__ uint32_t ld(const uint32_t* p) {
-    uint32_t v;
-    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(sa(p)) : "memory");
-    return v;
-  }
-  static __device__ __forceinline__ void st(uint32_t* p, uint32_t v) {
-    asm volatile("st.shared.u32 [%0], %1;" :: "r"(sa(p)), "r"(v) : "memory");
-  }
-  static __device__ __forceinline__ void or_(uint32_t* p, uint32_t v) {
-    asm volatile("red.shared.or.b32 [%0], %1;" :: "r"(sa(p)), "r"(v) : "memory");
-  }
-  static __device__ __forceinline__ void min_(uint32_t* p, uint32_t v) {
-    asm volatile("red.shared.min.u32 [%0], %1;" :: "r"(sa(p)), "r"(v) : "memory");
-  }
-  static __device__ __forceinline__ void max_(uint32_t* p, uint32_t v) {
-    asm volatile("red.shared.max.u32 [%0], %1;" :: "r"(sa(p)), "r"(v) : "memory");
-  }
-};
-
 // direction s: 0 = east, then counter-clockwise on a y-up plane (1 = x+1, y-1 on screen)
 __device__ __forceinline__ int dir_dx(int s) { return (int)((0x901Au >> (2 * s)) & 3u) - 1; }
 __device__ __forceinline__ int dir_dy(int s) { return (int)((0xA901u >> (2 * s)) & 3u) - 1; }
@@ -329,69 +305,6 @@ struct LaneTracer {
     }
   }
 };
-
-// One instance traced by a WHOLE WARP: lane 0 walks the borders (the serial part, LaneTracer);
-// the warp does the part of the raster scan that is parallel -- between two rows it looks, 32
-// rows at a time, for the next row holding a pixel that really starts an external border
-// (unvisited, background on its left, last mark on its left not positive), so lane 0 never steps
-// through rows without one.  Same results as the lane-per-instance loop (rejecting a candidate
-// has no side effect, so skipping rows whose candidates are all rejected changes nothing).
-// T is meaningful in lane 0 only.  Used by the experimental tracer warps of the paste kernel
-// (tuning build).  As a stand-alone kernel for small batches (a warp per instance, global memory)
-// it was measured SLOWER than a lane per instance (configs[0]: 8.8 vs 5.8 ms; the row search
-// costs an L2 round trip per word and is repeated for every row of a speckled mask) and removed.
-template <class Mem>
-__device__ __forceinline__ void warp_trace(const TileView& tv, uint32_t* ext_a, uint32_t* ext_b,
-                                           int estride, int ylo, int yhi, LaneTracer<Mem>& T, int lane) {
-  typedef LaneTracer<Mem> LT;
-  if (lane == 0) T.begin(tv, ext_a, ext_b, estride, ylo, yhi);
-  for (;;) {
-    int ffy = -1;
-    if (lane == 0 && T.state == LT::kScan && T.fresh && T.wi == 0 && T.y <= T.yhi) ffy = T.y;
-    ffy = __shfl_sync(kFull, ffy, 0);
-    if (ffy >= 0) {
-      __syncwarp();                                    // lane 0's marks are visible to the warp
-      int found = yhi + 1;
-      for (int yb = ffy; yb <= yhi; yb += 32) {
-        const int yy = yb + lane;
-        bool hit = false;
-        if (yy <= yhi) {
-          const uint32_t* mrow = tv.M + yy * tv.tw;
-          const uint32_t* vrow = tv.V + yy * tv.tw;
-          const uint32_t* grow = tv.G + yy * tv.tw;
-          uint32_t carry = 0;
-          int last_sign = 0;                           // sign of the last marked pixel in the words before
-          for (int w = 0; w < tv.tw && !hit; ++w) {
-            const uint32_t m = Mem::ldm(mrow + w);
-            const uint32_t v = Mem::ldc(vrow + w);
-            uint32_t cand = m & ~((m << 1) | carry) & ~v;
-            carry = m >> 31;
-            uint32_t g = 0;
-            if (cand || v) g = Mem::ldc(grow + w);
-            while (cand) {
-              const int bpos = __ffs(cand) - 1;
-              cand &= cand - 1;
-              const uint32_t below = v & ((1u << bpos) - 1u);
-              int sgn = last_sign;
-              if (below) sgn = ((g >> (31 - __clz(below))) & 1u) ? -1 : +1;
-              if (sgn <= 0) { hit = true; break; }
-            }
-            if (v) last_sign = ((g >> (31 - __clz(v))) & 1u) ? -1 : +1;
-          }
-        }
-        const unsigned bm = __ballot_sync(kFull, hit);
-        if (bm) { found = yb + __ffs(bm) - 1; break; }
-      }
-      if (lane == 0 && found != ffy) {
-        T.y = found;                                   // (carry = 0, wi = 0 at a row start)
-        T.m_next = (found <= T.yhi) ? T.load_pair_m(found, 0) : 0ull;
-      }
-    }
-    // serial part: one scan step (inside a row that holds a start) or one border step
-    if (lane == 0 && !T.done()) T.step();
-    if (__shfl_sync(kFull, T.done() ? 1 : 0, 0)) break;
-  }
-}
 
 __device__ __forceinline__ uint32_t pk(int x, int y) { return (uint32_t)x | ((uint32_t)y << 16); }
 __device__ __forceinline__ int pkx(uint32_t p) { return (int)(p & 0xffffu); }

@@ -75,8 +75,8 @@ __device__ __forceinline__ void block_scan2(int64_t& a, int64_t& b, int64_t& tot
 // pass A: one instance per thread -- geometry, CTA-local exclusive offsets, CTA totals
 __global__ void __launch_bounds__(kLayoutThreads)
 layout_local_kernel(const float* __restrict__ boxes, int64_t n, int H, int W,
-                    TileDesc* __restrict__ desc, TraceRec* __restrict__ rec,
-                    int64_t* __restrict__ block_sums, int64_t* __restrict__ big_tiles) {
+                    TileDesc* __restrict__ desc, int64_t* __restrict__ block_sums,
+                    int64_t* __restrict__ big_tiles) {
   __shared__ int64_t s_words[kLayoutThreads];
   __shared__ int64_t s_rows[kLayoutThreads];
   const int64_t i = (int64_t)blockIdx.x * kLayoutThreads + threadIdx.x;
@@ -89,9 +89,6 @@ layout_local_kernel(const float* __restrict__ boxes, int64_t n, int H, int W,
     d.wx0 = wx0; d.y0 = y0; d.tw = tw; d.th = th;
     d.word_off = words; d.row_off = rows;
     desc[i] = d;
-    TraceRec r;                                      // nobody has traced this instance yet
-    r.a2 = -1; r.perim = 0.0; r.best_y = 0; r.best_ymax = -1; r.npts = 0; r.ncont = kNotTraced;
-    rec[i] = r;
   }
   if (threadIdx.x == 0) {
     block_sums[2 * blockIdx.x] = tw_total;
@@ -212,8 +209,7 @@ template <bool kPlanes>
 __device__ __forceinline__ void paste_rows(const TileDesc& d, int rbase, const float* __restrict__ mk,
                                            float bx0, float by0, float bx1, float by1, float thr,
                                            int W, int wpr, uint32_t* __restrict__ plane,
-                                           uint32_t* __restrict__ tM, uint32_t* __restrict__ sM,
-                                           int lane, TileAcc& a) {
+                                           uint32_t* __restrict__ tM, int lane, TileAcc& a) {
   int rowb; float rn, rs;
   axis_coord(d.y0 + rbase + lane, by0, by1, rowb, rn, rs);
   rowb *= kMaskPitch;
@@ -250,7 +246,6 @@ __device__ __forceinline__ void paste_rows(const TileDesc& d, int rbase, const f
       UWCV_BOUND(o, (int64_t)d.tw * d.th);
       UWCV_BOUND(d.y0 + rbase + lane, 32768); UWCV_BOUND(d.wx0 + strip, wpr);
       tM[o] = myword;
-      if (sM) sM[o] = myword;                          // shared-memory copy for the tracer warp
       if (kPlanes) plane[(int64_t)(d.y0 + rbase + lane) * wpr + d.wx0 + strip] = myword;
       if (myword) { a.ymin = min(a.ymin, d.y0 + rbase + lane); a.ymax = max(a.ymax, d.y0 + rbase + lane); }
     }
@@ -289,45 +284,8 @@ __device__ __forceinline__ void stage_mask(const float* __restrict__ masks, cons
   }
 }
 
-// ---- fused border trace (EXPERIMENT, -DUWCV_TUNING builds only; measured slower, r02) -----
-// The paste kernel is bound by the HBM write path: its issue slots are ~15 % busy and the bit
-// tile of an instance sits in shared memory the moment it has been pasted.  The stand-alone
-// trace kernel, on the other hand, walks every border as a serial chain of dependent L2 / DRAM
-// round trips (1.6 ms per 64 000 instances, ~1.1 ms of it exposed).  So the trace rides inside
-// the paste kernel (kFused): the compute warps leave a copy of the tile (mask bits + zeroed mark
-// planes + room for two extremes sets) in a slot of a shared-memory arena and publish it on a
-// small queue; one extra warp per CTA -- the tracer warp, a lane per slot -- runs the same
-// scan / border-following state machine (LaneTracer) on shared memory (ld.shared, result-less
-// red.shared), writes the result record + the best contour's extremes to the workspace and
-// frees the slot.  The descriptor kernel afterwards only builds hulls / rectangles.
-#ifndef UWCV_TRACER_WARPS
-#define UWCV_TRACER_WARPS 2
-#endif
-constexpr int kTracerWarps = UWCV_TRACER_WARPS;
-#ifdef UWCV_TUNING
-// [0] page-allocation retries of the compute warps, [1] idle polls of the tracer warps,
-// [2] tracer warp iterations, [3] tracer lane steps
-__device__ unsigned long long g_fused_stats[4] = {0, 0, 0, 0};
-#endif
-constexpr int kFusedThreads = kPasteThreads + 32 * kTracerWarps;      // 288
-constexpr int kArenaPages = 16;
-constexpr int kPageWords = 832;                       // 3 328 B; a median tile (3 x 60 words) takes one page
-constexpr int kArenaBytes = kArenaPages * kPageWords * 4;             // 53 248 B
-constexpr int kQueue = 16;                            // >= slots that can exist at once
-
-struct SlotEntry {
-  long long inst;
-  long long row_off;
-  int tw, th, ylo, yhi;                               // scan rows (tile coordinates)
-  int page0, npages;
-};
-
-__device__ __forceinline__ int slot_pages(int tw, int th) {
-  return (3 * tw * th + 4 * th + kPageWords - 1) / kPageWords;
-}
-
-template <bool kPlanes, bool kFused>
-__global__ void __launch_bounds__(kFused ? kFusedThreads : kPasteThreads, kFused ? 2 : 3)
+template <bool kPlanes>
+__global__ void __launch_bounds__(kPasteThreads, 3)
 paste_measure_kernel(const float* __restrict__ masks, const float* __restrict__ boxes,
                      const int32_t* __restrict__ image_idx, const int32_t* __restrict__ inst_idx,
                      const int64_t* __restrict__ classes, int64_t n, int H, int W, float thr,
@@ -335,18 +293,12 @@ paste_measure_kernel(const float* __restrict__ masks, const float* __restrict__ 
                      Workspace ws, const int64_t* __restrict__ status, int zero_bytes,
                      int rot_mul, int fill_mode, int debug_skip, int64_t first, MaskSource src,
                      int only_big, int band_bytes_cap, const int32_t* __restrict__ order) {
-  extern __shared__ __align__(128) unsigned char s_zero[];     // zero_bytes + band buffer + trace arena (planes only)
+  extern __shared__ __align__(128) unsigned char s_zero[];     // zero_bytes + band buffer (planes only)
   __shared__ __align__(16) float s_mask[kMaskPitch * kMaskPitch];
   __shared__ unsigned long long s_acc[10];
   __shared__ int s_bbox[4];
   __shared__ long long s_next[2];
-  __shared__ SlotEntry s_q[kQueue];
-  __shared__ unsigned int s_pages;                  // bit p: arena page p is in use
-  __shared__ volatile int s_qtail;                  // entries published by the compute warps
-  __shared__ unsigned int s_qticket;                // entries handed to tracer warps
-  __shared__ volatile int s_cdone;                  // the compute warps have left their loop
-  __shared__ int s_slot;                            // first page of the current instance's slot (-1: none)
-  constexpr int kThreads = kFused ? kFusedThreads : kPasteThreads;
+  constexpr int kThreads = kPasteThreads;
 
   if (status[0] != 0) return;                       // layout overflowed the workspace
   if (only_big && status[3] == 0) return;           // nothing left for the whole-CTA pass
@@ -365,10 +317,8 @@ paste_measure_kernel(const float* __restrict__ masks, const float* __restrict__ 
     fence_proxy_async_smem();                       // generic-proxy zeros -> visible to TMA
   }
   uint32_t* s_band = reinterpret_cast<uint32_t*>(s_zero + zero_bytes);
-  uint32_t* s_arena = reinterpret_cast<uint32_t*>(s_zero + zero_bytes + band_bytes_cap);
   // the frame of the padded mask stays zero for the whole kernel
   for (int k = tid; k < kMaskPitch * kMaskPitch; k += kThreads) s_mask[k] = 0.f;
-  if (tid == 0) { s_pages = 0u; s_qtail = 0; s_qticket = 0u; s_cdone = 0; s_slot = -1; }
   __syncthreads();
   const uint32_t zero_smem = (uint32_t)__cvta_generic_to_shared(s_zero);
 
@@ -416,87 +366,12 @@ paste_measure_kernel(const float* __restrict__ masks, const float* __restrict__ 
       }
       bulk_wait_read_all();                            // the zero source must outlive the copies
     }
-  } else if (kFused && warp > kPasteWarps) {
-    // ---- tracer warps: one published slot per warp at a time ---------------------------------
-    // Lane 0 walks the borders (the serial part: LaneTracer on shared memory); the whole warp
-    // does the part of the raster scan that is parallel -- between two rows it looks, 32 rows
-    // at a time, for the next row holding a pixel that really starts an external border
-    // (unvisited, background on its left, last mark on its left not positive), so lane 0 never
-    // steps through rows without one.  Slots are taken in publication order by ticket.
-    typedef LaneTracer<SharedMem> LT;
-    LT T;
-    T.idle();
-#ifdef UWCV_TUNING
-    unsigned long long st_iters = 0, st_ff = 0, st_idle = 0;
-#endif
-    for (;;) {
-#ifdef UWCV_TUNING
-      ++st_iters;                                      // (slots taken)
-#endif
-      int ticket = 0;
-      if (lane == 0) ticket = (int)atomicAdd(&s_qticket, 1u);
-      ticket = __shfl_sync(kFull, ticket, 0);
-      bool quit = false;
-      for (;;) {
-        if (s_qtail > ticket) break;
-        if (s_cdone && s_qtail <= ticket) { quit = true; break; }
-#ifdef UWCV_TUNING
-        ++st_idle;
-#endif
-        __nanosleep(2000);
-      }
-      if (quit) break;
-      __threadfence_block();                           // the entry / slot contents behind the tail
-      const SlotEntry e = s_q[ticket % kQueue];
-      uint32_t* base = s_arena + e.page0 * kPageWords;
-      const int words = e.tw * e.th;
-      TileView tv;
-      tv.M = base; tv.V = base + words; tv.G = base + 2 * words; tv.tw = e.tw; tv.th = e.th;
-      uint32_t* ext = base + 3 * words;
-      warp_trace<SharedMem>(tv, ext, ext + 2 * e.th, e.th, e.ylo, e.yhi, T, lane);
-      // completion: extremes of the best contour -> workspace (whole warp), record, slot freed
-      if (lane == 0) __threadfence_block();            // its red.shared marks / extremes are performed
-      __syncwarp();
-      const int nc = __shfl_sync(kFull, T.ncont, 0);
-      if (nc > 0) {
-        const uint32_t bsa = __shfl_sync(kFull, SharedMem::sa(T.best), 0);
-        const int by = __shfl_sync(kFull, T.best_y, 0), bym = __shfl_sync(kFull, T.best_ymax, 0);
-        uint32_t* gl = ws.scratch + 4 * e.row_off;
-        for (int r = by + lane; r <= bym; r += 32) {
-          uint32_t l, rr;
-          asm volatile("ld.shared.u32 %0, [%1];" : "=r"(l) : "r"(bsa + 4u * r) : "memory");
-          asm volatile("ld.shared.u32 %0, [%1];" : "=r"(rr) : "r"(bsa + 4u * (e.th + r)) : "memory");
-          gl[r] = l;
-          gl[e.th + r] = rr;
-        }
-      }
-      __syncwarp();                                    // every lane has read the slot being freed
-      if (lane == 0) {
-        TraceRec r;
-        r.a2 = T.best_a2; r.perim = T.best_perim; r.best_y = T.best_y; r.best_ymax = T.best_ymax;
-        r.npts = T.best_npts; r.ncont = T.ncont;
-        ws.rec[e.inst] = r;
-        rows_i[e.inst * kNumInt + I_NCONT] = T.ncont;
-        rows_i[e.inst * kNumInt + I_NPTS] = T.best_npts;
-        atomicAnd(&s_pages, ~(((1u << e.npages) - 1u) << e.page0));
-      }
-    }
-#ifdef UWCV_TUNING
-    if (lane == 0) {
-      atomicAdd(&g_fused_stats[1], st_idle); atomicAdd(&g_fused_stats[2], st_iters);
-      atomicAdd(&g_fused_stats[3], st_ff);
-    }
-#endif
   } else {
 
   auto claim_next = [&]() -> long long {
     const long long k = (long long)atomicAdd(&ws.sched[1], 1u);
     return (order && first + k < n) ? (long long)order[first + k] : first + k;
   };
-  int qtail = 0;                                       // tid 0's private copy of s_qtail
-#ifdef UWCV_TUNING
-  unsigned long long st_retry = 0;
-#endif
   if (tid == 0) s_next[0] = claim_next();
   compute_barrier();
   for (int it = 0;; ++it) {
@@ -515,29 +390,6 @@ paste_measure_kernel(const float* __restrict__ masks, const float* __restrict__ 
     const float bx0 = boxes[4 * inst + 0], by0 = boxes[4 * inst + 1];
     const float bx1 = boxes[4 * inst + 2], by1 = boxes[4 * inst + 3];
     uint32_t* plane = kPlanes ? planes + inst * plane_words : nullptr;
-    // a slot of the trace arena for this tile: the only allocator is this thread, the tracer
-    // lanes only free, so a failed search is simply repeated until a trace has finished
-    const int npages = slot_pages(d.tw, d.th);
-    if (kFused && tid == 0) {
-      int p0 = -1;
-      if (d.th > 0 && npages <= kArenaPages && !(debug_skip & 4)) {    // (4: tuning, tracer off)
-        const unsigned m = (npages >= 32) ? 0xffffffffu : ((1u << npages) - 1u);
-        for (;;) {
-          const unsigned used = *(volatile unsigned int*)&s_pages;
-          for (int p = 0; p + npages <= kArenaPages; ++p)
-            if (!(used & (m << p))) { p0 = p; break; }
-          if (p0 >= 0) break;
-#ifdef UWCV_TUNING
-          ++st_retry;
-#endif
-          if (debug_skip & 8) break;                   // (8: tuning) no wait: the stand-alone kernel traces it
-          __nanosleep(200);
-        }
-        if (p0 >= 0) atomicOr(&s_pages, m << p0);
-      }
-      s_slot = p0;
-    }
-
     // fill_mode 1 (profiling): zero rows by 16-byte LSU stores from the compute warps
     if (kPlanes && fill_mode == 1) {
       const int band_lo = d.th > 0 ? d.y0 : H;
@@ -571,18 +423,12 @@ paste_measure_kernel(const float* __restrict__ masks, const float* __restrict__ 
     UWCV_BOUND(d.y0 + d.th, H + 1); UWCV_BOUND(d.wx0 + d.tw, wpr + 1);
     if (band_tma) UWCV_BOUND((int64_t)d.th * wpr * 4, (int64_t)band_bytes_cap + 1);
     uint32_t* tM = ws.M + d.word_off;
-    uint32_t* sM = nullptr;                            // the slot: mask bits | visited | sign | extremes
-    if (kFused && s_slot >= 0) {
-      sM = s_arena + s_slot * kPageWords;
-      const int words = d.tw * d.th;
-      for (int k = tid; k < 2 * words; k += kComputeThreads) sM[words + k] = 0u;   // marks start clear
-    }
 
     TileAcc ta;
     for (int g = warp; g * 32 < d.th && !(debug_skip & 1); g += kPasteWarps)
       paste_rows<kPlanes>(d, g * 32, s_mask, bx0, by0, bx1, by1, thr, W, wpr,
                           // band composed in shared memory: row y of the plane is row y - y0 of it
-                          band_tma ? s_band - (int64_t)d.y0 * wpr : plane, tM, sM, lane, ta);
+                          band_tma ? s_band - (int64_t)d.y0 * wpr : plane, tM, lane, ta);
     if (band_tma) fence_proxy_async_smem();           // my tile words -> visible to the TMA
     const long long m00 = ta.m00, m10 = ta.m10, m01 = ta.m01, m20 = ta.m20, m11 = ta.m11, m02 = ta.m02,
                     m30 = ta.m30, m21 = ta.m21, m12 = ta.m12, m03 = ta.m03;
@@ -626,15 +472,8 @@ paste_measure_kernel(const float* __restrict__ masks, const float* __restrict__ 
         case I_NPTS: v = 0; break;
         default: v = (long long)s_acc[tid - I_M10 + 1]; break;     // m10 .. m03
       }
-      // (the contour count / vertex count of a tile handed to a tracer warp are written by that
-      //  warp alone: no two threads ever write the same cell, so the hand-off needs no
-      //  device-wide fence)
-      const bool tracer_owns = kFused && sM != nullptr && area > 0 && (tid == I_NCONT || tid == I_NPTS);
-      if (!tracer_owns) rows_i[inst * kNumInt + tid] = v;
+      rows_i[inst * kNumInt + tid] = v;
     }
-    // what the tracer warp needs, read before the accumulators are reset for the next round
-    const bool has_px = s_acc[0] != 0ull;
-    const int scan_lo = s_bbox[1] - d.y0, scan_hi = s_bbox[3] - d.y0;
     if (tid == 0) s_next[(it + 1) & 1] = claim;
     if (band_tma) {
       // (the barrier after the reduction ordered every warp's tile words before this point)
@@ -653,32 +492,7 @@ paste_measure_kernel(const float* __restrict__ masks, const float* __restrict__ 
       fence_proxy_async_smem();
     }
     compute_barrier();                                 // s_mask / s_acc are rewritten next round
-    // ---- hand the tile to the tracer warp (every warp's row and slot writes precede the
-    //      barrier above) ------------------------------------------------------------------
-    if (kFused && tid == 0) {
-      const int p0 = s_slot;
-      if (p0 >= 0 && has_px) {
-        SlotEntry e;
-        e.inst = inst; e.row_off = d.row_off; e.tw = d.tw; e.th = d.th;
-        e.ylo = scan_lo; e.yhi = scan_hi; e.page0 = p0; e.npages = npages;
-        s_q[qtail % kQueue] = e;
-        __threadfence_block();                         // entry + slot contents before the tail
-        ++qtail;
-        s_qtail = qtail;
-      } else {
-        if (p0 >= 0) atomicAnd(&s_pages, ~(((1u << npages) - 1u) << p0));
-        if (!has_px || d.th == 0) {                    // nothing to trace: the record says so
-          TraceRec r;
-          r.a2 = -1; r.perim = 0.0; r.best_y = 0; r.best_ymax = -1; r.npts = 0; r.ncont = 0;
-          ws.rec[inst] = r;
-        }                                              // (a tile too large for the arena stays kNotTraced)
-      }
-    }
   }
-  if (kFused && tid == 0) { __threadfence_block(); s_cdone = 1; }
-#ifdef UWCV_TUNING
-  if (tid == 0 && st_retry) atomicAdd(&g_fused_stats[0], st_retry);
-#endif
   }
   // the last CTA out re-arms the counters for the next launch on this workspace
   __syncthreads();
@@ -727,7 +541,7 @@ tile_measure_kernel(const float* __restrict__ masks, const float* __restrict__ b
       TileAcc a;
       uint32_t* tM = ws.M + d.word_off;
       for (int rbase = 0; rbase < d.th; rbase += 32)
-        paste_rows<false>(d, rbase, mk, bx0, by0, bx1, by1, thr, W, wpr, nullptr, tM, nullptr, lane, a);
+        paste_rows<false>(d, rbase, mk, bx0, by0, bx1, by1, thr, W, wpr, nullptr, tM, lane, a);
       long long acc[10] = {a.m00, a.m10, a.m01, a.m20, a.m11, a.m02, a.m30, a.m21, a.m12, a.m03};
 #pragma unroll
       for (int k = 0; k < 10; ++k) {
@@ -806,8 +620,8 @@ cudaError_t launch_layout(const float* boxes, int64_t n, int H, int W, const Wor
   if (cudaMemsetAsync(status + 3, 0, sizeof(int64_t), stream) != cudaSuccess) return cudaGetLastError();
   if (cudaMemsetAsync(ws.block_sums + 2 * nblk, 0, sizeof(int64_t), stream) != cudaSuccess)   // moment-overflow flag
     return cudaGetLastError();
-  layout_local_kernel<<<nblk, kLayoutThreads, 0, stream>>>(boxes, n, H, W, ws.desc, ws.rec,
-                                                           ws.block_sums, status + 3);
+  layout_local_kernel<<<nblk, kLayoutThreads, 0, stream>>>(boxes, n, H, W, ws.desc, ws.block_sums,
+                                                           status + 3);
   layout_rebase_kernel<<<nblk, kLayoutThreads, 0, stream>>>(n, nblk, ws.desc, ws.block_sums,
                                                             ws.cap_words, status, ws.sched);
   zero_marks_kernel<<<num_sms * 4, 256, 0, stream>>>(ws.V, ws.G, status);
@@ -839,31 +653,14 @@ cudaError_t launch_paste_measure(const float* masks, const float* boxes, const i
   if (const char* v = getenv("UWCV_BAND_KB")) band_cap = atoi(v) * 1024;       // 0: generic stores
 #endif
   if (band_cap < 0 || band_cap > 96 * 1024 || !planes) band_cap = 0;
-  // The fused border trace (tracer warps inside the paste kernel, see above) is an experiment
-  // that LOST on B200 (profiles/README.md, r02): it exists in the -DUWCV_TUNING build only
-  // (UWCV_FUSED_TRACE=1); the release library always runs the stand-alone trace kernel.
-  bool fused = false;
-#ifdef UWCV_TUNING
-  if (planes && getenv("UWCV_FUSED_TRACE")) fused = true;
-#endif
-  const size_t dyn = planes ? (size_t)zero_bytes + band_cap + (fused ? kArenaBytes : 0) : 0;
-  const int threads = fused ? kFusedThreads : kPasteThreads;
+  const size_t dyn = planes ? (size_t)zero_bytes + band_cap : 0;
+  const int threads = kPasteThreads;
   if (planes) {
-#ifdef UWCV_TUNING
-    if (fused) {
-      cudaFuncSetAttribute(paste_measure_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
-      e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, paste_measure_kernel<true, true>, threads, dyn);
-    } else
-#endif
-    {
-      if (dyn > 40 * 1024)
-        cudaFuncSetAttribute(paste_measure_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)dyn);
-      e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, paste_measure_kernel<true, false>, threads, dyn);
-    }
+    if (dyn > 40 * 1024)
+      cudaFuncSetAttribute(paste_measure_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, paste_measure_kernel<true>, threads, dyn);
   } else {
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, paste_measure_kernel<false, false>,
-                                                      kPasteThreads, dyn);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, paste_measure_kernel<false>, kPasteThreads, dyn);
   }
   if (e != cudaSuccess) return e;
   if (per_sm < 1) per_sm = 1;
@@ -877,14 +674,7 @@ cudaError_t launch_paste_measure(const float* masks, const float* boxes, const i
   int64_t grid = (int64_t)num_sms * per_sm;           // persistent: a whole number of waves
   if (grid > count) grid = count;
   if (planes) {
-#ifdef UWCV_TUNING
-    if (fused)
-      paste_measure_kernel<true, true><<<(unsigned)grid, threads, dyn, stream>>>(
-          masks, boxes, image_idx, inst_idx, classes, n, H, W, thr, planes, rows_i, ws, status,
-          zero_bytes, rot_mul, fill_mode, debug_skip, first, src, 0, band_cap, nullptr);
-    else
-#endif
-      paste_measure_kernel<true, false><<<(unsigned)grid, threads, dyn, stream>>>(
+    paste_measure_kernel<true><<<(unsigned)grid, threads, dyn, stream>>>(
           masks, boxes, image_idx, inst_idx, classes, n, H, W, thr, planes, rows_i, ws, status,
           zero_bytes, rot_mul, fill_mode, debug_skip, first, src, 0, band_cap, nullptr);
     return cudaPeekAtLastError();
@@ -906,7 +696,7 @@ cudaError_t launch_paste_measure(const float* masks, const float* boxes, const i
     tile_measure_kernel<<<(unsigned)tgrid, kTileWarps * 32, 0, stream>>>(
         masks, boxes, image_idx, inst_idx, classes, n, H, W, thr, rows_i, ws, status, first, src);
   }
-  paste_measure_kernel<false, false><<<(unsigned)grid, kPasteThreads, dyn, stream>>>(
+  paste_measure_kernel<false><<<(unsigned)grid, kPasteThreads, dyn, stream>>>(
       masks, boxes, image_idx, inst_idx, classes, n, H, W, thr, planes, rows_i, ws, status,
       zero_bytes, rot_mul, fill_mode, debug_skip, first, src, per_warp ? 1 : 0, 0, nullptr);
   return cudaPeekAtLastError();
@@ -914,10 +704,3 @@ cudaError_t launch_paste_measure(const float* masks, const float* boxes, const i
 
 }  // namespace uwcv
 
-#ifdef UWCV_TUNING
-extern "C" int uwcv_tuning_fused_stats(unsigned long long* out4, int reset) {
-  if (cudaMemcpyFromSymbol(out4, uwcv::g_fused_stats, 32) != cudaSuccess) return -6;
-  if (reset) { unsigned long long z[4] = {0, 0, 0, 0}; cudaMemcpyToSymbol(uwcv::g_fused_stats, z, 32); }
-  return 0;
-}
-#endif

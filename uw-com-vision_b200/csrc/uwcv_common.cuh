@@ -81,26 +81,21 @@ struct GatherDst {
   double* rows_f[kMaxPeers];       // [total_rows, kNumFloat] per peer
 };
 
-// Result of the border trace of one instance, handed from the kernel that traced it (the tracer
-// warps of the paste kernel, or the stand-alone trace) to the descriptor kernel: the largest
-// external contour's twice-area, arc length, first / last row (tile coordinates) and vertex count;
-// its per-row extremes are the first extremes set of the instance in Workspace::scratch.
+// (reserved header record per instance: 32 bytes, kept so that the workspace carve-up -- and with it
+// uwcv_workspace_bytes -- does not change; the fused-trace experiment of round 2 handed its results
+// over through it)
 struct __align__(16) TraceRec {
-  long long a2;        // |twice the contour area| of the best contour
+  long long a2;
   double perim;
-  int32_t best_y;      // tile row of its raster-first pixel
-  int32_t best_ymax;   // last tile row it reaches
-  int32_t npts;        // CHAIN_APPROX_SIMPLE vertices
-  int32_t ncont;       // external contours of the instance; kNotTraced: still to be traced
+  int32_t best_y, best_ymax, npts, ncont;
 };
-constexpr int32_t kNotTraced = -1;
 
 // Workspace carve-up, computed identically on host and device.
 constexpr int kLayoutThreads = 1024;   // instances per layout CTA
 
 struct Workspace {
   TileDesc* desc;      // [N]
-  TraceRec* rec;       // [N]
+  TraceRec* rec;       // [N]  (reserved)
   int32_t* order;      // [N]  paste order of a launch's range: large tiles first (their traces are the long ones)
   int64_t* block_sums; // [2 * ceil(N / 1024)]  per-CTA (tile words, tile rows) of the layout
   unsigned int* sched; // [8]  work counters of the paste kernel (fill, tile, CTAs done, ...); zero between launches

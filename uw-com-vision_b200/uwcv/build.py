@@ -36,8 +36,8 @@ def needs_build(path: str = LIB_PATH) -> bool:
 
 def build(force: bool = False, verbose: bool = False, variant: str = "") -> str:
     """variant: "" (release), "tuning" (-DUWCV_TUNING) or "check" (-DUWCV_CHECK); development
-    sweeps may append compile-time overrides, e.g. "tuning,TRACER_WARPS=2" ->
-    lib/libuwcv_tuning_TRACER_WARPS_2.so built with -DUWCV_TUNING -DUWCV_TRACER_WARPS=2."""
+    sweeps may append compile-time overrides, e.g. "tuning,CONTOUR_MINBLOCKS=12" ->
+    lib/libuwcv_tuning_CONTOUR_MINBLOCKS_12.so built with -DUWCV_TUNING -DUWCV_CONTOUR_MINBLOCKS=12."""
     parts = [v for v in variant.split(",") if v]
     base = parts[0] if parts else ""
     out = {"": LIB_PATH, "tuning": TUNING_LIB_PATH, "check": CHECK_LIB_PATH}[base]
