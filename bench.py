@@ -636,7 +636,7 @@ def run_ours(args):
     if world == 1 and not args.no_other_configs:
         others = other_configs(eng, dev)
     if world == 1 and not args.no_cpu_baseline:
-        nc = 250
+        nc = 600                 # ~13 s of CPU work for baseline A on 16 cores
         sample = synth.blob_instances(0, nc, H, W, seed=1234)
         t0 = time.perf_counter()
         done, _ = reference_step(sample, (H, W))

@@ -933,3 +933,27 @@ def test_split_pipeline_equals_fused_kernel():
         # the planes are the Detectron2-literal masks
         ref = d2.paste_masks_in_image(masks, boxes, (H, W))
         assert torch.equal(eng.unpack(p2, H, W).cpu(), ref)
+
+
+def test_split_pipeline_streams_different_batches():
+    """Calls in flight on the three streams of the split pipeline (tile kernel of call i + 1, plane
+    fill and border trace of call i, two workspaces in turn) with a DIFFERENT batch per call: every
+    call returns its own planes and rows (a fill or a trace that read a workspace the next layout had
+    already handed out again would show here)."""
+    H, W = 384, 512
+    batches = [[synth.blob_instances(10 * s + k, 150 + 40 * ((s + k) % 4), H, W, seed=900 + 7 * s + k,
+                                     size_range=(6.0, 120.0)) for k in range(3)] for s in range(7)]
+    want = []
+    for b in batches:                                   # reference: the fused single-stream kernels
+        masks = torch.cat([i.pred_masks[:, 0] for i in b])
+        boxes = torch.cat([api.scale_clip_boxes(i.pred_boxes.tensor, (H, W), (H, W))[0] for i in b])
+        want.append(plane_crcs(uwcv.paste_masks_in_image(masks, boxes, (H, W), packed=True)))
+    rows = [uwcv.measure_instances(b, (H, W)) for b in batches]          # rows-only contract
+    for depth in (2, 3):
+        stream = uwcv.MeasurementStream(depth=depth)
+        got = list(stream.map(batches, (H, W), return_planes=True))
+        for (table, planes), crc, ref in zip(got, want, rows):
+            assert len(table) == len(crc)
+            assert np.array_equal(plane_crcs(planes), crc)
+            assert np.array_equal(table.ints, ref.ints)
+            assert np.array_equal(table.floats, ref.floats, equal_nan=True)
