@@ -60,6 +60,24 @@ const char* uwcv_strerror(int code);
  * ceil(W / 32) rounded up to a multiple of 4 (16-byte rows). */
 int uwcv_plane_row_words(int W);
 
+/*
+ * uwcv_planes_alloc / uwcv_planes_free -- device memory for the full-frame bit-planes as a
+ * COMPRESSIBLE allocation on the current device (CUDA virtual memory management with generic
+ * compression).  The planes are zeros almost everywhere; in compressible pages B200 compresses
+ * them between L2 and HBM, so the same kernels write them 14 % and read them 40 % faster
+ * (profiles/r02_fill_compress_microbench.txt).  Purely optional: every entry point works on any
+ * device pointer, and these two are the only calls of the library that allocate.  `bytes` is
+ * rounded up to the allocation granularity (2 MiB); *compressed (may be NULL) reports whether the
+ * driver granted compression (0: ordinary pages, still valid).  The memory is NOT initialised.
+ * uwcv_planes_free is the caller's cudaFree for such a pointer: no work may still use it.
+ * Stands in for: the `torch.zeros(N, img_h, img_w)` behind Detectron2's paste_masks_in_image
+ * (layers/mask_ops.py), reached from nn_inference.py:372.
+ * Errors: UWCV_E_NULL, UWCV_E_SHAPE (bytes == 0 / foreign pointer), UWCV_E_WORKSPACE (out of
+ * memory), UWCV_E_LAUNCH (no driver / VMM call failed).
+ */
+int uwcv_planes_alloc(size_t bytes, void** ptr, int* compressed);
+int uwcv_planes_free(void* ptr);
+
 /* Bytes of workspace uwcv_paste_measure needs for N instances whose tiles hold
  * `tile_words` 32-pixel words in total (28 bytes per word + descriptors).  The exact
  * word count of a call is reported back in status[1]; a caller that does not know it

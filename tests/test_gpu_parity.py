@@ -957,3 +957,43 @@ def test_split_pipeline_streams_different_batches():
             assert np.array_equal(plane_crcs(planes), crc)
             assert np.array_equal(table.ints, ref.ints)
             assert np.array_equal(table.floats, ref.floats, equal_nan=True)
+
+
+def test_compressible_plane_buffers():
+    """uwcv_planes_alloc: planes written into compressible device memory are the planes written into
+    ordinary memory, bit for bit, for the fused kernel and for the split pipeline; the allocation is
+    released with its last tensor; the raw calls round-trip."""
+    import ctypes as C
+    from uwcv import _lib
+    dev = torch.device("cuda", 0)
+    eng = api.Engine.get(dev)
+    L = _lib.lib()
+    ptr, comp = C.c_void_p(), C.c_int(-1)
+    assert L.uwcv_planes_alloc(3 << 20, C.byref(ptr), C.byref(comp)) == 0 and ptr.value and comp.value in (0, 1)
+    assert ptr.value % (2 << 20) == 0
+    assert L.uwcv_planes_free(ptr) == 0 and L.uwcv_planes_free(ptr) == -2   # second free: unknown pointer
+    H, W, n = 300, 500, 120
+    inst = synth.blob_instances(3, n, H, W, seed=41, size_range=(4.0, 200.0))
+    masks, boxes = inst.pred_masks[:, 0].contiguous().to(dev), inst.pred_boxes.tensor.contiguous().to(dev)
+    wpr = L.uwcv_plane_row_words(W)
+    plain = torch.empty((n, H, wpr), dtype=torch.int32, device=dev).fill_(-1)
+    eng.run(masks, boxes, H, W, planes=plain)
+    for split in (False, True):
+        pc = eng.alloc_planes(n, H, W)
+        assert pc.is_cuda and pc.shape == plain.shape and pc.dtype == torch.int32
+        pc.fill_(-1)
+        if split:
+            eng.run_overlapped(masks, boxes, H, W, planes=pc, split=True)
+        else:
+            eng.run(masks, boxes, H, W, planes=pc)
+        torch.cuda.synchronize()
+        assert torch.equal(pc, plain)
+        assert torch.equal(eng.unpack(pc, H, W).cpu(), d2.paste_masks_in_image(inst.pred_masks[:, 0], inst.pred_boxes.tensor, (H, W)))
+        view = pc[5:9]                               # a view keeps the allocation alive
+        del pc
+        assert torch.equal(view, plain[5:9])
+        del view
+    if eng.compressible_planes:                      # granted on this device: the buffers above were compressible
+        buf = api._CompressibleBuffer.create(eng, 1 << 18)
+        assert buf is not None and buf.compressed
+        del buf

@@ -52,6 +52,14 @@ def test_argument_validation_without_gpu():
     assert _lib.strerror(-7).startswith("tile words")
     assert L.uwcv_unpack_planes(None, 1, 8, 8, None, None) == -1
     assert L.uwcv_unpack_planes(None, 0, 8, 8, None, None) == 0
+    # the plane allocator validates before it touches the driver; without a driver it reports a launch error
+    ptr, comp = C.c_void_p(), C.c_int(7)
+    assert L.uwcv_planes_alloc(0, C.byref(ptr), C.byref(comp)) == -2 and comp.value == 0
+    assert L.uwcv_planes_alloc(1 << 20, None, None) == -1
+    assert L.uwcv_planes_free(None) == 0
+    assert L.uwcv_planes_free(C.c_void_p(4096)) == -2                       # not one of ours
+    if not torch.cuda.is_available():
+        assert L.uwcv_planes_alloc(1 << 20, C.byref(ptr), None) == -6 and not ptr.value
     # split pipeline: stage 8 (planes from the tiles) without a plane buffer is refused before any launch
     fake = 4096                                          # non-NULL, 16-byte aligned, never dereferenced
     assert L.uwcv_paste_measure_stages(fake, fake, None, None, None, None, 1, 8, 8, 0.5, 0.85, None, fake, fake,

@@ -56,6 +56,10 @@ def lib() -> C.CDLL:
     L.uwcv_plane_row_words.argtypes = [C.c_int]
     L.uwcv_workspace_bytes.restype = sz
     L.uwcv_workspace_bytes.argtypes = [i64, i64]
+    L.uwcv_planes_alloc.restype = C.c_int
+    L.uwcv_planes_alloc.argtypes = [sz, C.POINTER(vp), C.POINTER(C.c_int)]
+    L.uwcv_planes_free.restype = C.c_int
+    L.uwcv_planes_free.argtypes = [vp]
     L.uwcv_paste_measure.restype = C.c_int
     L.uwcv_paste_measure.argtypes = [vp, vp, vp, vp, vp, vp, i64, i32, i32, f32, f64,
                                      vp, vp, vp, vp, sz, vp, vp]
@@ -109,6 +113,7 @@ def lib() -> C.CDLL:
 
 
 EXPORTS = ("uwcv_version", "uwcv_strerror", "uwcv_plane_row_words", "uwcv_workspace_bytes",
+           "uwcv_planes_alloc", "uwcv_planes_free",
            "uwcv_paste_measure", "uwcv_paste_measure_stages", "uwcv_paste_measure_range", "uwcv_paste_measure_heads", "uwcv_paste_measure_gather",
            "uwcv_unpack_planes", "uwcv_ingest", "uwcv_mask_column_totals", "uwcv_clean_masks", "uwcv_rle_write",
            "uwcv_rle_text_prep", "uwcv_rle_text_write",

@@ -15,7 +15,7 @@ TUNING_LIB_PATH = os.path.join(LIB_DIR, "libuwcv_tuning.so")
 # -DUWCV_CHECK: device-side bounds traps on every tile / plane / scratch index (memory-safety
 # substitute for compute-sanitizer, which is closed on the GPU pool)
 CHECK_LIB_PATH = os.path.join(LIB_DIR, "libuwcv_check.so")
-SOURCES = ["uwcv_capi.cu", "paste_measure.cu", "plane_fill.cu", "contour.cu", "union.cu", "nms.cu", "unpack.cu", "cleanup.cu"]
+SOURCES = ["uwcv_capi.cu", "paste_measure.cu", "plane_fill.cu", "planes_alloc.cu", "contour.cu", "union.cu", "nms.cu", "unpack.cu", "cleanup.cu"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
