@@ -272,6 +272,128 @@ def timed_steps(db, steps, warmup, barrier, step_fn):
     return e0.elapsed_time(e1), wall0, wall1
 
 
+def library_paste_cuda(masks, boxes, img_h, img_w, threshold=0.5):
+    """The library composition the reference triggers on a GPU, written with the
+    torch calls Detectron2's CUDA branch makes (layers/mask_ops.py paste_masks_in_image /
+    _do_paste_mask with skip_empty=False): chunks of at most 1 GiB of float32 result, a
+    materialised (n, H, W, 2) grid, F.grid_sample, `>=`, an indexed copy into N x H x W bool.
+    Here as a MEASURED BASELINE of the same B200, never as a product path."""
+    import torch.nn.functional as F
+    n = int(masks.shape[0])
+    dev = masks.device
+    chunks = torch.chunk(torch.arange(n, device=dev), int(np.ceil(n * img_h * img_w * 4 / 1024 ** 3)))
+    img_masks = torch.zeros(n, img_h, img_w, device=dev, dtype=torch.bool)
+    for inds in chunks:
+        m, b = masks[inds, None, :, :], boxes[inds]
+        x0, y0, x1, y1 = torch.split(b, 1, dim=1)
+        img_y = torch.arange(0, img_h, device=dev, dtype=torch.float32) + 0.5
+        img_x = torch.arange(0, img_w, device=dev, dtype=torch.float32) + 0.5
+        img_y = (img_y - y0) / (y1 - y0) * 2 - 1
+        img_x = (img_x - x0) / (x1 - x0) * 2 - 1
+        k = int(m.shape[0])
+        gx = img_x[:, None, :].expand(k, img_y.size(1), img_x.size(1))
+        gy = img_y[:, :, None].expand(k, img_y.size(1), img_x.size(1))
+        grid = torch.stack([gx, gy], dim=3)
+        chunk = F.grid_sample(m, grid.to(m.dtype), align_corners=False)[:, 0]
+        img_masks[(inds,)] = (chunk >= threshold).to(dtype=torch.bool)
+    return img_masks
+
+
+def library_baseline_gpu(eng, dev, n_inst=1000, reps=3):
+    """One image of the bench workload through the libraries on this GPU: Detectron2's CUDA paste
+    (library_paste_cuda), `.to("cpu")` of the N x H x W bool as nn_inference.py:376 reads it, and
+    torchvision's CUDA batched_nms on the configs[3] candidates next to uwcv_nms.  Device times from
+    CUDA events, the copy by wall clock.  The pixels are compared with this repo's planes for the same
+    instances and the count of differing pixels is reported (CUDA grid_sample is not the parity oracle:
+    the bar is the reference's CPU path, tests/)."""
+    import torchvision
+    from uwcv import api, synth
+    out = {}
+    inst = synth.blob_instances(0, n_inst, H, W, seed=1234)
+    bx, keep = api.scale_clip_boxes(inst.pred_boxes.tensor, (H, W), (H, W))
+    masks = inst.pred_masks[keep, 0].contiguous().to(dev)
+    boxes = bx[keep].contiguous().to(dev)
+    n = int(boxes.shape[0])
+    bits = library_paste_cuda(masks, boxes, H, W)              # warm-up (allocator, cuDNN-free path)
+    torch.cuda.synchronize(dev)
+    ts = []
+    for _ in range(reps):
+        del bits
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); bits = library_paste_cuda(masks, boxes, H, W); b.record(); b.synchronize()
+        ts.append(a.elapsed_time(b))
+    paste_ms = statistics.median(ts)
+    t0 = time.perf_counter()
+    host = bits.to("cpu").numpy()
+    d2h_ms = (time.perf_counter() - t0) * 1e3
+    del host
+    # this repo's path on the same instances: planes + rows, device-resident inputs
+    words = api.tile_words(boxes.cpu(), H, W)
+    planes = eng.alloc_planes(n, H, W)
+    ri = torch.empty((n, 20), dtype=torch.int64, device=dev)
+    rf = torch.empty((n, 30), dtype=torch.float64, device=dev)
+    kw = dict(planes=planes, n_tile_words=words, rows_i=ri, rows_f=rf)
+    for _ in range(3):
+        eng.run(masks, boxes, H, W, **kw)
+    ts = []
+    for _ in range(10):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); eng.run(masks, boxes, H, W, **kw); b.record(); b.synchronize()
+        ts.append(a.elapsed_time(b))
+    ours_ms = statistics.median(ts)
+    mine = eng.unpack(planes, H, W)
+    differing = int((mine != bits).sum().item())
+    area_equal = bool(torch.equal(bits.flatten(1).sum(1), ri[:, 5]))
+    del mine, bits, planes
+    out["paste"] = {
+        "sample": f"1 image {H}x{W} x {n} instances, device-resident inputs",
+        "library_ms": paste_ms, "library_instances_per_s": n / paste_ms * 1e3,
+        "library": f"torch {torch.__version__} F.grid_sample + >= + indexed copy, 1 GiB chunks "
+                   "(Detectron2 paste_masks_in_image, CUDA branch) -> N x H x W bool",
+        "library_mask_d2h_ms": d2h_ms,
+        "library_mask_d2h_note": "N x H x W bool .to('cpu') (pageable), what nn_inference.py:376 does next; "
+                                 "the contour / descriptor work of the reference then runs on the host (cpu_baseline)",
+        "ours_ms": ours_ms, "ours_instances_per_s": n / ours_ms * 1e3,
+        "ours": "single-stream uwcv_paste_measure call: planes (bit-packed) + moments + contours + "
+                "descriptor rows for the same instances (more work than the library leg: it also measures)",
+        "speedup_device": paste_ms / ours_ms,
+        "pixels_differing": differing, "pixels_total": n * H * W,
+        "area_px_equal_to_library_popcount": area_equal,
+    }
+    # NMS: fast_rcnn_inference_single_image's filter + batched_nms + top-k on the configs[3] candidates
+    cb, cs, cc = synth.clustered_candidates(5000, 4096, 4096, seed=99)
+    dcb, dcs, dcc = cb.to(dev), cs.to(dev), cc.to(dev)
+
+    def tv():
+        f = dcs > 0.05
+        b2, s2, c2 = dcb[f], dcs[f], dcc[f]
+        k = torchvision.ops.batched_nms(b2, s2, c2, 0.5)[:6000]
+        return f.nonzero()[:, 0][k]
+
+    for _ in range(3):
+        kept = tv()
+    ts = []
+    for _ in range(5):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); kept = tv(); b.record(); b.synchronize()
+        ts.append(a.elapsed_time(b))
+    tv_ms = statistics.median(ts)
+    for _ in range(3):
+        keep_o, cnt = eng.nms(dcb, dcs, dcc, [0, len(cb)], 0.05, 0.5, 6000)
+    ts = []
+    for _ in range(5):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); keep_o, cnt = eng.nms(dcb, dcs, dcc, [0, len(cb)], 0.05, 0.5, 6000); b.record(); b.synchronize()
+        ts.append(a.elapsed_time(b))
+    out["nms"] = {
+        "sample": f"configs[3]: {len(cb)} candidates, 4 classes, score > 0.05, IoU 0.5, top 6000",
+        "library_ms": tv_ms, "library": f"torchvision {torchvision.__version__} batched_nms (CUDA) after the score filter",
+        "ours_ms": statistics.median(ts), "speedup_device": tv_ms / statistics.median(ts),
+        "keep_list_equal": bool(torch.equal(keep_o[: int(cnt[0])].to(torch.int64), kept.to(torch.int64))),
+    }
+    return out
+
+
 def other_configs(eng, dev):
     """configs[0] and configs[3] (parity-test shapes, not bench lines) with their kernel breakdown:
     device-resident, full-frame planes, CUDA events per kernel group."""
@@ -632,9 +754,15 @@ def run_ours(args):
         dres_s = float(t.item())
 
     # ---- other configs + CPU baselines (rank 0, N = 1 only) ---------------------------------
-    cpu = cpu_b = others = None
+    cpu = cpu_b = others = lib_gpu = None
     if world == 1 and not args.no_other_configs:
         others = other_configs(eng, dev)
+    if world == 1 and not args.no_library_baseline:
+        try:
+            lib_gpu = library_baseline_gpu(eng, dev)
+        except Exception as e:                       # a baseline leg never takes the bench line down
+            lib_gpu = {"error": f"{type(e).__name__}: {e}"[:300]}
+        torch.cuda.empty_cache()
     if world == 1 and not args.no_cpu_baseline:
         nc = 600                 # ~13 s of CPU work for baseline A on 16 cores
         sample = synth.blob_instances(0, nc, H, W, seed=1234)
@@ -721,6 +849,8 @@ def run_ours(args):
             line["weak_scaling"] = weak
         if others is not None:
             line["other_configs"] = others
+        if lib_gpu is not None:
+            line["library_baseline_gpu"] = lib_gpu
         if cpu is not None:
             line["cpu_baseline"] = cpu
         if cpu_b is not None:
@@ -742,6 +872,8 @@ def main():
     ap.add_argument("--no-other-configs", action="store_true")
     ap.add_argument("--instances", type=int, default=INSTANCES_PER_IMAGE)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-library-baseline", action="store_true",
+                    help="skip the torch / torchvision CUDA baseline of the same GPU (library_baseline_gpu)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

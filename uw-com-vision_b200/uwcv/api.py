@@ -17,6 +17,7 @@ computation runs in libuwcv.so.  There is no CPU path.
 from __future__ import annotations
 
 import ctypes as C
+import threading
 from dataclasses import dataclass
 from typing import List, Optional, Sequence, Tuple, Union
 
@@ -237,13 +238,15 @@ class Engine:
     buffer caches here are not locked)."""
 
     _engines = {}
+    _engines_lock = threading.Lock()
 
     @classmethod
     def get(cls, device=None) -> "Engine":
         device = _require_cuda(device)
-        e = cls._engines.get(device)
-        if e is None:
-            e = cls._engines[device] = Engine(device)
+        with cls._engines_lock:                 # two threads asking at once get the same engine
+            e = cls._engines.get(device)
+            if e is None:
+                e = cls._engines[device] = Engine(device)
         return e
 
     def __init__(self, device: torch.device):
