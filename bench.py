@@ -760,9 +760,9 @@ def run_ours(args):
     if world == 1 and not args.no_library_baseline:
         try:
             lib_gpu = library_baseline_gpu(eng, dev)
+            torch.cuda.empty_cache()
         except Exception as e:                       # a baseline leg never takes the bench line down
             lib_gpu = {"error": f"{type(e).__name__}: {e}"[:300]}
-        torch.cuda.empty_cache()
     if world == 1 and not args.no_cpu_baseline:
         nc = 600                 # ~13 s of CPU work for baseline A on 16 cores
         sample = synth.blob_instances(0, nc, H, W, seed=1234)
