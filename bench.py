@@ -699,8 +699,8 @@ def run_ours(args):
     #     flight, so the H2D of step i + 1 and the D2H of step i - 1 run under the kernels of
     #     step i.  Every step still copies its inputs from pinned host memory and reads its
     #     rows back; all K tables are materialised on the host inside the timed region.
-    stream = uwcv.MeasurementStream(dev, depth=2)
-    for table in stream.map((batch for _ in range(3)), (H, W), **kw):
+    stream = uwcv.MeasurementStream(dev, depth=args.e2e_depth)
+    for table in stream.map((batch for _ in range(stream.depth + 3)), (H, W), **kw):
         pass
     barrier()
     t0 = time.perf_counter()
@@ -804,7 +804,7 @@ def run_ours(args):
             "mp_per_sec": args.steps * world * n_img * H * W / 1e6 / (ms * 1e-3),
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": e2e_s / e2e_steps * 1e3,
-                    "call": "uwcv.MeasurementStream(depth=2).map (pinned host Instances in, "
+                    "call": f"uwcv.MeasurementStream(depth={args.e2e_depth}).map (pinned host Instances in, "
                             "host MeasurementTable out, every step)",
                     "sync_call_ms_per_step": sync_s / e2e_steps * 1e3,
                     "h2d_gbs_whole_job": h2d * world / (e2e_s / e2e_steps) / 1e9,
@@ -869,6 +869,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--images", type=int, default=None,
                     help="images per GPU (default: 64 at N = 1; 256 / N at N > 1, configs[2])")
+    ap.add_argument("--e2e-depth", type=int, default=3,
+                    help="calls in flight of the streamed e2e leg (uwcv.MeasurementStream)")
     ap.add_argument("--no-other-configs", action="store_true")
     ap.add_argument("--instances", type=int, default=INSTANCES_PER_IMAGE)
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -949,8 +949,10 @@ def test_split_pipeline_streams_different_batches():
         boxes = torch.cat([api.scale_clip_boxes(i.pred_boxes.tensor, (H, W), (H, W))[0] for i in b])
         want.append(plane_crcs(uwcv.paste_masks_in_image(masks, boxes, (H, W), packed=True)))
     rows = [uwcv.measure_instances(b, (H, W)) for b in batches]          # rows-only contract
-    for depth in (2, 3):
-        stream = uwcv.MeasurementStream(depth=depth)
+    # (three images per call = three chunks of tiles; one plane fill per chunk or one per call)
+    for depth, fills in ((2, None), (3, None), (2, "once"), (3, "per_chunk")):
+        stream = uwcv.MeasurementStream(depth=depth, fills=fills)
+        assert stream.fill_once == ((depth >= 3) if fills is None else fills == "once")
         got = list(stream.map(batches, (H, W), return_planes=True))
         for (table, planes), crc, ref in zip(got, want, rows):
             assert len(table) == len(crc)

@@ -164,15 +164,31 @@ contour_measure_kernel(int64_t first, int64_t n, int lanes, const float* __restr
   }
 }
 
+// Dynamic shared memory the trace of the split pipeline asks for and never touches, so that the
+// driver honours its carve-out hint (share_carveout, uwcv_common.cuh).  Streamed call, one fill per
+// call, two calls in flight -- the trace lands a few microseconds before the fill of its own call:
+// 6.05 ms per 64 000 instances with 0 B, 5.50 with 1 KB, 4.91 with 16 KB, 5.26 with 40 KB (fewer
+// trace CTAs fit); three calls in flight 4.60 / 4.57 / 4.58 / 5.12 (profiles/r02_carveout_probe.txt).
+constexpr size_t kContourCarveoutBytes = 16 * 1024;
+
 cudaError_t launch_contour_measure(int64_t first, int64_t count, const float* scores, double ppm,
                                    int64_t* rows_i, double* rows_f, const Workspace& ws,
                                    const int64_t* status, int num_sms, cudaStream_t stream,
                                    const GatherDst& gather, int reserve_ctas) {
   if (count == 0) return cudaSuccess;
   const int64_t n = count;                               // sizing below is per launched range
+  const bool beside_fill = reserve_ctas > 0;
+  share_carveout(contour_measure_kernel, beside_fill);
+  size_t dyn = beside_fill ? kContourCarveoutBytes : 0;
+#ifdef UWCV_TUNING
+  if (const char* v = getenv("UWCV_TRACE_SMEM")) {
+    const int b = atoi(v);
+    if (beside_fill && b >= 0 && b <= 48 * 1024) dyn = (size_t)b;
+  }
+#endif
   int per_sm = 0;
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, contour_measure_kernel,
-                                                    kContourThreads, 0) != cudaSuccess || per_sm < 1)
+                                                    kContourThreads, dyn) != cudaSuccess || per_sm < 1)
     per_sm = 8;
   // split pipeline: the plane-fill CTAs of the same call are resident beside this kernel; keep the
   // trace grid within ONE wave of what is left (a second wave starts behind the shortest warps
@@ -187,7 +203,7 @@ cudaError_t launch_contour_measure(int64_t first, int64_t count, const float* sc
 #endif
   const int64_t warps = (n + lanes - 1) / lanes;
   const unsigned grid = (unsigned)((warps * 32 + kContourThreads - 1) / kContourThreads);
-  contour_measure_kernel<<<grid, kContourThreads, 0, stream>>>(first, first + count, lanes, scores,
+  contour_measure_kernel<<<grid, kContourThreads, dyn, stream>>>(first, first + count, lanes, scores,
                                                                ppm, rows_i, rows_f, ws, status,
                                                                gather);
   return cudaPeekAtLastError();

@@ -620,6 +620,9 @@ cudaError_t launch_layout(const float* boxes, int64_t n, int H, int W, const Wor
   if (cudaMemsetAsync(status + 3, 0, sizeof(int64_t), stream) != cudaSuccess) return cudaGetLastError();
   if (cudaMemsetAsync(ws.block_sums + 2 * nblk, 0, sizeof(int64_t), stream) != cudaSuccess)   // moment-overflow flag
     return cudaGetLastError();
+  share_carveout(layout_local_kernel);
+  share_carveout(layout_rebase_kernel);
+  share_carveout(zero_marks_kernel);
   layout_local_kernel<<<nblk, kLayoutThreads, 0, stream>>>(boxes, n, H, W, ws.desc, ws.block_sums,
                                                            status + 3);
   layout_rebase_kernel<<<nblk, kLayoutThreads, 0, stream>>>(n, nblk, ws.desc, ws.block_sums,
@@ -655,6 +658,9 @@ cudaError_t launch_paste_measure(const float* masks, const float* boxes, const i
   if (band_cap < 0 || band_cap > 96 * 1024 || !planes) band_cap = 0;
   const size_t dyn = planes ? (size_t)zero_bytes + band_cap : 0;
   const int threads = kPasteThreads;
+  share_carveout(paste_measure_kernel<true>);
+  share_carveout(paste_measure_kernel<false>);
+  share_carveout(tile_measure_kernel);
   if (planes) {
     if (dyn > 40 * 1024)
       cudaFuncSetAttribute(paste_measure_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);

@@ -159,6 +159,7 @@ cudaError_t launch_plane_fill(uint32_t* planes, int64_t first, int64_t count, in
   if (cudaFuncSetAttribute(plane_fill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn) !=
       cudaSuccess)
     return cudaGetLastError();
+  share_carveout(plane_fill_kernel);
   int per_sm = 2;                      // two issuer threads per SM saturate the write path (r01 v9)
 #ifdef UWCV_TUNING
   if (const char* v = getenv("UWCV_FILL_CTAS")) { const int c = atoi(v); if (c >= 1 && c <= 4) per_sm = c; }

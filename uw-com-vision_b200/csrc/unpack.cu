@@ -63,6 +63,7 @@ ingest_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, size_t n16
 cudaError_t launch_ingest(const void* src_host_mapped, void* dst, size_t bytes, cudaStream_t stream) {
   const size_t n16 = (bytes + 15) / 16;
   if (n16 == 0) return cudaSuccess;
+  share_carveout(ingest_kernel);
   ingest_kernel<<<(unsigned)((n16 + 255) / 256), 256, 0, stream>>>(
       reinterpret_cast<const uint4*>(src_host_mapped), reinterpret_cast<uint4*>(dst), n16);
   return cudaPeekAtLastError();

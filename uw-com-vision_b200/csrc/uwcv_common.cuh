@@ -5,6 +5,7 @@
 // reaches through predictor(im), :372).  See DESIGN.md for the data layout.
 #pragma once
 #include <cstdint>
+#include <cstdlib>
 #include <cuda_runtime.h>
 
 // -DUWCV_CHECK (lib/libuwcv_check.so): device-side bounds traps on every tile / plane / band /
@@ -89,6 +90,32 @@ struct __align__(16) TraceRec {
   double perim;
   int32_t best_y, best_ymax, npts, ncont;
 };
+
+// One shared-memory / L1 split for every kernel of the measure pipeline.
+//
+// The plane fill is a persistent kernel of 2 CTAs per SM with 53 KB of shared memory each.  An SM
+// changes its shared-memory carve-out only when it is empty, and a persistent fill CTA keeps it
+// occupied for the whole launch: when the fill's CTAs arrive on SMs that a co-running kernel with
+// a small carve-out (layout, mark clearing, the border trace: no or little shared memory) reached a
+// microsecond earlier, only ONE fill CTA fits per SM and the second never gets in -- the whole
+// fill then runs at 60 % of its rate (6.6 instead of 4.3 ms per 64 000 instances), and which of
+// the two happens is decided by the launch order of that microsecond (CUPTI timelines,
+// profiles/r02_carveout_*.txt).  With every kernel that can be resident beside the fill asking for
+// the same split (all of it shared memory), the carve-out never stands in the way.  The driver
+// ignores the hint for a kernel that uses no shared memory at all, so the border trace of the split
+// pipeline also asks for 16 KB it never touches (kContourCarveoutBytes, contour.cu).
+// (`on` = false hands the choice back to the driver: the border trace of a call that writes no
+// planes has no fill beside it and keeps the large L1 -- 1.74 against 1.90 ms per 64 000 instances.)
+template <class Kernel>
+inline void share_carveout(Kernel kernel, bool on = true) {
+#ifdef UWCV_TUNING
+  if (getenv("UWCV_NO_CARVEOUT")) return;
+#endif
+  if (cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                           on ? (int)cudaSharedmemCarveoutMaxShared
+                              : (int)cudaSharedmemCarveoutDefault) != cudaSuccess)
+    cudaGetLastError();                 // a hint: never fails a launch
+}
 
 // Workspace carve-up, computed identically on host and device.
 constexpr int kLayoutThreads = 1024;   // instances per layout CTA

@@ -439,7 +439,8 @@ class Engine:
                 + ((stages >> 2) & 1) + ((stages >> 3) & 1)
         return rows_i, rows_f, status
 
-    def run_overlapped(self, masks, boxes, H, W, *, paste_ranges=None, after=None, split=None, **kw):
+    def run_overlapped(self, masks, boxes, H, W, *, paste_ranges=None, after=None, split=None,
+                       fill_once=False, **kw):
         """Layout + paste on the current stream, border trace on ``trace_stream``, alternating
         between the two workspaces.  ``paste_ranges``: [(first, count, event or None), ...] --
         the paste of a range waits for its event (chunks of a host->device copy in flight).
@@ -448,6 +449,10 @@ class Engine:
         only (compute-bound) and the planes are written from the tiles on ``fill_stream`` by a
         kernel that only moves data, so the HBM-bound fill shares the SMs with the trace of this
         call and the tile kernel of the next; ``self.planes_done`` is the event behind the fill.
+        ``fill_once``: ONE plane fill over the whole call behind the last range's tiles instead of
+        one per range (a fill launch pays its ramp and its drain -- ~0.1 ms -- whatever its size;
+        callers that keep three or more calls in flight have the previous call's fill to run under
+        the ranges still arriving, so nothing is gained by starting this call's fill early).
         Returns the event that marks the rows complete."""
         dev = self.device
         main = torch.cuda.current_stream(dev)
@@ -460,24 +465,34 @@ class Engine:
         split = bool(split) and kw.get("planes") is not None
         sbit = 16 if split else 0
         self.run(masks, boxes, H, W, stages=1, **kw)
-        for first, count, ev in (paste_ranges or [(0, n, None)]):
+        def fill(first, count):
+            tiles = torch.cuda.Event()
+            tiles.record(main)
+            with torch.cuda.stream(self.fill_stream):
+                self.fill_stream.wait_event(tiles)
+                if self.fill_events is not None:       # (bench: live time of the fill inside the pipeline)
+                    t0 = torch.cuda.Event(enable_timing=True)
+                    t0.record(self.fill_stream)
+                self.run(masks, boxes, H, W, stages=8 | sbit, first=first, count=count, **kw)
+                if self.fill_events is not None:
+                    t1 = torch.cuda.Event(enable_timing=True)
+                    t1.record(self.fill_stream)
+                    self.fill_events.append((t0, t1))
+
+        ranges = list(paste_ranges or [(0, n, None)])
+        fill_once = bool(fill_once) and split and len(ranges) > 1
+        for first, count, ev in ranges:
             if ev is not None:
                 main.wait_event(ev)
             if count > 0:
                 self.run(masks, boxes, H, W, stages=2 | sbit, first=first, count=count, **kw)
-                if split:
-                    tiles = torch.cuda.Event()
-                    tiles.record(main)
-                    with torch.cuda.stream(self.fill_stream):
-                        self.fill_stream.wait_event(tiles)
-                        if self.fill_events is not None:       # (bench: live time of the fill inside the pipeline)
-                            t0 = torch.cuda.Event(enable_timing=True)
-                            t0.record(self.fill_stream)
-                        self.run(masks, boxes, H, W, stages=8 | sbit, first=first, count=count, **kw)
-                        if self.fill_events is not None:
-                            t1 = torch.cuda.Event(enable_timing=True)
-                            t1.record(self.fill_stream)
-                            self.fill_events.append((t0, t1))
+                if split and not fill_once:
+                    fill(first, count)
+        if fill_once:
+            lo = min(f for f, c, _ in ranges)
+            hi = max(f + c for f, c, _ in ranges)
+            if hi > lo:
+                fill(lo, hi - lo)
         pasted = torch.cuda.Event()
         pasted.record(main)
         if split:
@@ -868,21 +883,38 @@ class MeasurementStream:
     in flight, so the host->device copy of batch i + 1 and the device->host read of batch
     i - 1 run under the kernels of batch i.
 
-        stream = uwcv.MeasurementStream(device, depth=2)
+        stream = uwcv.MeasurementStream(device, depth=3)
         for table in stream.map(batches, (H, W)): ...
 
-    ``submit`` returns a ``PendingTable``; tables come back in submission order."""
+    ``submit`` returns a ``PendingTable``; tables come back in submission order.
 
-    def __init__(self, device=None, depth: int = 2):
+    ``fills``: "per_chunk" starts a call's plane fill as soon as its first chunk of masks has
+    landed (shortest path through ONE call: right for depth <= 2, where the next call's copies
+    are only issued once this call's predecessor has been collected); "once" writes a call's
+    planes with one fill launch behind its last chunk (each launch pays its ramp and drain:
+    right for depth >= 3, where the copy engine runs back to back and the previous call's fill
+    covers the wait).  Default: by depth.  Planes and rows are the same bytes either way."""
+
+    def __init__(self, device=None, depth: int = 3, fills: Optional[str] = None):
         self.device = _require_cuda(device)
         self.depth = max(1, int(depth))
+        if fills not in (None, "per_chunk", "once"):
+            raise ValueError("fills must be 'per_chunk' or 'once'")
+        self.fill_once = (self.depth >= 3) if fills is None else (fills == "once")
         self._next = 0
 
     def submit(self, instances, output_size=None, classes_of_interest=None, **kw) -> PendingTable:
+        if kw.get("gather") and dist_is_multi():
+            from .dist import SharedHostTable
+            if self.depth > SharedHostTable.SETS - 1:
+                # (a set of the shared host table is written again only when the table that last
+                #  used it has been let go of: depth calls in flight + the one the caller reads)
+                raise ValueError(f"gathered calls: depth <= {SharedHostTable.SETS - 1}")
         slot = self._next
         self._next = (self._next + 1) % self.depth
         return submit_measure_instances(instances, output_size, classes_of_interest,
-                                        device=self.device, _slot=slot, **kw)
+                                        device=self.device, _slot=slot,
+                                        _fill_once=self.fill_once, **kw)
 
     def map(self, batches, output_size=None, classes_of_interest=None, **kw):
         inflight: List[PendingTable] = []
@@ -1111,7 +1143,8 @@ def submit_measure_instances(instances, output_size=None, classes_of_interest=No
                              gather_dst: Optional[int] = None, gather_sink: str = "auto",
                              mask_channel_offset: int = 0,
                              pipeline_chunks: int = 4, device=None, _exact_words: bool = False,
-                             _slot: int = 0, _no_fast: bool = False) -> PendingTable:
+                             _slot: int = 0, _no_fast: bool = False,
+                             _fill_once: bool = False) -> PendingTable:
     """Enqueue one ``measure_instances`` call (same arguments) and return its handle."""
     single = not isinstance(instances, (list, tuple))
     batch: List[object] = [instances] if single else list(instances)
@@ -1235,7 +1268,7 @@ def submit_measure_instances(instances, output_size=None, classes_of_interest=No
                 d_masks, d_boxes, H, W,
                 paste_ranges=[(lo, hi - lo, ev_in[c]) for c, (i0, i1, lo, hi) in enumerate(bounds)],
                 gather=gstruct, after=(lambda: fg.barrier(gset)) if fg is not None else None,
-                **common)
+                fill_once=_fill_once, **common)
             if planes is not None and eng.planes_done is not None:
                 pend._planes_done = eng.planes_done
         else:
@@ -1301,6 +1334,9 @@ def _issue_mask_copies(eng: "Engine", slot: _Slot, dev, ml, counts, pipeline_chu
     and with it every paste, back until the last mask has landed)."""
     n = int(sum(counts))
     nchunks = max(1, min(int(pipeline_chunks), len(ml)))
+    if all(m.is_cuda for m in ml):
+        nchunks = 1          # nothing crosses PCIe: chunks would only split the kernels (4.47 vs 5.02 ms per
+        #                      64 000 instances, profiles/r02_e2e_depth.txt)
     per = (len(ml) + nchunks - 1) // nchunks
     bounds = []                                   # (first image, last image + 1, lo row, hi row)
     lo = 0
