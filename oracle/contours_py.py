@@ -242,13 +242,123 @@ def rotating_calipers_f32(hull: np.ndarray):
     return out
 
 
+def _sklansky(P, start: int, end: int, nsign: int, sign2: int) -> List[int]:
+    """UPSTREAM convhull.cpp::Sklansky_ over the sorted points P (one quarter of the hull, walked
+    from ``start`` towards ``end``); returns the stack of indices into P."""
+    def sgn(v):
+        return (v > 0) - (v < 0)
+    incr = 1 if end > start else -1
+    pprev, pcur, pnext = start, start + incr, start + 2 * incr
+    if start == end or P[start] == P[end]:
+        return [start]
+    stack = [pprev, pcur, pnext]
+    end += incr
+    while pnext != end:
+        cury, nexty = P[pcur][1], P[pnext][1]
+        by = nexty - cury
+        if sgn(by) != nsign:
+            ax = P[pcur][0] - P[pprev][0]
+            bx = P[pnext][0] - P[pcur][0]
+            ay = cury - P[pprev][1]
+            convexity = ay * bx - ax * by
+            if sgn(convexity) == sign2 and (ax != 0 or ay != 0):
+                pprev, pcur = pcur, pnext
+                pnext += incr
+                stack.append(pnext)
+            elif pprev == start:
+                pcur = pnext
+                stack[1] = pcur
+                pnext += incr
+                stack[2] = pnext
+            else:
+                stack[-2] = pnext
+                pcur = pprev
+                pprev = stack[-4]
+                stack.pop()
+        else:
+            pnext += incr
+            stack[-1] = pnext
+    stack.pop()
+    return stack
+
+
+def convex_hull_cv(contour_pts: np.ndarray) -> np.ndarray:
+    """cv2.convexHull(points, clockwise=False, returnPoints=True) restated IN FULL for integer
+    points -- what cv2.minAreaRect (called at nn_inference.py:417) hands to its rotating calipers,
+    including the ORDER of the output, which decides ties between rectangles of equal float32 area.
+
+    OpenCV is a dependency of the reference, not part of /root/reference (opencv-python 4.13 in
+    this image); restated from its published source (imgproc/src/convhull.cpp): points sorted by
+    (x, y, position), four Sklansky walks (top-left, top-right, bottom-left, bottom-right quarter),
+    then "try to make the convex hull indices form an ascending or descending sequence by the
+    cyclic shift of the output" -- a shift that is only made when the contour indices of the hull
+    vertices are a rotation of a monotone sequence.  For a simple contour they always are and the
+    result is ``hull_like_cv``'s order; a contour that visits a hull vertex twice (one-pixel spurs)
+    can fail the test and keeps the natural order, which starts at the (x, y)-largest point.
+    tests/test_oracle.py pins this against cv2.convexHull and cv2.minAreaRect on thousands of
+    speckle contours, bit for bit."""
+    pts = [(int(x), int(y)) for x, y in np.asarray(contour_pts).reshape(-1, 2)]
+    total = len(pts)
+    if total == 0:
+        return np.zeros((0, 2), dtype=np.int64)
+    order = sorted(range(total), key=lambda i: (pts[i][0], pts[i][1], i))
+    P = [pts[i] for i in order]
+    miny = maxy = 0
+    for i in range(1, total):
+        if P[miny][1] > P[i][1]:
+            miny = i
+        if P[maxy][1] < P[i][1]:
+            maxy = i
+    if P[0] == P[total - 1]:
+        return np.array([pts[order[0]]], dtype=np.int64)
+    hull: List[int] = []
+    # (clockwise=False: the two upper stacks, then the two lower ones, swap places)
+    tl = _sklansky(P, total - 1, maxy, -1, -1)
+    tr = _sklansky(P, 0, maxy, -1, 1)
+    hull += [order[k] for k in tl[:-1]]
+    hull += [order[tr[i]] for i in range(len(tr) - 1, 0, -1)]
+    stop_idx = tr[1] if len(tr) > 2 else (tl[-2] if len(tl) > 2 else -1)
+    bl = _sklansky(P, 0, miny, 1, -1)
+    br = _sklansky(P, total - 1, miny, 1, 1)
+    blc, brc = len(bl), len(br)
+    if stop_idx >= 0:
+        check_idx = bl[1] if blc > 2 else (br[2 - blc] if blc + brc > 2 else -1)
+        if check_idx == stop_idx or (check_idx >= 0 and P[check_idx] == P[stop_idx]):
+            # all points on one line: the bottom part mirrors the top part
+            blc, brc = min(blc, 2), min(brc, 2)
+    hull += [order[bl[i]] for i in range(blc - 1)]
+    hull += [order[br[i]] for i in range(brc - 1, 0, -1)]
+    nout = len(hull)
+    if nout >= 3:
+        min_i = max_i = lt = 0
+        for i in range(1, nout):
+            lt += hull[i - 1] < hull[i]
+            if 1 < lt <= i - 2:
+                break
+            if hull[i] < hull[min_i]:
+                min_i = i
+            if hull[i] > hull[max_i]:
+                max_i = i
+        mmdist = abs(max_i - min_i)
+        if (mmdist == 1 or mmdist == nout - 1) and (lt <= 1 or lt >= nout - 2):
+            ascending = (max_i + 1) % nout == min_i
+            i0 = min_i if ascending else max_i
+            if i0 > 0:
+                rot = hull[i0:] + hull[:i0]
+                if all(ascending == (rot[i] < rot[i + 1]) for i in range(nout - 1)):
+                    hull = rot
+    return np.array([pts[k] for k in hull], dtype=np.int64)
+
+
 def hull_like_cv(contour_pts: np.ndarray) -> np.ndarray:
-    """Hull of a traced external contour in the order cv2.convexHull(c, clockwise=False)
-    returns it for a simple contour: clockwise on screen, cyclically shifted so
-    that the hull indices into the contour descend, i.e. the contour's start
-    pixel (raster-first pixel of the component, always a hull vertex) comes LAST.
-    (UPSTREAM convhull.cpp: "try to make the convex hull indices form an
-    ascending or descending sequence by the cyclic shift of the output".)"""
+    """THE DEVICE'S RULE (csrc/contour_common.cuh::Hull): hull of a traced external contour
+    clockwise on screen, cyclically shifted so that the contour's start pixel (raster-first
+    pixel of the component, always a hull vertex) comes LAST.  This is the order
+    cv2.convexHull(c, clockwise=False) returns for every SIMPLE contour (its hull indices then
+    descend after OpenCV's cyclic shift); for a contour that visits a hull vertex twice OpenCV's
+    shift test can fail -- ``convex_hull_cv`` is the exact restatement, and the two differ in
+    the START of the cycle only, which matters to minAreaRect when two rectangles tie in float32
+    area ("Known deviation")."""
     pts = np.asarray(contour_pts, dtype=np.int64).reshape(-1, 2)
     h = convex_hull(pts)
     if len(h) <= 2:

@@ -132,6 +132,26 @@ def test_min_area_rect_restatement_is_bit_exact():
             assert np.array_equal(cp.box_points_cv(rr), cv2.boxPoints(r))
             n += 1
     assert n > 250
+    # speckle: contours that are NOT simple (one-pixel spurs, pixels visited twice) -- the exact
+    # restatement of OpenCV's convexHull (order included) feeds the same calipers
+    differ = 0
+    for t in range(1200):
+        h, w = rng.integers(6, 30), rng.integers(6, 30)
+        m = (rng.random((h, w)) < rng.uniform(0.3, 0.8)).astype(np.uint8)
+        cs, _ = cv2.findContours(m, cv2.RETR_EXTERNAL, cv2.CHAIN_APPROX_SIMPLE)
+        for c in cs:
+            hull = cp.convex_hull_cv(c.reshape(-1, 2))
+            assert np.array_equal(hull, cv2.convexHull(c).reshape(-1, 2))
+            r = cv2.minAreaRect(c)
+            rr = cp.min_area_rect_cv(hull)
+            assert rr == ((r[0][0], r[0][1]), (r[1][0], r[1][1]), r[2])
+            assert np.array_equal(cp.box_points_cv(rr), cv2.boxPoints(r))
+            simple = len({tuple(q) for q in c.reshape(-1, 2).tolist()}) == len(c)
+            same = np.array_equal(cp.hull_like_cv(c.reshape(-1, 2)), hull)
+            assert same or not simple or len(hull) <= 2      # the device's rule: every simple contour
+            differ += not same
+            n += 1
+    assert n > 5000 and differ > 50          # (the sample does contain what the rule misses)
     for pts in ([[2, 3], [7, 3]], [[2, 3], [2, 9]], [[1, 1], [5, 5]], [[5, 1], [1, 5]], [[3, 3]],
                 [[0, 0], [9, 2]], [[4, 1], [5, 9]]):
         c = np.array(pts, np.int32).reshape(-1, 1, 2)
@@ -139,6 +159,34 @@ def test_min_area_rect_restatement_is_bit_exact():
         rr = cp.min_area_rect_cv(cp.hull_like_cv(c.reshape(-1, 2)))
         assert rr == ((r[0][0], r[0][1]), (r[1][0], r[1][1]), r[2])
         assert np.array_equal(cp.box_points_cv(rr), cv2.boxPoints(r))
+
+
+def test_known_deviation_hull_start_of_a_non_simple_contour():
+    """DESIGN.md section 4, "Known deviation": the one instance of the 77 000-seed sweep whose
+    min-area rectangle differs on the device.  The contour has a one-pixel diagonal spur (hull
+    vertex (495, 407) is visited twice), cv2.convexHull therefore does NOT rotate its output
+    behind the contour's start pixel, and two rectangles of equal float32 area (35.0) swap places
+    in the calipers' last-minimum rule.  The restatement below follows the device code ("start
+    pixel last"): this test pins what differs (the hull's START only) and what does not (the hull
+    itself, the tie), so a fix has to change exactly this."""
+    pts = [[496, 402], [497, 403], [497, 404], [498, 405], [497, 406], [496, 406], [495, 407], [494, 406],
+           [495, 407], [496, 406], [497, 407], [500, 407], [501, 406], [500, 405], [500, 404], [501, 403],
+           [500, 404], [500, 405], [499, 406], [497, 404], [497, 403]]
+    c = np.array(pts, np.int32).reshape(-1, 1, 2)
+    hull_cv = cv2.convexHull(c).reshape(-1, 2)
+    hull_dev = cp.hull_like_cv(c.reshape(-1, 2))
+    assert hull_cv.tolist() == [[501, 406], [500, 407], [495, 407], [494, 406], [496, 402], [501, 403]]
+    assert np.array_equal(np.roll(hull_cv, 1, axis=0), hull_dev)          # same polygon, other start
+    # the exact restatement of OpenCV's convexHull (contour positions of the hull vertices
+    # 12, 11, 6, 7, 0, 15: 6 < 7, not a rotation of a descending sequence -> no cyclic shift)
+    assert np.array_equal(cp.convex_hull_cv(c.reshape(-1, 2)), hull_cv)
+    r_cv = cv2.minAreaRect(c)
+    r_dev = cp.min_area_rect_cv(hull_dev)
+    assert r_cv == ((497.5, 404.5), (5.0, 7.0), -90.0)
+    assert r_dev != r_cv and abs(r_dev[2] + 78.69007) < 1e-4
+    assert abs(r_dev[1][0] * r_dev[1][1] - 35.0) < 1e-4                   # the tie
+    # started where OpenCV starts, the same calipers give OpenCV's rectangle
+    assert cp.min_area_rect_cv(hull_cv) == r_cv
 
 
 def test_contour_known_answers(kat):
