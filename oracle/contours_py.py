@@ -350,6 +350,70 @@ def convex_hull_cv(contour_pts: np.ndarray) -> np.ndarray:
     return np.array([pts[k] for k in hull], dtype=np.int64)
 
 
+def _cv_shift_start(pos: List[int]) -> int:
+    """OpenCV's cyclic-shift test on the contour positions of the hull vertices (natural order):
+    index the output starts at (0: no shift)."""
+    nout = len(pos)
+    if nout < 3:
+        return 0
+    min_i = max_i = lt = 0
+    for i in range(1, nout):
+        lt += pos[i - 1] < pos[i]
+        if 1 < lt <= i - 2:
+            break
+        if pos[i] < pos[min_i]:
+            min_i = i
+        if pos[i] > pos[max_i]:
+            max_i = i
+    mmdist = abs(max_i - min_i)
+    if (mmdist == 1 or mmdist == nout - 1) and (lt <= 1 or lt >= nout - 2):
+        ascending = (max_i + 1) % nout == min_i
+        i0 = min_i if ascending else max_i
+        if i0 > 0:
+            rot = pos[i0:] + pos[:i0]
+            if all(ascending == (rot[i] < rot[i + 1]) for i in range(nout - 1)):
+                return i0
+    return 0
+
+
+def hull_order_from_visits(contour_pts: np.ndarray) -> np.ndarray:
+    """The same order as ``convex_hull_cv`` from what a border trace can carry along: the strict
+    hull and, per hull vertex, the position of its FIRST and of its LAST visit in the
+    CHAIN_APPROX_SIMPLE point list (the closed form of what OpenCV's sort + Sklansky walks do to a
+    vertex the border passes more than once; the specification of the open device fix, DESIGN.md
+    section 4).  Natural order: clockwise on screen from the (x, y)-largest vertex.  Position of a
+    vertex: last visit for the (x, y)-largest vertex and for the inner vertices of the two LEFT
+    chains (top -> (x, y)-smallest -> bottom); first visit for everything else (the (x, y)-smallest
+    vertex, top = (max y, min x), bottom = (min y, min x), the right chains).  Then OpenCV's shift
+    test.  Hulls of fewer than three vertices: as ``hull_like_cv``."""
+    pts = [(int(x), int(y)) for x, y in np.asarray(contour_pts).reshape(-1, 2)]
+    cyc = [tuple(int(v) for v in q) for q in hull_like_cv(np.asarray(pts))]
+    n = len(cyc)
+    if n < 3:
+        return np.array(cyc, dtype=np.int64).reshape(-1, 2)
+    first, last = {}, {}
+    for i, q in enumerate(pts):
+        first.setdefault(q, i)
+        last[q] = i
+    k = cyc.index(max(cyc))
+    nat = cyc[k:] + cyc[:k]
+    ymax, ymin = max(q[1] for q in nat), min(q[1] for q in nat)
+    top = min(q for q in nat if q[1] == ymax)
+    bot = min(q for q in nat if q[1] == ymin)
+    it, im, ib = nat.index(top), nat.index(min(nat)), nat.index(bot)
+    if im < it:
+        im += n
+    if ib < im:
+        ib += n
+    pos = []
+    for j, q in enumerate(nat):
+        left_inner = any(it < jj < im or im < jj < ib for jj in (j, j + n))
+        use_last = j == 0 or (left_inner and q not in (top, bot, min(nat)))
+        pos.append(last[q] if use_last else first[q])
+    s0 = _cv_shift_start(pos)
+    return np.array(nat[s0:] + nat[:s0], dtype=np.int64)
+
+
 def hull_like_cv(contour_pts: np.ndarray) -> np.ndarray:
     """THE DEVICE'S RULE (csrc/contour_common.cuh::Hull): hull of a traced external contour
     clockwise on screen, cyclically shifted so that the contour's start pixel (raster-first

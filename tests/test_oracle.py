@@ -146,6 +146,8 @@ def test_min_area_rect_restatement_is_bit_exact():
             rr = cp.min_area_rect_cv(hull)
             assert rr == ((r[0][0], r[0][1]), (r[1][0], r[1][1]), r[2])
             assert np.array_equal(cp.box_points_cv(rr), cv2.boxPoints(r))
+            if len(hull) >= 3:        # the closed form a border trace can carry (first / last visits)
+                assert np.array_equal(cp.hull_order_from_visits(c.reshape(-1, 2)), hull)
             simple = len({tuple(q) for q in c.reshape(-1, 2).tolist()}) == len(c)
             same = np.array_equal(cp.hull_like_cv(c.reshape(-1, 2)), hull)
             assert same or not simple or len(hull) <= 2      # the device's rule: every simple contour
@@ -187,6 +189,7 @@ def test_known_deviation_hull_start_of_a_non_simple_contour():
     assert abs(r_dev[1][0] * r_dev[1][1] - 35.0) < 1e-4                   # the tie
     # started where OpenCV starts, the same calipers give OpenCV's rectangle
     assert cp.min_area_rect_cv(hull_cv) == r_cv
+    assert np.array_equal(cp.hull_order_from_visits(c.reshape(-1, 2)), hull_cv)
 
 
 def test_contour_known_answers(kat):

@@ -58,7 +58,12 @@ for case in range(n_cases):
         scale[:, FC[name]] = np.maximum(scale[:, FC[name]], m00[:, FC[name]] ** 2.5 * 1e-6)
     scale[:, FC["mu11"]] = np.maximum(scale[:, FC["mu11"]], 1e-6 * m00[:, FC["mu11"]] ** 2)
     scale[:, FC["ell_theta"]] = np.maximum(scale[:, FC["ell_theta"]], 1e-6)
-    tot["float_over_1e5"] += int((np.abs(a - b)[ok] > 1e-5 * scale[ok] + 1e-300).sum())
+    over = ok & (np.abs(a - b) > 1e-5 * scale + 1e-300)
+    tot["float_over_1e5"] += int(over.sum())
+    for r_, c_ in zip(*np.nonzero(over)):          # which cells: (case, row, column, device, oracle)
+        if len(tot.setdefault("float_over_cells", [])) < 40:
+            tot["float_over_cells"].append([case, int(r_), schema.FLOAT_COLUMNS[c_] if hasattr(schema, "FLOAT_COLUMNS")
+                                            else int(c_), float(a[r_, c_]), float(b[r_, c_])])
     # planes against the oracle's pasted masks
     res = d2.detector_postprocess(P.to_oracle_instances(inst), H, W, 0.5)
     om = res.pred_masks.numpy()
